@@ -1,0 +1,159 @@
+/* ps_b200.h -- C ABI of the B200-native consecutive-partitions dynamic-programming engine.
+ *
+ * This is the drop-in boundary for ONE path of pehlivanian/PartitionSolvers: everything the
+ * constructor of `DPSolver<DataType>` does (reference: src/cpp/include/DP.hpp:43-149,194-197 ->
+ * DP_impl.hpp:69-230, score_impl.hpp:233-285).  The reference has no FFI of its own; its hot path
+ * is a C++ class template.  The host facade in include/partitionsolvers/DP.hpp keeps that class
+ * (same constructors and getters) and calls ONLY the functions declared here.  INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints.  No C++ or torch types cross this boundary.
+ *   - the caller owns every buffer it passes; the library owns its device workspaces (inside ps_ctx).
+ *   - errors are return codes (ps_status); nothing throws across the ABI.
+ *   - a ps_ctx may be used by one host thread at a time; any number of contexts may run concurrently
+ *     (the reference constructs solvers from pool threads: python_dpsolver.cpp:275-301).  CUDA is
+ *     initialised lazily inside ps_create, never at load time, so fork()ed workers are safe
+ *     (solverSWIG_DP.py:152-167).
+ *   - there is no CPU fallback: without a usable CUDA device ps_create fails with PS_ERR_NODEVICE.
+ */
+#ifndef PS_B200_H
+#define PS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_B200_ABI_VERSION 1
+
+typedef enum ps_status {
+  PS_OK = 0,
+  PS_ERR_INVALID = 1,     /* bad argument (n<1, T<1, NULL input, unknown enum value ...)            */
+  PS_ERR_DIST = 2,        /* parametric_dist outside {0,1,2}: the facade maps this to                */
+                          /* distributionException (reference LTSS.hpp:21-25, DP_impl.hpp:62-64)      */
+  PS_ERR_CUDA = 3,        /* a CUDA runtime call failed; ps_last_error(ctx) has the text              */
+  PS_ERR_NOMEM = 4,       /* device or host allocation failed                                         */
+  PS_ERR_NODEVICE = 5,    /* no CUDA device / driver: there is deliberately no CPU path               */
+  PS_ERR_UNSUPPORTED = 6
+} ps_status;
+
+/* objective_fn of the reference (score.hpp:20-22) */
+enum { PS_DIST_GAUSSIAN = 0, PS_DIST_POISSON = 1, PS_DIST_RATIONAL = 2 };
+
+/* How range sums Sigma a, Sigma b over [i,k) are formed.
+ * RUNNING reproduces the reference's rounding exactly: sums are accumulated left to right starting
+ * at i (score_impl.hpp:248-256).  PREFIX forms them as differences of a device prefix scan
+ * (bit-identical to RUNNING whenever all partial sums are exactly representable, e.g. counts). */
+enum { PS_SUM_RUNNING = 0, PS_SUM_PREFIX = 1 };
+
+/* Priority sort (DP_impl.hpp:7-28).  DEVICE = stable LSD radix sort of a[i]/b[i] on the GPU (ties
+ * keep input order).  GIVEN = the caller supplies the permutation (e.g. std::sort's, whose order on
+ * tied priorities is implementation-defined and cannot be reproduced by any other algorithm). */
+enum { PS_SORT_DEVICE = 0, PS_SORT_GIVEN = 1 };
+
+typedef struct ps_ctx ps_ctx; /* opaque: device, stream, workspaces, timing events */
+
+typedef struct ps_problem {
+  int n;           /* ground-set size; a and b hold n values per instance                            */
+  int T;           /* subsets requested; capped at n like DP_impl.hpp:37-38                          */
+  int dist;        /* PS_DIST_*                                                                       */
+  int risk_part;   /* risk_partitioning_objective (0 = multiple clustering)                           */
+  int sum_mode;    /* PS_SUM_*                                                                        */
+  int sort_mode;   /* PS_SORT_*                                                                       */
+  const int* perm; /* PS_SORT_GIVEN: [batch][n] permutation, position -> original index              */
+  int sweep;       /* 0: backtrace S=T only (DP_impl.hpp:226-228); 1: every S=T..1 (:203-214)         */
+  int batch;       /* independent instances R>=1 (replicas); a,b are [R][n] row-major                 */
+  int on_device;   /* 1: a, b, perm AND every ps_result pointer are device pointers on ctx's device   */
+  int tile_rows;   /* tuning, 0 = default                                                             */
+  int chunk_len;   /* tuning, 0 = default                                                             */
+} ps_problem;
+
+/* Caller-allocated outputs; any pointer may be NULL (= not wanted).  D = float or double.
+ * Let Tc = min(T, n).
+ *   perm          [R][n]          priority_sortind_: sorted position -> original index
+ *   bounds        sweep=0: [R][Tc+1]          0 = b_0 < b_1 < ... < b_Tc = n  (subset t = positions
+ *                 sweep=1: [R][Tc+1][Tc+1]    [b_t, b_{t+1}) of the sorted order); row S of the sweep
+ *                                             table holds the S+1 boundaries of the S-partition
+ *   subset_scores sweep=0: [R][Tc]            S(b_t, b_{t+1}) in backtrace order, BEFORE the
+ *                 sweep=1: [R][Tc+1][Tc]      mult-clust reorder (the facade applies DP_impl.hpp:232-259)
+ *   max_score     [R][Tc+1][n]    maxScore_  rows 0..Tc  (unwritten cells = lowest(), like the reference)
+ *   next_start    [R][Tc+1][n]    nextStart_ rows 0..Tc  (unwritten cells = -1)
+ */
+typedef struct ps_result {
+  int* perm;
+  int* bounds;
+  void* subset_scores;
+  void* max_score;
+  int* next_start;
+} ps_result;
+
+#define PS_MAX_TIMED_LEVELS 130
+typedef struct ps_timings {
+  float total_ms;       /* whole call on the context's stream (CUDA events)                           */
+  float h2d_ms;
+  float sort_scan_ms;   /* keys + radix sort + gather + scan / record build                           */
+  float prepass_ms;     /* level 1 (+ chunk-start sums in RUNNING mode)                               */
+  float levels_ms;      /* sum over levels 2..T of tile kernel + combine                              */
+  float backtrace_ms;
+  float d2h_ms;
+  int n_levels;                           /* number of level launches timed                          */
+  float level_ms[PS_MAX_TIMED_LEVELS];    /* tile kernel only, per level j = 2.. (index j-2)         */
+  long long level_cells[PS_MAX_TIMED_LEVELS]; /* (i,k) cells evaluated by that launch, all instances  */
+  long long kernel_launches;              /* kernels launched by the call                            */
+  long long h2d_bytes, d2h_bytes;
+} ps_timings;
+
+int ps_abi_version(void);
+const char* ps_status_string(ps_status s);
+
+/* device < 0 selects the current CUDA device.  Creates a non-blocking stream. */
+ps_status ps_create(ps_ctx** out, int device);
+void ps_destroy(ps_ctx* ctx);
+const char* ps_last_error(const ps_ctx* ctx);
+int ps_device(const ps_ctx* ctx);
+/* cudaStream_t of the context, as an integer (for callers that order their own work after ours) */
+uintptr_t ps_stream(const ps_ctx* ctx);
+
+/* One call = the whole constructor of DPSolver<D>: sort_by_priority, range scores, the T-level DP
+ * fill and the backtrace(s) (DP_impl.hpp:69-153,200-230).  Blocking. */
+ps_status ps_solve_f32(ps_ctx* ctx, const ps_problem* p, const float* a, const float* b, ps_result* r);
+ps_status ps_solve_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, ps_result* r);
+
+/* Timings of the most recent ps_solve_* on this context. */
+ps_status ps_get_timings(const ps_ctx* ctx, ps_timings* out);
+
+/* S(0,n) of the inputs as given, no sort: `compute_score` (python_dpsolver.cpp:74-111). */
+ps_status ps_range_score_f32(ps_ctx* ctx, int n, const float* a, const float* b, int dist, int risk_part,
+                             float* out);
+ps_status ps_range_score_f64(ps_ctx* ctx, int n, const double* a, const double* b, int dist, int risk_part,
+                             double* out);
+
+/* ---- row-sharded single instance: building blocks driven by a multi-process host ----
+ * Rank `rank` of `world` owns row blocks rb with rb % world == rank.  The caller (one process per GPU)
+ * holds the level vector, calls ps_shard_level_* for its rows, and exchanges the level vector with an
+ * all-gather of its own (torch.distributed / NCCL).  All pointers are DEVICE pointers.            */
+typedef struct ps_shard ps_shard; /* opaque per-rank state */
+ps_status ps_shard_create_f64(ps_ctx* ctx, const ps_problem* p, const double* a_sorted_dev,
+                              const double* b_sorted_dev, int rank, int world, ps_shard** out);
+ps_status ps_shard_create_f32(ps_ctx* ctx, const ps_problem* p, const float* a_sorted_dev,
+                              const float* b_sorted_dev, int rank, int world, ps_shard** out);
+/* rows owned by this rank at any level, padded: the all-gather chunk length (same on every rank) */
+int ps_shard_chunk_rows(const ps_shard* s);
+/* level 1: writes this rank's chunk of maxScore_[1] (owned rows, block-cyclic order) */
+ps_status ps_shard_level1(ps_shard* s, void* my_chunk_dev);
+/* gathered [world][chunk] -> natural order level vector inside the shard state */
+ps_status ps_shard_set_prev(ps_shard* s, const void* gathered_dev);
+/* level j>=2: computes owned rows from the previous level vector; writes value chunk and keeps splits */
+ps_status ps_shard_level(ps_shard* s, int j, void* my_chunk_dev);
+/* split index next_start[j][i] (host lookup of one element; valid on the owning rank, else -2) */
+ps_status ps_shard_next_start(ps_shard* s, int j, int i, int* out);
+int ps_shard_owner(const ps_shard* s, int i);
+void ps_shard_destroy(ps_shard* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PS_B200_H */

@@ -1,0 +1,203 @@
+"""ctypes binding of the C ABI in include/ps_b200.h (libps_b200.so).
+
+This module is plumbing for tests and bench.py: it loads the in-tree CUDA library, mirrors the ABI
+structs, and exposes :class:`Context`.  There is no fallback: if the library is missing or no CUDA
+device is usable, it raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libps_b200.so")
+
+PS_OK = 0
+PS_ERR_DIST = 2
+PS_ERR_NODEVICE = 5
+PS_SUM_RUNNING, PS_SUM_PREFIX = 0, 1
+PS_SORT_DEVICE, PS_SORT_GIVEN = 0, 1
+PS_MAX_TIMED_LEVELS = 130
+
+# every symbol include/ps_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+ABI_SYMBOLS = [
+    "ps_abi_version", "ps_status_string", "ps_create", "ps_destroy", "ps_last_error", "ps_device",
+    "ps_stream", "ps_solve_f32", "ps_solve_f64", "ps_get_timings", "ps_range_score_f32",
+    "ps_range_score_f64", "ps_shard_create_f64", "ps_shard_create_f32", "ps_shard_chunk_rows",
+    "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",
+    "ps_shard_destroy",
+]
+
+
+class PsProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("T", C.c_int), ("dist", C.c_int), ("risk_part", C.c_int),
+                ("sum_mode", C.c_int), ("sort_mode", C.c_int), ("perm", C.c_void_p), ("sweep", C.c_int),
+                ("batch", C.c_int), ("on_device", C.c_int), ("tile_rows", C.c_int), ("chunk_len", C.c_int)]
+
+
+class PsResult(C.Structure):
+    _fields_ = [("perm", C.c_void_p), ("bounds", C.c_void_p), ("subset_scores", C.c_void_p),
+                ("max_score", C.c_void_p), ("next_start", C.c_void_p)]
+
+
+class PsTimings(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("sort_scan_ms", C.c_float),
+                ("prepass_ms", C.c_float), ("levels_ms", C.c_float), ("backtrace_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("n_levels", C.c_int), ("level_ms", C.c_float * PS_MAX_TIMED_LEVELS),
+                ("level_cells", C.c_longlong * PS_MAX_TIMED_LEVELS), ("kernel_launches", C.c_longlong),
+                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+
+
+class PsError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"ps_b200 status {status}: {msg}")
+        self.status = status
+
+
+class DistributionError(PsError):
+    """PS_ERR_DIST: the reference throws distributionException here (LTSS.hpp:21-25)."""
+
+
+_lib = None
+
+
+def load():
+    """Load libps_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.ps_status_string.restype = C.c_char_p
+        L.ps_last_error.restype = C.c_char_p
+        L.ps_last_error.argtypes = [C.c_void_p]
+        L.ps_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.ps_destroy.argtypes = [C.c_void_p]
+        L.ps_destroy.restype = None
+        L.ps_device.argtypes = [C.c_void_p]
+        L.ps_stream.argtypes = [C.c_void_p]
+        L.ps_stream.restype = C.c_size_t
+        for nm in ("ps_solve_f32", "ps_solve_f64"):
+            getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(PsProblem), C.c_void_p, C.c_void_p,
+                                       C.POINTER(PsResult)]
+        L.ps_get_timings.argtypes = [C.c_void_p, C.POINTER(PsTimings)]
+        for nm in ("ps_range_score_f32", "ps_range_score_f64"):
+            getattr(L, nm).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_void_p]
+        for nm in ("ps_shard_create_f32", "ps_shard_create_f64"):
+            getattr(L, nm).argtypes = [C.c_void_p, C.POINTER(PsProblem), C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_int, C.POINTER(C.c_void_p)]
+        L.ps_shard_chunk_rows.argtypes = [C.c_void_p]
+        L.ps_shard_level1.argtypes = [C.c_void_p, C.c_void_p]
+        L.ps_shard_set_prev.argtypes = [C.c_void_p, C.c_void_p]
+        L.ps_shard_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ps_shard_next_start.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.ps_shard_owner.argtypes = [C.c_void_p, C.c_int]
+        L.ps_shard_destroy.argtypes = [C.c_void_p]
+        L.ps_shard_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _vp(arr):
+    return arr.ctypes.data_as(C.c_void_p) if arr is not None else None
+
+
+class Context:
+    """One ps_ctx: a device, a stream and grow-only workspaces.  Use from one thread at a time."""
+
+    def __init__(self, device=-1):
+        self.lib = load()
+        self._h = C.c_void_p()
+        st = self.lib.ps_create(C.byref(self._h), int(device))
+        if st != PS_OK:
+            raise PsError(st, self.lib.ps_status_string(st).decode())
+
+    def close(self):
+        if self._h:
+            self.lib.ps_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != PS_OK:
+            msg = self.lib.ps_last_error(self._h).decode() or self.lib.ps_status_string(st).decode()
+            raise (DistributionError if st == PS_ERR_DIST else PsError)(st, msg)
+
+    @property
+    def device(self):
+        return self.lib.ps_device(self._h)
+
+    @property
+    def stream(self):
+        return self.lib.ps_stream(self._h)
+
+    def timings(self):
+        t = PsTimings()
+        self._check(self.lib.ps_get_timings(self._h, C.byref(t)))
+        nl = t.n_levels
+        return dict(total_ms=t.total_ms, h2d_ms=t.h2d_ms, sort_scan_ms=t.sort_scan_ms,
+                    prepass_ms=t.prepass_ms, levels_ms=t.levels_ms, backtrace_ms=t.backtrace_ms,
+                    d2h_ms=t.d2h_ms, level_ms=[t.level_ms[i] for i in range(nl)],
+                    level_cells=[t.level_cells[i] for i in range(nl)],
+                    kernel_launches=t.kernel_launches, h2d_bytes=t.h2d_bytes, d2h_bytes=t.d2h_bytes)
+
+    def solve_raw(self, a, b, T, dist, risk_part, dtype=np.float32, sum_mode=PS_SUM_RUNNING, perm=None,
+                  sweep=False, levels=False, chunk_len=0, want_perm=True):
+        """Host-buffer call.  a, b: [n] or [R, n].  Returns the raw ABI outputs as numpy arrays."""
+        a = np.ascontiguousarray(a, dtype=dtype)
+        b = np.ascontiguousarray(b, dtype=dtype)
+        assert a.shape == b.shape
+        batched = a.ndim == 2
+        R = a.shape[0] if batched else 1
+        n = a.shape[-1]
+        Tc = min(T, n)
+        nS = Tc + 1 if sweep else 1
+        p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode,
+                      sort_mode=PS_SORT_GIVEN if perm is not None else PS_SORT_DEVICE, perm=None,
+                      sweep=int(sweep), batch=R, on_device=0, tile_rows=0, chunk_len=chunk_len)
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, dtype=np.int32).reshape(R, n)
+            p.perm = perm.ctypes.data
+        out_perm = np.empty((R, n), np.int32) if want_perm else None
+        bounds = np.empty((R, nS, Tc + 1), np.int32)
+        sscores = np.empty((R, nS, Tc), dtype)
+        ms = np.empty((R, Tc + 1, n), dtype) if levels else None
+        ns = np.empty((R, Tc + 1, n), np.int32) if levels else None
+        r = PsResult(perm=_vp(out_perm), bounds=_vp(bounds), subset_scores=_vp(sscores), max_score=_vp(ms),
+                     next_start=_vp(ns))
+        fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
+        self._check(fn(self._h, C.byref(p), _vp(a), _vp(b), C.byref(r)))
+        out = dict(n=n, T=Tc, R=R, perm=out_perm, bounds=bounds, subset_scores=sscores, max_score=ms,
+                   next_start=ns)
+        if not batched:
+            for k in ("perm", "bounds", "subset_scores", "max_score", "next_start"):
+                if out[k] is not None:
+                    out[k] = out[k][0]
+        return out
+
+    def solve_device(self, d_a, d_b, n, T, dist, risk_part, dtype, R=1, sum_mode=PS_SUM_RUNNING, sweep=False,
+                     d_perm_out=0, d_bounds=0, d_scores=0, d_perm_in=0, chunk_len=0):
+        """Device-pointer call (inputs resident in HBM; integers are raw device addresses)."""
+        p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode,
+                      sort_mode=PS_SORT_GIVEN if d_perm_in else PS_SORT_DEVICE, perm=d_perm_in or None,
+                      sweep=int(sweep), batch=R, on_device=1, tile_rows=0, chunk_len=chunk_len)
+        r = PsResult(perm=d_perm_out or None, bounds=d_bounds or None, subset_scores=d_scores or None,
+                     max_score=None, next_start=None)
+        fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
+        self._check(fn(self._h, C.byref(p), C.c_void_p(d_a), C.c_void_p(d_b), C.byref(r)))
+
+    def range_score(self, a, b, dist, risk_part, dtype=np.float32):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        b = np.ascontiguousarray(b, dtype=dtype)
+        out = np.zeros(1, dtype)
+        fn = self.lib.ps_range_score_f32 if dtype == np.float32 else self.lib.ps_range_score_f64
+        self._check(fn(self._h, a.shape[0], _vp(a), _vp(b), dist, int(risk_part), _vp(out)))
+        return out[0]

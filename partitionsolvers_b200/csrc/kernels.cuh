@@ -1,0 +1,549 @@
+// kernels.cuh -- device side of the consecutive-partitions DP for sm_100a.
+//
+// Data layout in HBM (per instance; instances of a batch are strided copies):
+//   rec[2][n+1]   level records {x, y, p, -}: one 16 B (float) / 32 B (double) record per k so that a
+//                 k-step of the inner loop is ONE broadcast shared-memory load.  x,y are constant
+//                 across levels (RUNNING: a[k-1], b[k-1];  PREFIX: scan values Pa[k], Pb[k]);
+//                 p = maxScore_[j-1][k] is rewritten by every level into the other buffer.
+//   SA,SB[NCH][n] RUNNING mode only: sums over [i, c*L) for every chunk boundary c*L > i, produced by
+//                 the level-1 pass; lets any (row block, k-chunk) tile start mid-row while keeping the
+//                 reference's left-to-right summation order (score_impl.hpp:248-256).
+//   part[NCH][n]  per-chunk (best value, argmax k) of the level in flight.
+//   ms, ns[T+1][n]  maxScore_ / nextStart_ (DP.hpp:162-163); ns drives the backtrace.
+//
+// Work decomposition of one level (DP_impl.hpp:101-118, the O(n^2) part): the upper-triangular
+// (i,k) space is cut into tiles of BR rows x L columns.  One CTA = one tile, one thread = one row;
+// the k loop streams records through a double-buffered shared-memory stage, so the three per-k
+// operands are loaded from L2 once per CTA and broadcast to all rows.  Tiles are enumerated far from
+// the diagonal first so the half-empty diagonal tiles fill the tail of the launch.  A second, tiny
+// kernel folds the per-chunk partials in ascending k, which preserves the reference's
+// "first maximum wins" rule (strict >, DP_impl.hpp:107).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "score.cuh"
+
+namespace ps {
+
+template <typename D>
+struct Rec4;
+template <>
+struct __align__(16) Rec4<float> {
+  float x, y, p, w;
+};
+template <>
+struct __align__(32) Rec4<double> {
+  double x, y, p, w;
+};
+
+struct Geom {
+  int n;        // ground-set size
+  int nrows;    // rows computed at this level
+  int kmax;     // largest k considered (n - j + 1)
+  int L;        // k-chunk length, multiple of BR
+  int NCH;      // chunks covering 1..kmax
+  int G;        // L / BR
+  int NRB;      // row blocks covering nrows
+  int ntiles;
+  int nch_alloc;          // chunk stride of part/SA arrays
+  long long rec_stride;   // records per instance (n+1)
+  // row sharding (single huge instance over several GPUs): this rank owns row blocks
+  // rb_first + rb_step * m, m = 0..NRB-1 (NRB counts OWNED blocks).  Unsharded: 0, 1.
+  int rb_first, rb_step;
+};
+
+__host__ __device__ inline int geom_count_tiles(int NRB_total_hint, int NCH, int G, int NRB, int rb_first,
+                                                int rb_step) {
+  (void)NRB_total_hint;
+  // number of owned row blocks whose diagonal chunk s satisfies s + d <= NCH-1, summed over d
+  long long t = 0;
+  for (int d = 0; d < NCH; ++d) {
+    long long lim = (long long)(NCH - d) * G;  // global row blocks rb < lim
+    // owned blocks: rb = rb_first + rb_step*m < lim
+    long long m = lim > rb_first ? (lim - rb_first + rb_step - 1) / rb_step : 0;
+    if (m > NRB) m = NRB;
+    t += m;
+  }
+  return (int)t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One (row block, k-chunk) tile of one level.
+// ---------------------------------------------------------------------------------------------
+template <typename D, int DIST, bool RP, bool RUNNING, int BR>
+__global__ void __launch_bounds__(BR)
+level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__ SA,
+                  const D* __restrict__ SB, D* __restrict__ part_val, int* __restrict__ part_arg) {
+  constexpr int BK = BR;
+  __shared__ Rec4<D> sbuf[2][BK];
+
+  const int inst = blockIdx.y;
+  rec += (long long)inst * g.rec_stride;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  part_val += inst * pstride;
+  part_arg += inst * pstride;
+  if (RUNNING) {
+    SA += inst * pstride;
+    SB += inst * pstride;
+  }
+
+  // ---- tile decode: distance from the diagonal d = NCH-1 .. 0, then owned row block m
+  int t = blockIdx.x;
+  int d = g.NCH - 1;
+  for (;;) {
+    long long lim = (long long)(g.NCH - d) * g.G;
+    long long cnt = lim > g.rb_first ? (lim - g.rb_first + g.rb_step - 1) / g.rb_step : 0;
+    if (cnt > g.NRB) cnt = g.NRB;
+    if (t < cnt) break;
+    t -= (int)cnt;
+    --d;
+  }
+  const int rb = g.rb_first + g.rb_step * t;
+  const int c = rb / g.G + d;
+
+  const int tid = threadIdx.x;
+  const int i0 = rb * BR;
+  const int i = i0 + tid;
+  const int k_lo = max(c * g.L + 1, i0 + 1);
+  const int k_hi = min((c + 1) * g.L, g.kmax);
+  const bool diag = (c == rb / g.G);
+
+  D A = 0, B = 0, Xi = 0, Yi = 0;
+  {
+    const int il = min(i, g.n - 1);
+    if (RUNNING) {
+      if (!diag) {
+        A = SA[(long long)c * g.n + il];
+        B = SB[(long long)c * g.n + il];
+      }
+    } else {
+      Xi = rec[il].x;
+      Yi = rec[il].y;
+    }
+  }
+  D best = Lim<D>::lowest();
+  int arg = -1;
+
+  const int nk = k_hi - k_lo + 1;
+  const int nstages = (nk + BK - 1) / BK;
+  {
+    int k = k_lo + tid;
+    Rec4<D> r;
+    r.x = r.y = r.p = r.w = 0;
+    if (k <= k_hi) r = rec[k];
+    sbuf[0][tid] = r;
+  }
+  for (int s = 0; s < nstages; ++s) {
+    __syncthreads();
+    const int kb = k_lo + s * BK;
+    const int kn = kb + BK + tid;
+    Rec4<D> nx;
+    nx.x = nx.y = nx.p = nx.w = 0;
+    const bool has_next = (s + 1 < nstages);
+    if (has_next && kn <= k_hi) nx = rec[kn];
+    const int cnt = min(BK, k_hi - kb + 1);
+    const Rec4<D>* __restrict__ sb = sbuf[s & 1];
+    if (kb > i0 + BR - 1) {
+      // interior: every row of the block sees every k of the stage
+      if (cnt == BK) {
+#pragma unroll 4
+        for (int kk = 0; kk < BK; ++kk) {
+          const Rec4<D> r = sb[kk];
+          if (RUNNING) {
+            A = add_rn<D>(A, r.x);
+            B = add_rn<D>(B, r.y);
+          } else {
+            A = sub_rn<D>(r.x, Xi);
+            B = sub_rn<D>(r.y, Yi);
+          }
+          const D v = add_rn<D>(ScoreFn<D, DIST, RP>::eval(A, B), r.p);
+          if (v > best) {
+            best = v;
+            arg = kb + kk;
+          }
+        }
+      } else {
+        for (int kk = 0; kk < cnt; ++kk) {
+          const Rec4<D> r = sb[kk];
+          if (RUNNING) {
+            A = add_rn<D>(A, r.x);
+            B = add_rn<D>(B, r.y);
+          } else {
+            A = sub_rn<D>(r.x, Xi);
+            B = sub_rn<D>(r.y, Yi);
+          }
+          const D v = add_rn<D>(ScoreFn<D, DIST, RP>::eval(A, B), r.p);
+          if (v > best) {
+            best = v;
+            arg = kb + kk;
+          }
+        }
+      }
+    } else {
+      // diagonal stage: row i only sees k > i
+      for (int kk = 0; kk < cnt; ++kk) {
+        const int k = kb + kk;
+        const Rec4<D> r = sb[kk];
+        if (k > i) {
+          if (RUNNING) {
+            A = add_rn<D>(A, r.x);
+            B = add_rn<D>(B, r.y);
+          } else {
+            A = sub_rn<D>(r.x, Xi);
+            B = sub_rn<D>(r.y, Yi);
+          }
+          const D v = add_rn<D>(ScoreFn<D, DIST, RP>::eval(A, B), r.p);
+          if (v > best) {
+            best = v;
+            arg = k;
+          }
+        }
+      }
+    }
+    if (has_next) sbuf[(s + 1) & 1][tid] = nx;
+  }
+  if (i < g.nrows) {
+    part_val[(long long)c * g.n + i] = best;
+    part_arg[(long long)c * g.n + i] = arg;
+  }
+}
+
+// Fold the per-chunk partials of row i in ascending chunk order (= ascending k): strict > keeps the
+// first maximum, exactly like the reference's scan over k.  Writes maxScore_[j][i], nextStart_[j][i]
+// and the p field of the NEXT level's records.  Sharded runs also emit the value in block-cyclic
+// "chunk" order for the all-gather.
+template <typename D, int BR>
+__global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int* __restrict__ part_arg,
+                               D* __restrict__ ms_row, int* __restrict__ ns_row, long long table_stride,
+                               Rec4<D>* __restrict__ rec_next, D* __restrict__ shard_chunk) {
+  const int inst = blockIdx.y;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  part_val += inst * pstride;
+  part_arg += inst * pstride;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;  // index among owned rows
+  if (m >= g.NRB * BR) return;
+  const int rb = g.rb_first + g.rb_step * (m / BR);
+  const int i = rb * BR + (m % BR);
+  D best = Lim<D>::lowest();
+  int arg = -1;
+  if (i < g.nrows) {
+    for (int c = i / g.L; c < g.NCH; ++c) {
+      const D v = part_val[(long long)c * g.n + i];
+      if (v > best) {
+        best = v;
+        arg = part_arg[(long long)c * g.n + i];
+      }
+    }
+    if (ms_row) ms_row[inst * table_stride + i] = best;
+    if (ns_row) ns_row[inst * table_stride + i] = arg;
+    if (rec_next) rec_next[inst * g.rec_stride + i].p = best;
+  }
+  if (shard_chunk) shard_chunk[m] = best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level 1 (DP_impl.hpp:90-95): maxScore_[1][i] = S(i,n), nextStart_[1][i] = n.
+// RUNNING: one thread per row walks k = i+1..n accumulating the sums the way the reference does and
+// drops the running sums at every chunk boundary into SA/SB.  2 adds per cell, once per solve.
+// ---------------------------------------------------------------------------------------------
+template <typename D, int BR>
+__global__ void __launch_bounds__(BR)
+level1_running_kernel(int n, int L, int nch_alloc, long long rec_stride, int dist, int rp,
+                      const Rec4<D>* __restrict__ rec, D* __restrict__ SA, D* __restrict__ SB,
+                      D* __restrict__ ms1, int* __restrict__ ns1, long long table_stride,
+                      Rec4<D>* __restrict__ rec_next, int rb_first, int rb_step, D* __restrict__ shard_chunk) {
+  constexpr int BK = BR;
+  __shared__ Rec4<D> sbuf[2][BK];
+  const int inst = blockIdx.y;
+  rec += (long long)inst * rec_stride;
+  const long long pstride = (long long)nch_alloc * n;
+  const int rb = rb_first + rb_step * blockIdx.x;
+  const int tid = threadIdx.x;
+  const int i0 = rb * BR;
+  const int i = i0 + tid;
+  D A = 0, B = 0;
+  if (i0 < n) {
+    const int k_lo = i0 + 1, k_hi = n;
+    const int nstages = (k_hi - k_lo + 1 + BK - 1) / BK;
+    {
+      int k = k_lo + tid;
+      Rec4<D> r;
+      r.x = r.y = r.p = r.w = 0;
+      if (k <= k_hi) r = rec[k];
+      sbuf[0][tid] = r;
+    }
+    for (int s = 0; s < nstages; ++s) {
+      __syncthreads();
+      const int kb = k_lo + s * BK;
+      const int kn = kb + BK + tid;
+      Rec4<D> nx;
+      nx.x = nx.y = nx.p = nx.w = 0;
+      const bool has_next = (s + 1 < nstages);
+      if (has_next && kn <= k_hi) nx = rec[kn];
+      const int cnt = min(BK, k_hi - kb + 1);
+      const Rec4<D>* __restrict__ sb = sbuf[s & 1];
+      if (s == 0) {
+        for (int kk = 0; kk < cnt; ++kk) {
+          if (kb + kk > i) {
+            A = add_rn<D>(A, sb[kk].x);
+            B = add_rn<D>(B, sb[kk].y);
+          }
+        }
+      } else {
+#pragma unroll 8
+        for (int kk = 0; kk < cnt; ++kk) {
+          A = add_rn<D>(A, sb[kk].x);
+          B = add_rn<D>(B, sb[kk].y);
+        }
+      }
+      const int kend = kb + cnt - 1;  // last k of the stage
+      if (cnt == BK && (kend % L) == 0 && i < n && SA) {
+        const int c = kend / L;
+        if (c < nch_alloc) {
+          SA[inst * pstride + (long long)c * n + i] = A;
+          SB[inst * pstride + (long long)c * n + i] = B;
+        }
+      }
+      if (has_next) sbuf[(s + 1) & 1][tid] = nx;
+    }
+  }
+  D v = Lim<D>::lowest();
+  if (i < n) {
+    v = score_dyn<D>(dist, rp, A, B);
+    if (ms1) ms1[inst * table_stride + i] = v;
+    if (ns1) ns1[inst * table_stride + i] = n;
+    if (rec_next) rec_next[inst * rec_stride + i].p = v;
+  }
+  if (shard_chunk) shard_chunk[blockIdx.x * BR + tid] = v;
+}
+
+template <typename D>
+__global__ void level1_prefix_kernel(int n, long long rec_stride, int dist, int rp,
+                                     const Rec4<D>* __restrict__ rec, D* __restrict__ ms1,
+                                     int* __restrict__ ns1, long long table_stride,
+                                     Rec4<D>* __restrict__ rec_next) {
+  const int inst = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rec += (long long)inst * rec_stride;
+  const D A = sub_rn<D>(rec[n].x, rec[i].x);
+  const D B = sub_rn<D>(rec[n].y, rec[i].y);
+  const D v = score_dyn<D>(dist, rp, A, B);
+  ms1[inst * table_stride + i] = v;
+  ns1[inst * table_stride + i] = n;
+  rec_next[inst * rec_stride + i].p = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1: priority keys, gather, level records.
+// ---------------------------------------------------------------------------------------------
+template <typename D>
+__global__ void keys_kernel(long long total, int n, const D* __restrict__ a, const D* __restrict__ b,
+                            D* __restrict__ key, int* __restrict__ idx) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  key[g] = a[g] / b[g];  // IEEE divide in D, as the comparator of DP_impl.hpp:14-15
+  idx[g] = (int)(g % n);
+}
+
+__global__ void offsets_kernel(int R, int n, int* __restrict__ off) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g <= R) off[g] = g * n;
+}
+
+template <typename D>
+__global__ void gather_kernel(long long total, int n, const int* __restrict__ perm,
+                              const D* __restrict__ a, const D* __restrict__ b, D* __restrict__ as,
+                              D* __restrict__ bs) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const long long base = (g / n) * n;
+  const int p = perm[g];
+  as[g] = a[base + p];
+  bs[g] = b[base + p];
+}
+
+// RUNNING records: rec[k] = {a[k-1], b[k-1]}; both level buffers.
+template <typename D>
+__global__ void build_rec_running_kernel(int n, long long rec_stride, const D* __restrict__ as,
+                                         const D* __restrict__ bs, Rec4<D>* __restrict__ rec0,
+                                         Rec4<D>* __restrict__ rec1) {
+  const int inst = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n) return;
+  Rec4<D> r;
+  r.x = k ? as[(long long)inst * n + k - 1] : (D)0;
+  r.y = k ? bs[(long long)inst * n + k - 1] : (D)0;
+  r.p = 0;
+  r.w = 0;
+  rec0[inst * rec_stride + k] = r;
+  rec1[inst * rec_stride + k] = r;
+}
+
+// PREFIX records: rec[k] = {sum a[0..k), sum b[0..k)}.  One CTA per instance: every thread owns a
+// contiguous slice, slice totals are scanned in shared memory, slices are re-walked with their offset.
+template <typename D, int NT>
+__global__ void __launch_bounds__(NT)
+build_rec_prefix_kernel(int n, long long rec_stride, const D* __restrict__ as, const D* __restrict__ bs,
+                        Rec4<D>* __restrict__ rec0, Rec4<D>* __restrict__ rec1) {
+  __shared__ D sa[NT], sb[NT];
+  const int inst = blockIdx.x;
+  as += (long long)inst * n;
+  bs += (long long)inst * n;
+  rec0 += inst * rec_stride;
+  rec1 += inst * rec_stride;
+  const int tid = threadIdx.x;
+  const int per = (n + NT - 1) / NT;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  D ta = 0, tb = 0;
+  for (int k = lo; k < hi; ++k) {
+    ta = add_rn<D>(ta, as[k]);
+    tb = add_rn<D>(tb, bs[k]);
+  }
+  sa[tid] = ta;
+  sb[tid] = tb;
+  __syncthreads();
+  if (tid == 0) {  // NT partials: serial exclusive scan, left to right
+    D ra = 0, rb = 0;
+    for (int q = 0; q < NT; ++q) {
+      D xa = sa[q], xb = sb[q];
+      sa[q] = ra;
+      sb[q] = rb;
+      ra = add_rn<D>(ra, xa);
+      rb = add_rn<D>(rb, xb);
+    }
+  }
+  __syncthreads();
+  D ra = sa[tid], rb = sb[tid];
+  if (tid == 0) {
+    Rec4<D> z;
+    z.x = z.y = z.p = z.w = 0;
+    rec0[0] = z;
+    rec1[0] = z;
+  }
+  for (int k = lo; k < hi; ++k) {
+    ra = add_rn<D>(ra, as[k]);
+    rb = add_rn<D>(rb, bs[k]);
+    Rec4<D> r;
+    r.x = ra;
+    r.y = rb;
+    r.p = 0;
+    r.w = 0;
+    rec0[k + 1] = r;
+    rec1[k + 1] = r;
+  }
+}
+
+template <typename D>
+__global__ void init_tables_kernel(long long total, int n, D* __restrict__ ms, int* __restrict__ ns) {
+  // row 0 of every instance: 0 / -1; all other rows: lowest() / -1  (DP_impl.hpp:83-95)
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  (void)n;
+  ms[g] = Lim<D>::lowest();
+  ns[g] = -1;
+}
+template <typename D>
+__global__ void init_row0_kernel(int n, long long inst_stride, D* __restrict__ ms) {
+  const int inst = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ms[inst * inst_stride + i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backtrace (DP_impl.hpp:122-139): boundaries by walking nextStart_, then one range score per subset.
+// ---------------------------------------------------------------------------------------------
+// One thread per (instance, S).  bounds row layout: stride (Tc+1) per S.
+__global__ void backtrace_bounds_kernel(int R, int n, int Tc, int sweep, const int* __restrict__ ns,
+                                        int* __restrict__ bounds) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nS = sweep ? Tc + 1 : 1;
+  if (g >= R * nS) return;
+  const int inst = g / nS;
+  const int S = sweep ? (g % nS) : Tc;
+  int* out = bounds + ((long long)inst * nS + (sweep ? S : 0)) * (Tc + 1);
+  const int* nsi = ns + (long long)inst * (Tc + 1) * n;
+  int cur = 0;
+  out[0] = 0;
+  for (int t = S; t > 0; --t) {
+    int nxt = (cur >= 0 && cur < n) ? nsi[(long long)t * n + cur] : -1;
+    out[S - t + 1] = nxt;
+    cur = nxt;
+  }
+  for (int q = S + 1; q <= Tc; ++q) out[q] = -1;
+}
+
+template <typename D>
+__global__ void backtrace_scores_kernel(int R, int n, int Tc, int sweep, int dist, int rp, int running,
+                                        const int* __restrict__ bounds, const D* __restrict__ as,
+                                        const D* __restrict__ bs, const Rec4<D>* __restrict__ rec,
+                                        long long rec_stride, D* __restrict__ scores) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nS = sweep ? Tc + 1 : 1;
+  const long long total = (long long)R * nS * Tc;
+  if (g >= total) return;
+  const int t = g % Tc;
+  const int sidx = (g / Tc) % nS;
+  const int inst = g / (Tc * nS);
+  const int S = sweep ? sidx : Tc;
+  D out = 0;
+  if (t < S) {
+    const int* bd = bounds + ((long long)inst * nS + sidx) * (Tc + 1);
+    const int lo = bd[t], hi = bd[t + 1];
+    if (lo >= 0 && hi >= lo && hi <= n) {
+      D A = 0, B = 0;
+      if (running) {
+        const D* ap = as + (long long)inst * n;
+        const D* bp = bs + (long long)inst * n;
+#pragma unroll 8
+        for (int k = lo; k < hi; ++k) {
+          A = add_rn<D>(A, ap[k]);
+          B = add_rn<D>(B, bp[k]);
+        }
+      } else {
+        const Rec4<D>* r = rec + inst * rec_stride;
+        A = sub_rn<D>(r[hi].x, r[lo].x);
+        B = sub_rn<D>(r[hi].y, r[lo].y);
+      }
+      out = score_dyn<D>(dist, rp, A, B);
+    } else {
+      out = nan("");
+    }
+  }
+  scores[g] = out;
+}
+
+// compute_score (python_dpsolver.cpp:74-111): S(0,n) of the unsorted inputs, sequential sums.
+template <typename D>
+__global__ void range_score_kernel(int n, int dist, int rp, const D* __restrict__ a,
+                                   const D* __restrict__ b, D* __restrict__ out) {
+  if (blockIdx.x || threadIdx.x) return;
+  D A = 0, B = 0;
+#pragma unroll 8
+  for (int k = 0; k < n; ++k) {
+    A = add_rn<D>(A, a[k]);
+    B = add_rn<D>(B, b[k]);
+  }
+  *out = score_dyn<D>(dist, rp, A, B);
+}
+
+// Sharded runs: scatter the all-gathered [world][chunk] level values back to natural row order
+// and into the p field of the next level's records.
+template <typename D, int BR>
+__global__ void shard_unpermute_kernel(int n, int world, int chunk, const D* __restrict__ gathered,
+                                       Rec4<D>* __restrict__ rec_next, D* __restrict__ level_nat) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)world * chunk) return;
+  const int r = (int)(g / chunk);
+  const int m = (int)(g % chunk);
+  const int rb = r + world * (m / BR);
+  const int i = rb * BR + (m % BR);
+  if (i < n) {
+    const D v = gathered[g];
+    rec_next[i].p = v;
+    if (level_nat) level_nat[i] = v;
+  }
+}
+
+}  // namespace ps

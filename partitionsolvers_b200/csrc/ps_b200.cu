@@ -1,0 +1,686 @@
+// ps_b200.cu -- C ABI (include/ps_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// Host-side orchestration of one DPSolver construction (reference DP_impl.hpp:69-230):
+//   sort_by_priority  -> keys_kernel + device radix sort + gather_kernel
+//   createContext     -> build_rec_* (no n x n tables)
+//   create()          -> level-1 kernel, then per level j=2..T: level_tile_kernel + combine_kernel
+//   optimize()        -> backtrace_bounds_kernel + backtrace_scores_kernel
+// Everything runs on the context's own non-blocking stream; the call blocks on that stream only.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ps_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int BR = 128;  // rows per tile == threads per CTA == records per shared-memory stage
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct ps_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  ps_timings tm;
+  // grow-only device workspaces
+  DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
+      bounds, scores, cub_tmp, seg_off, scalar;
+  std::vector<cudaEvent_t> events;
+  size_t ev_used = 0;
+  long long launches = 0;
+};
+
+struct ps_shard {
+  ps_ctx* ctx = nullptr;
+  int dtype = 0;  // 4 or 8
+  ps_problem p;
+  int rank = 0, world = 1;
+  int L = 0, nch_alloc = 0, owned_blocks = 0, chunk_rows = 0;
+  void* rec = nullptr;   // [2][n+1]
+  void* SA = nullptr;
+  void* SB = nullptr;
+  void* part_val = nullptr;
+  int* part_arg = nullptr;
+  int* ns = nullptr;     // [T+1][n] (owned rows filled)
+  int cur = 0;           // record buffer holding the previous level in its p field
+};
+
+namespace {
+
+#define PS_CUDA(ctx, expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                        \
+      return (e__ == cudaErrorMemoryAllocation) ? PS_ERR_NOMEM : PS_ERR_CUDA;                  \
+    }                                                                                          \
+  } while (0)
+
+#define PS_TRY(expr)                 \
+  do {                               \
+    ps_status s__ = (expr);          \
+    if (s__ != PS_OK) return s__;    \
+  } while (0)
+
+ps_status ensure(ps_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return PS_OK;
+  if (b.p) {
+    PS_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + (bytes >> 3) + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ctx->err = "cudaMalloc(" + std::to_string(bytes) + " B): " + cudaGetErrorString(e);
+    return PS_ERR_NOMEM;
+  }
+  b.cap = want;
+  return PS_OK;
+}
+
+ps_status mark(ps_ctx* ctx, cudaEvent_t* out) {
+  if (ctx->ev_used == ctx->events.size()) {
+    cudaEvent_t e;
+    PS_CUDA(ctx, cudaEventCreate(&e));
+    ctx->events.push_back(e);
+  }
+  cudaEvent_t e = ctx->events[ctx->ev_used++];
+  PS_CUDA(ctx, cudaEventRecord(e, ctx->stream));
+  *out = e;
+  return PS_OK;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// k-chunk length: a multiple of BR giving enough equal tiles to balance 148 SMs (SURVEY.md hard part 5)
+int choose_chunk(int n, int batch, int user) {
+  if (user > 0) return std::max(BR, (user / BR) * BR);
+  const long long want_tiles = 148LL * 64;
+  const int nrb = cdiv(n, BR);
+  long long nch = (2 * want_tiles + (long long)batch * nrb - 1) / ((long long)batch * nrb);
+  nch = std::max(1LL, std::min(64LL, nch));
+  long long L = ((cdiv(n, nch) + BR - 1) / BR) * (long long)BR;
+  L = std::max<long long>(L, 4 * BR);
+  L = std::min<long long>(L, 16384);
+  L = std::min<long long>(L, ((n + BR - 1) / BR) * (long long)BR);
+  return (int)std::max<long long>(L, BR);
+}
+
+template <typename D>
+struct LevelLaunch {
+  using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const D*, const D*, D*, int*);
+  static Fn pick(int dist, int rp, int running) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                               \
+  return running ? (Fn)level_tile_kernel<D, DI, RPV, true, BR>                         \
+                 : (Fn)level_tile_kernel<D, DI, RPV, false, BR>;
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: PS_PICK(DIST_GAUSSIAN, false)
+      case 1: PS_PICK(DIST_GAUSSIAN, true)
+      case 2: PS_PICK(DIST_POISSON, false)
+      case 3: PS_PICK(DIST_POISSON, true)
+      default: PS_PICK(DIST_RATIONAL, false)
+    }
+#undef PS_PICK
+  }
+};
+
+ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int rb_step) {
+  ps::Geom g;
+  g.n = n;
+  g.kmax = n - j + 1;
+  g.nrows = (j == Tc) ? 1 : (n - j + 1);  // DP_impl.hpp:114-116: last level needs row 0 only
+  g.L = L;
+  g.NCH = cdiv(g.kmax, L);
+  g.G = L / BR;
+  const int nrb_total = cdiv(g.nrows, BR);
+  g.NRB = nrb_total > rb_first ? (nrb_total - rb_first + rb_step - 1) / rb_step : 0;
+  g.nch_alloc = nch_alloc;
+  g.rec_stride = (long long)n + 1;
+  g.rb_first = rb_first;
+  g.rb_step = rb_step;
+  g.ntiles = ps::geom_count_tiles(0, g.NCH, g.G, g.NRB, rb_first, rb_step);
+  return g;
+}
+
+long long level_cells(int n, int j, int Tc) {
+  long long m = n - j + 1;
+  return (j == Tc) ? m : m * (m + 1) / 2;
+}
+
+template <typename D>
+ps_status sort_stage(ps_ctx* ctx, const ps_problem& p, const D* d_a, const D* d_b, int R, int n) {
+  const long long total = (long long)R * n;
+  cudaStream_t st = ctx->stream;
+  PS_TRY(ensure(ctx, ctx->perm, total * sizeof(int)));
+  PS_TRY(ensure(ctx, ctx->a_s, total * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->b_s, total * sizeof(D)));
+  int* d_perm = (int*)ctx->perm.p;
+  if (p.sort_mode == PS_SORT_GIVEN) {
+    PS_CUDA(ctx, cudaMemcpyAsync(d_perm, p.perm, total * sizeof(int),
+                                 p.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!p.on_device) ctx->tm.h2d_bytes += total * sizeof(int);
+  } else {
+    PS_TRY(ensure(ctx, ctx->key_in, total * sizeof(D)));
+    PS_TRY(ensure(ctx, ctx->key_out, total * sizeof(D)));
+    PS_TRY(ensure(ctx, ctx->idx_in, total * sizeof(int)));
+    D* kin = (D*)ctx->key_in.p;
+    D* kout = (D*)ctx->key_out.p;
+    int* iin = (int*)ctx->idx_in.p;
+    ps::keys_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, n, d_a, d_b, kin, iin);
+    ctx->launches++;
+    size_t tmp = 0;
+    if (R == 1) {
+      PS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, iin, d_perm, (int)total, 0,
+                                                   (int)sizeof(D) * 8, st));
+      PS_TRY(ensure(ctx, ctx->cub_tmp, tmp));
+      PS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, kin, kout, iin, d_perm,
+                                                   (int)total, 0, (int)sizeof(D) * 8, st));
+    } else {
+      PS_TRY(ensure(ctx, ctx->seg_off, (size_t)(R + 1) * sizeof(int)));
+      int* off = (int*)ctx->seg_off.p;
+      ps::offsets_kernel<<<cdiv(R + 1, 256), 256, 0, st>>>(R, n, off);
+      ctx->launches++;
+      PS_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, kin, kout, iin, d_perm,
+                                                            (int)total, R, off, off + 1, 0,
+                                                            (int)sizeof(D) * 8, st));
+      PS_TRY(ensure(ctx, ctx->cub_tmp, tmp));
+      PS_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortPairs(ctx->cub_tmp.p, tmp, kin, kout, iin, d_perm,
+                                                            (int)total, R, off, off + 1, 0,
+                                                            (int)sizeof(D) * 8, st));
+    }
+    ctx->launches += 8;  // radix passes (histogram + onesweep); library kernels, counted approximately
+  }
+  ps::gather_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, n, d_perm, d_a, d_b, (D*)ctx->a_s.p,
+                                                         (D*)ctx->b_s.p);
+  ctx->launches++;
+  PS_CUDA(ctx, cudaGetLastError());
+  return PS_OK;
+}
+
+template <typename D>
+ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res) {
+  if (!ctx) return PS_ERR_INVALID;
+  ctx->err.clear();
+  if (!pp || !a || !b || !res) {
+    ctx->err = "null argument";
+    return PS_ERR_INVALID;
+  }
+  const ps_problem p = *pp;
+  if (p.n < 1 || p.T < 1 || p.batch < 1) {
+    ctx->err = "n, T and batch must be >= 1";
+    return PS_ERR_INVALID;
+  }
+  if (p.dist < 0 || p.dist > 2) {
+    ctx->err = "Bad distributional assignment";
+    return PS_ERR_DIST;
+  }
+  if (p.sort_mode == PS_SORT_GIVEN && !p.perm) {
+    ctx->err = "PS_SORT_GIVEN without perm";
+    return PS_ERR_INVALID;
+  }
+  if (p.sum_mode != PS_SUM_RUNNING && p.sum_mode != PS_SUM_PREFIX) {
+    ctx->err = "bad sum_mode";
+    return PS_ERR_INVALID;
+  }
+  const int n = p.n, R = p.batch;
+  const int Tc = std::min(p.T, n);  // DP_impl.hpp:37-38
+  if (Tc - 1 > PS_MAX_TIMED_LEVELS) {
+    // timing slots only; the solve itself has no such limit
+  }
+  const int running = (p.sum_mode == PS_SUM_RUNNING);
+  const int rp = p.risk_part ? 1 : 0;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  memset(&ctx->tm, 0, sizeof(ctx->tm));
+  ctx->ev_used = 0;
+  ctx->launches = 0;
+  const long long total = (long long)R * n;
+  const cudaMemcpyKind in_kind = p.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind out_kind = p.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+
+  cudaEvent_t e_begin, e_h2d, e_sort, e_pre, e_lev, e_bt, e_end;
+  PS_TRY(mark(ctx, &e_begin));
+
+  // ---- inputs
+  const D* d_a = a;
+  const D* d_b = b;
+  if (!p.on_device) {
+    PS_TRY(ensure(ctx, ctx->a_in, total * sizeof(D)));
+    PS_TRY(ensure(ctx, ctx->b_in, total * sizeof(D)));
+    PS_CUDA(ctx, cudaMemcpyAsync(ctx->a_in.p, a, total * sizeof(D), in_kind, st));
+    PS_CUDA(ctx, cudaMemcpyAsync(ctx->b_in.p, b, total * sizeof(D), in_kind, st));
+    ctx->tm.h2d_bytes += 2 * total * sizeof(D);
+    d_a = (const D*)ctx->a_in.p;
+    d_b = (const D*)ctx->b_in.p;
+  }
+  PS_TRY(mark(ctx, &e_h2d));
+
+  // ---- stage 1: sort by priority, gather, records
+  PS_TRY(sort_stage<D>(ctx, p, d_a, d_b, R, n));
+  const long long rec_stride = (long long)n + 1;
+  PS_TRY(ensure(ctx, ctx->rec, 2 * R * rec_stride * sizeof(ps::Rec4<D>)));
+  ps::Rec4<D>* rec0 = (ps::Rec4<D>*)ctx->rec.p;
+  ps::Rec4<D>* rec1 = rec0 + R * rec_stride;
+  ps::Rec4<D>* recs[2] = {rec0, rec1};
+  const D* d_as = (const D*)ctx->a_s.p;
+  const D* d_bs = (const D*)ctx->b_s.p;
+  if (running) {
+    ps::build_rec_running_kernel<D><<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(n, rec_stride, d_as, d_bs,
+                                                                              rec0, rec1);
+  } else {
+    ps::build_rec_prefix_kernel<D, 1024><<<R, 1024, 0, st>>>(n, rec_stride, d_as, d_bs, rec0, rec1);
+  }
+  ctx->launches++;
+
+  // ---- DP tables
+  const long long table_stride = (long long)(Tc + 1) * n;
+  PS_TRY(ensure(ctx, ctx->ms, R * table_stride * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->ns, R * table_stride * sizeof(int)));
+  D* d_ms = (D*)ctx->ms.p;
+  int* d_ns = (int*)ctx->ns.p;
+  ps::init_tables_kernel<D><<<cdiv(R * table_stride, 256), 256, 0, st>>>(R * table_stride, n, d_ms, d_ns);
+  ps::init_row0_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, table_stride, d_ms);
+  ctx->launches += 2;
+  PS_TRY(mark(ctx, &e_sort));
+
+  // ---- level 1
+  const int L = choose_chunk(n, R, p.chunk_len);
+  const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
+  const long long pstride = (long long)nch_alloc * n;
+  PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->part_arg, R * pstride * sizeof(int)));
+  D* d_pv = (D*)ctx->part_val.p;
+  int* d_pa = (int*)ctx->part_arg.p;
+  D* d_SA = nullptr;
+  D* d_SB = nullptr;
+  if (running) {
+    if (nch_alloc > 1) {
+      PS_TRY(ensure(ctx, ctx->SA, R * pstride * sizeof(D)));
+      PS_TRY(ensure(ctx, ctx->SB, R * pstride * sizeof(D)));
+      d_SA = (D*)ctx->SA.p;
+      d_SB = (D*)ctx->SB.p;
+    }
+    ps::level1_running_kernel<D, BR><<<dim3(cdiv(n, BR), R), BR, 0, st>>>(
+        n, L, nch_alloc, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
+        0, 1, nullptr);
+  } else {
+    ps::level1_prefix_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, rec_stride, p.dist, rp, rec0,
+                                                                      d_ms + n, d_ns + n, table_stride, rec1);
+  }
+  ctx->launches++;
+  PS_TRY(mark(ctx, &e_pre));
+
+  // ---- levels 2..Tc  (DP_impl.hpp:101-118)
+  auto fn = LevelLaunch<D>::pick(p.dist, rp, running);
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lev_ev;
+  for (int j = 2; j <= Tc; ++j) {
+    ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1);
+    const ps::Rec4<D>* rin = recs[(j - 1) & 1];
+    ps::Rec4<D>* rout = recs[j & 1];
+    const bool timed = (j - 2) < PS_MAX_TIMED_LEVELS;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) PS_TRY(mark(ctx, &e0));
+    fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+    if (timed) PS_TRY(mark(ctx, &e1));
+    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), R), 256, 0, st>>>(
+        g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr);
+    ctx->launches += 2;
+    if (timed) {
+      lev_ev.push_back({e0, e1});
+      ctx->tm.level_cells[j - 2] = level_cells(n, j, Tc) * R;
+    }
+  }
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_TRY(mark(ctx, &e_lev));
+
+  // ---- backtrace
+  const int nS = p.sweep ? Tc + 1 : 1;
+  PS_TRY(ensure(ctx, ctx->bounds, (size_t)R * nS * (Tc + 1) * sizeof(int)));
+  PS_TRY(ensure(ctx, ctx->scores, (size_t)R * nS * Tc * sizeof(D)));
+  int* d_bounds = (int*)ctx->bounds.p;
+  D* d_scores = (D*)ctx->scores.p;
+  ps::backtrace_bounds_kernel<<<cdiv((long long)R * nS, 128), 128, 0, st>>>(R, n, Tc, p.sweep ? 1 : 0, d_ns,
+                                                                           d_bounds);
+  ps::backtrace_scores_kernel<D><<<cdiv((long long)R * nS * Tc, 128), 128, 0, st>>>(
+      R, n, Tc, p.sweep ? 1 : 0, p.dist, rp, running, d_bounds, d_as, d_bs, rec0, rec_stride, d_scores);
+  ctx->launches += 2;
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_TRY(mark(ctx, &e_bt));
+
+  // ---- outputs
+  auto copy_out = [&](void* dst, const void* src, size_t bytes) -> ps_status {
+    if (!dst) return PS_OK;
+    PS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, out_kind, st));
+    if (!p.on_device) ctx->tm.d2h_bytes += bytes;
+    return PS_OK;
+  };
+  PS_TRY(copy_out(res->perm, ctx->perm.p, total * sizeof(int)));
+  PS_TRY(copy_out(res->bounds, d_bounds, (size_t)R * nS * (Tc + 1) * sizeof(int)));
+  PS_TRY(copy_out(res->subset_scores, d_scores, (size_t)R * nS * Tc * sizeof(D)));
+  PS_TRY(copy_out(res->max_score, d_ms, R * table_stride * sizeof(D)));
+  PS_TRY(copy_out(res->next_start, d_ns, R * table_stride * sizeof(int)));
+  PS_TRY(mark(ctx, &e_end));
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+
+  auto ms_between = [&](cudaEvent_t x, cudaEvent_t y) {
+    float v = 0.f;
+    cudaEventElapsedTime(&v, x, y);
+    return v;
+  };
+  ctx->tm.total_ms = ms_between(e_begin, e_end);
+  ctx->tm.h2d_ms = ms_between(e_begin, e_h2d);
+  ctx->tm.sort_scan_ms = ms_between(e_h2d, e_sort);
+  ctx->tm.prepass_ms = ms_between(e_sort, e_pre);
+  ctx->tm.levels_ms = ms_between(e_pre, e_lev);
+  ctx->tm.backtrace_ms = ms_between(e_lev, e_bt);
+  ctx->tm.d2h_ms = ms_between(e_bt, e_end);
+  ctx->tm.n_levels = (int)lev_ev.size();
+  for (size_t q = 0; q < lev_ev.size(); ++q)
+    ctx->tm.level_ms[q] = ms_between(lev_ev[q].first, lev_ev[q].second);
+  ctx->tm.kernel_launches = ctx->launches;
+  return PS_OK;
+}
+
+template <typename D>
+ps_status range_score_impl(ps_ctx* ctx, int n, const D* a, const D* b, int dist, int rp, D* out) {
+  if (!ctx || !a || !b || !out || n < 1) return PS_ERR_INVALID;
+  if (dist < 0 || dist > 2) return PS_ERR_DIST;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  PS_TRY(ensure(ctx, ctx->a_in, (size_t)n * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->b_in, (size_t)n * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->scalar, 64));
+  PS_CUDA(ctx, cudaMemcpyAsync(ctx->a_in.p, a, (size_t)n * sizeof(D), cudaMemcpyHostToDevice, st));
+  PS_CUDA(ctx, cudaMemcpyAsync(ctx->b_in.p, b, (size_t)n * sizeof(D), cudaMemcpyHostToDevice, st));
+  ps::range_score_kernel<D><<<1, 32, 0, st>>>(n, dist, rp, (const D*)ctx->a_in.p, (const D*)ctx->b_in.p,
+                                             (D*)ctx->scalar.p);
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaMemcpyAsync(out, ctx->scalar.p, sizeof(D), cudaMemcpyDeviceToHost, st));
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  return PS_OK;
+}
+
+// ------------------------------------------------------------------------------- row sharding
+template <typename D>
+ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, const D* b_s, int rank,
+                            int world, ps_shard** out) {
+  if (!ctx || !pp || !a_s || !b_s || !out || world < 1 || rank < 0 || rank >= world) return PS_ERR_INVALID;
+  if (pp->n < 2 || pp->T < 1 || pp->batch > 1) return PS_ERR_INVALID;
+  if (pp->dist < 0 || pp->dist > 2) return PS_ERR_DIST;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  ps_shard* s = new (std::nothrow) ps_shard();
+  if (!s) return PS_ERR_NOMEM;
+  s->ctx = ctx;
+  s->dtype = (int)sizeof(D);
+  s->p = *pp;
+  s->rank = rank;
+  s->world = world;
+  const int n = pp->n;
+  const int Tc = std::min(pp->T, n);
+  s->L = choose_chunk(n, 1, pp->chunk_len);
+  s->nch_alloc = std::max(1, cdiv(std::max(1, n - 1), s->L));
+  const int nrb_total = cdiv(n, BR);
+  s->owned_blocks = nrb_total > rank ? (nrb_total - rank + world - 1) / world : 0;
+  s->chunk_rows = cdiv(nrb_total, world) * BR;  // same on every rank
+  const long long rec_stride = (long long)n + 1;
+  const long long pstride = (long long)s->nch_alloc * n;
+  cudaStream_t st = ctx->stream;
+  PS_CUDA(ctx, cudaMalloc(&s->rec, 2 * rec_stride * sizeof(ps::Rec4<D>)));
+  PS_CUDA(ctx, cudaMalloc(&s->part_val, pstride * sizeof(D)));
+  PS_CUDA(ctx, cudaMalloc((void**)&s->part_arg, pstride * sizeof(int)));
+  PS_CUDA(ctx, cudaMalloc((void**)&s->ns, (size_t)(Tc + 1) * n * sizeof(int)));
+  PS_CUDA(ctx, cudaMemsetAsync(s->ns, 0xff, (size_t)(Tc + 1) * n * sizeof(int), st));
+  const int running = (pp->sum_mode == PS_SUM_RUNNING);
+  if (running && s->nch_alloc > 1) {
+    PS_CUDA(ctx, cudaMalloc(&s->SA, pstride * sizeof(D)));
+    PS_CUDA(ctx, cudaMalloc(&s->SB, pstride * sizeof(D)));
+  }
+  ps::Rec4<D>* rec0 = (ps::Rec4<D>*)s->rec;
+  ps::Rec4<D>* rec1 = rec0 + rec_stride;
+  if (running)
+    ps::build_rec_running_kernel<D><<<dim3(cdiv(n + 1, 256), 1), 256, 0, st>>>(n, rec_stride, a_s, b_s, rec0,
+                                                                              rec1);
+  else
+    ps::build_rec_prefix_kernel<D, 1024><<<1, 1024, 0, st>>>(n, rec_stride, a_s, b_s, rec0, rec1);
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  s->cur = 0;
+  *out = s;
+  return PS_OK;
+}
+
+template <typename D>
+ps_status shard_level1_impl(ps_shard* s, D* my_chunk) {
+  ps_ctx* ctx = s->ctx;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = s->p.n;
+  const long long rec_stride = (long long)n + 1;
+  ps::Rec4<D>* rec0 = (ps::Rec4<D>*)s->rec;
+  cudaStream_t st = ctx->stream;
+  PS_CUDA(ctx, cudaMemsetAsync(my_chunk, 0, (size_t)s->chunk_rows * sizeof(D), st));
+  // level 1 always walks the row (RUNNING) so that SA/SB get filled; in PREFIX mode the same kernel is
+  // run on the prefix records' increments?  No: PREFIX shards use the closed form below.
+  if (s->p.sum_mode == PS_SUM_RUNNING) {
+    if (s->owned_blocks > 0)
+      ps::level1_running_kernel<D, BR><<<dim3(s->owned_blocks, 1), BR, 0, st>>>(
+          n, s->L, s->nch_alloc, rec_stride, s->p.dist, s->p.risk_part ? 1 : 0, rec0, (D*)s->SA, (D*)s->SB,
+          (D*)nullptr, s->ns + n, 0, (ps::Rec4<D>*)nullptr, s->rank, s->world, my_chunk);
+  } else {
+    return PS_ERR_UNSUPPORTED;
+  }
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  return PS_OK;
+}
+
+template <typename D>
+ps_status shard_set_prev_impl(ps_shard* s, const D* gathered) {
+  ps_ctx* ctx = s->ctx;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = s->p.n;
+  const long long rec_stride = (long long)n + 1;
+  ps::Rec4<D>* rec0 = (ps::Rec4<D>*)s->rec;
+  s->cur ^= 1;
+  ps::Rec4<D>* dst = rec0 + (long long)s->cur * rec_stride;
+  const long long tot = (long long)s->world * s->chunk_rows;
+  ps::shard_unpermute_kernel<D, BR><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(n, s->world, s->chunk_rows,
+                                                                            gathered, dst, (D*)nullptr);
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PS_OK;
+}
+
+template <typename D>
+ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
+  ps_ctx* ctx = s->ctx;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = s->p.n;
+  const int Tc = std::min(s->p.T, n);
+  if (j < 2 || j > Tc) return PS_ERR_INVALID;
+  const long long rec_stride = (long long)n + 1;
+  ps::Rec4<D>* rec0 = (ps::Rec4<D>*)s->rec;
+  const ps::Rec4<D>* rin = rec0 + (long long)s->cur * rec_stride;
+  ps::Geom g = make_geom(n, j, Tc, s->L, s->nch_alloc, s->rank, s->world);
+  cudaStream_t st = ctx->stream;
+  PS_CUDA(ctx, cudaMemsetAsync(my_chunk, 0, (size_t)s->chunk_rows * sizeof(D), st));
+  if (g.ntiles > 0) {
+    auto fn = LevelLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, s->p.sum_mode == PS_SUM_RUNNING);
+    fn<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, (const D*)s->SA, (const D*)s->SB, (D*)s->part_val,
+                                         s->part_arg);
+    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
+        g, (const D*)s->part_val, s->part_arg, (D*)nullptr, s->ns + (long long)j * n, 0,
+        (ps::Rec4<D>*)nullptr, my_chunk);
+  }
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  return PS_OK;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+int ps_abi_version(void) { return PS_B200_ABI_VERSION; }
+
+const char* ps_status_string(ps_status s) {
+  switch (s) {
+    case PS_OK: return "ok";
+    case PS_ERR_INVALID: return "invalid argument";
+    case PS_ERR_DIST: return "Bad distributional assignment";
+    case PS_ERR_CUDA: return "CUDA error";
+    case PS_ERR_NOMEM: return "out of memory";
+    case PS_ERR_NODEVICE: return "no CUDA device (this library has no CPU path)";
+    case PS_ERR_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown";
+}
+
+ps_status ps_create(ps_ctx** out, int device) {
+  if (!out) return PS_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return PS_ERR_NODEVICE;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return PS_ERR_NODEVICE;
+  }
+  if (device >= count) return PS_ERR_INVALID;
+  ps_ctx* ctx = new (std::nothrow) ps_ctx();
+  if (!ctx) return PS_ERR_NOMEM;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return PS_ERR_CUDA;
+  }
+  memset(&ctx->tm, 0, sizeof(ctx->tm));
+  *out = ctx;
+  return PS_OK;
+}
+
+void ps_destroy(ps_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->a_in,  &ctx->b_in,     &ctx->key_in,   &ctx->key_out, &ctx->idx_in, &ctx->perm,
+                    &ctx->a_s,   &ctx->b_s,      &ctx->rec,      &ctx->SA,      &ctx->SB,     &ctx->part_val,
+                    &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->cub_tmp,
+                    &ctx->seg_off,  &ctx->scalar};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* ps_last_error(const ps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int ps_device(const ps_ctx* ctx) { return ctx ? ctx->device : -1; }
+uintptr_t ps_stream(const ps_ctx* ctx) { return ctx ? (uintptr_t)ctx->stream : 0; }
+
+ps_status ps_solve_f32(ps_ctx* ctx, const ps_problem* p, const float* a, const float* b, ps_result* r) {
+  return solve_impl<float>(ctx, p, a, b, r);
+}
+ps_status ps_solve_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, ps_result* r) {
+  return solve_impl<double>(ctx, p, a, b, r);
+}
+
+ps_status ps_get_timings(const ps_ctx* ctx, ps_timings* out) {
+  if (!ctx || !out) return PS_ERR_INVALID;
+  *out = ctx->tm;
+  return PS_OK;
+}
+
+ps_status ps_range_score_f32(ps_ctx* ctx, int n, const float* a, const float* b, int dist, int risk_part,
+                             float* out) {
+  return range_score_impl<float>(ctx, n, a, b, dist, risk_part ? 1 : 0, out);
+}
+ps_status ps_range_score_f64(ps_ctx* ctx, int n, const double* a, const double* b, int dist, int risk_part,
+                             double* out) {
+  return range_score_impl<double>(ctx, n, a, b, dist, risk_part ? 1 : 0, out);
+}
+
+ps_status ps_shard_create_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, int rank,
+                              int world, ps_shard** out) {
+  return shard_create_impl<double>(ctx, p, a, b, rank, world, out);
+}
+ps_status ps_shard_create_f32(ps_ctx* ctx, const ps_problem* p, const float* a, const float* b, int rank,
+                              int world, ps_shard** out) {
+  return shard_create_impl<float>(ctx, p, a, b, rank, world, out);
+}
+int ps_shard_chunk_rows(const ps_shard* s) { return s ? s->chunk_rows : 0; }
+
+ps_status ps_shard_level1(ps_shard* s, void* my_chunk_dev) {
+  if (!s || !my_chunk_dev) return PS_ERR_INVALID;
+  return s->dtype == 4 ? shard_level1_impl<float>(s, (float*)my_chunk_dev)
+                       : shard_level1_impl<double>(s, (double*)my_chunk_dev);
+}
+ps_status ps_shard_set_prev(ps_shard* s, const void* gathered_dev) {
+  if (!s || !gathered_dev) return PS_ERR_INVALID;
+  return s->dtype == 4 ? shard_set_prev_impl<float>(s, (const float*)gathered_dev)
+                       : shard_set_prev_impl<double>(s, (const double*)gathered_dev);
+}
+ps_status ps_shard_level(ps_shard* s, int j, void* my_chunk_dev) {
+  if (!s || !my_chunk_dev) return PS_ERR_INVALID;
+  return s->dtype == 4 ? shard_level_impl<float>(s, j, (float*)my_chunk_dev)
+                       : shard_level_impl<double>(s, j, (double*)my_chunk_dev);
+}
+int ps_shard_owner(const ps_shard* s, int i) { return s ? (i / BR) % s->world : -1; }
+
+ps_status ps_shard_next_start(ps_shard* s, int j, int i, int* out) {
+  if (!s || !out) return PS_ERR_INVALID;
+  const int n = s->p.n;
+  const int Tc = std::min(s->p.T, n);
+  if (j < 1 || j > Tc || i < 0 || i >= n) return PS_ERR_INVALID;
+  if (ps_shard_owner(s, i) != s->rank) {
+    *out = -2;
+    return PS_OK;
+  }
+  ps_ctx* ctx = s->ctx;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  PS_CUDA(ctx, cudaMemcpyAsync(out, s->ns + (long long)j * n + i, sizeof(int), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+  PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PS_OK;
+}
+
+void ps_shard_destroy(ps_shard* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaFree(s->rec);
+  cudaFree(s->SA);
+  cudaFree(s->SB);
+  cudaFree(s->part_val);
+  cudaFree(s->part_arg);
+  cudaFree(s->ns);
+  delete s;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+// score.cuh -- range-score functors evaluated in registers (the n x n score table of the reference,
+// score.hpp:47 `partialSums_`, is never materialised).
+//
+// Each functor reproduces the ROUNDING RECIPE of the reference formula it replaces
+// (score_impl.hpp:374-390 Poisson, :426-441 Gaussian, :461-474 RationalScore):
+//   * DataType=float, Poisson: everything in float (std::log(float) is logf).
+//   * DataType=float, Gaussian mult-clust and RationalScore: std::pow(float,int) returns double, so the
+//     expression is evaluated in double from the float sums and rounded to float once.
+//   * DataType=float, Gaussian risk-part: A*A in float, the two divisions in double, one rounding.
+//   * DataType=double: everything in double.
+//   * no fused multiply-add (reference build: -O3 -mavx2, no -mfma): every product/sum below is an
+//     explicit round-to-nearest intrinsic so nvcc cannot contract it; divisions are IEEE (div.rn).
+// log/logf are CUDA's (<= 1 ulp); glibc's differ in the last bit on a fraction of arguments, which
+// is the tolerance clause of the parity contract (DESIGN.md "Parity").
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ps {
+
+enum { DIST_GAUSSIAN = 0, DIST_POISSON = 1, DIST_RATIONAL = 2 };
+
+// kind = dist*2 + risk_part
+template <typename D, int DIST, bool RP>
+struct ScoreFn;
+
+// ------------------------------------------------------------------ float
+template <>
+struct ScoreFn<float, DIST_POISSON, false> {
+  static __device__ __forceinline__ float eval(float A, float B) {
+    float q = __fdiv_rn(A, B);
+    float s = __fsub_rn(__fadd_rn(__fmul_rn(A, logf(q)), B), A);
+    return (A > B) ? s : 0.f;
+  }
+};
+template <>
+struct ScoreFn<float, DIST_POISSON, true> {
+  static __device__ __forceinline__ float eval(float A, float B) {
+    return __fmul_rn(A, logf(__fdiv_rn(A, B)));
+  }
+};
+template <>
+struct ScoreFn<float, DIST_GAUSSIAN, false> {
+  static __device__ __forceinline__ float eval(float A, float B) {
+    double a = (double)A, b = (double)B;
+    double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(__ddiv_rn(__dmul_rn(a, a), b), b)), a);
+    return (A > B) ? __double2float_rn(s) : 0.f;
+  }
+};
+template <>
+struct ScoreFn<float, DIST_GAUSSIAN, true> {
+  static __device__ __forceinline__ float eval(float A, float B) {
+    float sq = __fmul_rn(A, A);
+    return __double2float_rn(__ddiv_rn(__ddiv_rn((double)sq, 2.), (double)B));
+  }
+};
+template <bool RP>
+struct ScoreFn<float, DIST_RATIONAL, RP> {
+  static __device__ __forceinline__ float eval(float A, float B) {
+    double a = (double)A;
+    return __double2float_rn(__ddiv_rn(__dmul_rn(a, a), (double)B));
+  }
+};
+
+// ------------------------------------------------------------------ double
+template <>
+struct ScoreFn<double, DIST_POISSON, false> {
+  static __device__ __forceinline__ double eval(double A, double B) {
+    double q = __ddiv_rn(A, B);
+    double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log(q)), B), A);
+    return (A > B) ? s : 0.;
+  }
+};
+template <>
+struct ScoreFn<double, DIST_POISSON, true> {
+  static __device__ __forceinline__ double eval(double A, double B) {
+    return __dmul_rn(A, log(__ddiv_rn(A, B)));
+  }
+};
+template <>
+struct ScoreFn<double, DIST_GAUSSIAN, false> {
+  static __device__ __forceinline__ double eval(double A, double B) {
+    double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(__ddiv_rn(__dmul_rn(A, A), B), B)), A);
+    return (A > B) ? s : 0.;
+  }
+};
+template <>
+struct ScoreFn<double, DIST_GAUSSIAN, true> {
+  static __device__ __forceinline__ double eval(double A, double B) {
+    return __ddiv_rn(__ddiv_rn(__dmul_rn(A, A), 2.), B);
+  }
+};
+template <bool RP>
+struct ScoreFn<double, DIST_RATIONAL, RP> {
+  static __device__ __forceinline__ double eval(double A, double B) {
+    return __ddiv_rn(__dmul_rn(A, A), B);
+  }
+};
+
+// Runtime-dispatched evaluation for the cold paths (level 1, backtrace, compute_score).
+template <typename D>
+__device__ __forceinline__ D score_dyn(int dist, int rp, D A, D B) {
+  switch (dist * 2 + (rp ? 1 : 0)) {
+    case 0: return ScoreFn<D, DIST_GAUSSIAN, false>::eval(A, B);
+    case 1: return ScoreFn<D, DIST_GAUSSIAN, true>::eval(A, B);
+    case 2: return ScoreFn<D, DIST_POISSON, false>::eval(A, B);
+    case 3: return ScoreFn<D, DIST_POISSON, true>::eval(A, B);
+    default: return ScoreFn<D, DIST_RATIONAL, false>::eval(A, B);
+  }
+}
+
+template <typename D>
+struct Lim;
+template <>
+struct Lim<float> {
+  static __device__ __host__ __forceinline__ float lowest() { return -3.402823466e+38f; }
+};
+template <>
+struct Lim<double> {
+  static __device__ __host__ __forceinline__ double lowest() { return -1.7976931348623157e+308; }
+};
+
+template <typename D>
+__device__ __forceinline__ D add_rn(D x, D y);
+template <>
+__device__ __forceinline__ float add_rn<float>(float x, float y) { return __fadd_rn(x, y); }
+template <>
+__device__ __forceinline__ double add_rn<double>(double x, double y) { return __dadd_rn(x, y); }
+template <typename D>
+__device__ __forceinline__ D sub_rn(D x, D y);
+template <>
+__device__ __forceinline__ float sub_rn<float>(float x, float y) { return __fsub_rn(x, y); }
+template <>
+__device__ __forceinline__ double sub_rn<double>(double x, double y) { return __dsub_rn(x, y); }
+
+}  // namespace ps
