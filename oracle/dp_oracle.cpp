@@ -369,6 +369,31 @@ double time_impl(int n, int T, const D* a, const D* b, int dist, int risk_part, 
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// One DP row in isolation (DP_impl.hpp:103-113): best/argmax over k=i+1..kmax of S(i,k)+prev[k] on
+// ALREADY SORTED inputs.  Lets the GPU tests check sampled rows at sizes where a full CPU solve would
+// take minutes: feed the GPU's own level j-1 row as `prev`.
+template <typename D>
+void rows_impl(int n, int kmax, int dist, int rp, const D* a, const D* b, const D* prev, int nrows,
+                      const int* rows, D* best_out, int* arg_out) {
+  (void)n;
+  for (int r = 0; r < nrows; ++r) {
+    const int i = rows[r];
+    D best = std::numeric_limits<D>::lowest();
+    int bestk = -1;
+    D A = 0, B = 0;
+    for (int k = i + 1; k <= kmax; ++k) {
+      A = A + a[k - 1];
+      B = B + b[k - 1];
+      D v = Score<D>::eval(dist, rp != 0, A, B) + prev[k];
+      if (v > best) {
+        best = v;
+        bestk = k;
+      }
+    }
+    best_out[r] = best;
+    arg_out[r] = bestk;
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -429,6 +454,15 @@ double oracle_range_score_f64(int n, const double* a, const double* b, int dist,
     B = B + b[k];
   }
   return Score<double>::eval(dist, risk_part != 0, A, B);
+}
+
+void oracle_dp_rows_f32(int n, int kmax, int dist, int rp, const float* a, const float* b, const float* prev,
+                        int nrows, const int* rows, float* best_out, int* arg_out) {
+  rows_impl<float>(n, kmax, dist, rp, a, b, prev, nrows, rows, best_out, arg_out);
+}
+void oracle_dp_rows_f64(int n, int kmax, int dist, int rp, const double* a, const double* b,
+                        const double* prev, int nrows, const int* rows, double* best_out, int* arg_out) {
+  rows_impl<double>(n, kmax, dist, rp, a, b, prev, nrows, rows, best_out, arg_out);
 }
 
 int oracle_ols_f32(int m, const float* scores) {

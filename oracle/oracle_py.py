@@ -172,6 +172,22 @@ def ref_score_pairs(a, b, dist, risk_part, ii, jj, dtype=np.float32):
     return out
 
 
+def dp_rows(a_sorted, b_sorted, prev, kmax, dist, risk_part, rows, dtype=np.float32):
+    """(best, argmax) of single DP rows given the previous level vector (port only)."""
+    a = np.ascontiguousarray(a_sorted, dtype=dtype)
+    b = np.ascontiguousarray(b_sorted, dtype=dtype)
+    prev = np.ascontiguousarray(prev, dtype=dtype)
+    rows = np.ascontiguousarray(rows, np.int32)
+    ct = C.c_float if dtype == np.float32 else C.c_double
+    best = np.zeros(rows.shape[0], dtype)
+    arg = np.zeros(rows.shape[0], np.int32)
+    fn = lib("port").oracle_dp_rows_f32 if dtype == np.float32 else lib("port").oracle_dp_rows_f64
+    fn.restype = None
+    fn(C.c_int(a.shape[0]), C.c_int(kmax), C.c_int(dist), C.c_int(int(risk_part)), _ptr(a, ct), _ptr(b, ct),
+       _ptr(prev, ct), C.c_int(rows.shape[0]), _ptr(rows, C.c_int), _ptr(best, ct), _ptr(arg, C.c_int))
+    return best, arg
+
+
 def ltss(which, a, b, dist):
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)

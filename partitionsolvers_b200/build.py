@@ -1,0 +1,86 @@
+"""In-tree builds (nvcc / g++ invoked directly; nothing is JIT-cached outside the repository).
+
+    python -m partitionsolvers_b200.build [--force]
+
+Outputs (git-ignored, shipped to the GPU box by gpurun):
+    partitionsolvers_b200/_lib/libps_b200.so     CUDA kernels + C ABI, sm_100a only
+    partitionsolvers_b200/_lib/proto*.so         pybind11 module `proto` (reference proto.i surface)
+"""
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+HOSTSRC = os.path.join(HERE, "host")
+LIBDIR = os.path.join(HERE, "_lib")
+INCLUDE = os.path.join(ROOT, "include")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _sources(d, exts):
+    out = []
+    for dp, _, files in os.walk(d):
+        out += [os.path.join(dp, f) for f in files if f.endswith(exts)]
+    return out
+
+
+def nvcc_path():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def build_cuda(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    target = os.path.join(LIBDIR, "libps_b200.so")
+    srcs = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(INCLUDE, "ps_b200.h")]
+    if force or _newer(target, srcs):
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+            "-I", INCLUDE, "-o", target, os.path.join(CSRC, "ps_b200.cu")]
+        subprocess.run(cmd, check=True)
+    return target
+
+
+def build_proto(force=False):
+    """pybind11 twin of the reference's SWIG module (src/cpp/proto.i): same name, functions, shapes."""
+    src = os.path.join(HOSTSRC, "proto_pybind.cpp")
+    if not os.path.exists(src):
+        return None
+    import pybind11
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    target = os.path.join(LIBDIR, "proto" + ext)
+    srcs = _sources(HOSTSRC, (".cpp", ".hpp")) + _sources(INCLUDE, (".h", ".hpp"))
+    if force or _newer(target, srcs):
+        cxx = os.environ.get("CXX", "g++")
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I", INCLUDE, "-I",
+               pybind11.get_include(), "-I", sysconfig.get_paths()["include"], src,
+               os.path.join(HOSTSRC, "python_dpsolver.cpp"), "-L", LIBDIR, "-lps_b200",
+               "-Wl,-rpath,$ORIGIN", "-pthread", "-o", target]
+        subprocess.run(cmd, check=True)
+    return target
+
+
+def build_all(force=False, verbose=False):
+    out = [build_cuda(force, verbose)]
+    p = build_proto(force)
+    if p:
+        out.append(p)
+    return out
+
+
+if __name__ == "__main__":
+    print("\n".join(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)))

@@ -39,19 +39,20 @@ def ols_num_clusters(scores, dtype):
         y = np.log((sc[2:] - sc[1:-1]).astype(dtype)).astype(np.float32)
     xd, yd = x.astype(np.float64), y.astype(np.float64)
     sx, sy, sxx, sxy = xd.sum(), yd.sum(), (xd * xd).sum(), (xd * yd).sum()
-    den = m * sxx - sx * sx
-    if den != 0:
-        b0 = np.float32((m * sxy - sx * sy) / den)
-        b1 = np.float32((sy - np.float64(b0) * sx) / m)
-    else:
-        nrm = xd[0] * xd[0] + 1.0
-        b0 = np.float32(xd[0] * yd[0] / nrm)
-        b1 = np.float32(yd[0] / nrm)
-    best, minres = 0, np.finfo(dtype).max
-    for i in range(m):
-        r = np.float32(np.float32(y[i] - np.float32(b0 * x[i])) - b1)
-        if r < minres:
-            best, minres = i, r
+    with np.errstate(all="ignore"):
+        den = m * sxx - sx * sx
+        if den != 0:
+            b0 = np.float32((m * sxy - sx * sy) / den)
+            b1 = np.float32((sy - np.float64(b0) * sx) / m)
+        else:
+            nrm = xd[0] * xd[0] + 1.0
+            b0 = np.float32(xd[0] * yd[0] / nrm)
+            b1 = np.float32(yd[0] / nrm)
+        best, minres = 0, np.finfo(dtype).max
+        for i in range(m):
+            r = np.float32(np.float32(y[i] - np.float32(b0 * x[i])) - b1)
+            if r < minres:
+                best, minres = i, r
     return best + 1
 
 

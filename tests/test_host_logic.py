@@ -1,0 +1,75 @@
+"""CPU tests of the host-side finishing logic (partitionsolvers_b200/host.py, the Python mirror of the
+C++ facade): given the engine's raw outputs (sort index, boundaries, per-subset scores) it must
+reproduce the reference's subsets, reorder, regulariser, getter quirk, sweep table and OLS choice.
+The raw outputs are synthesised from the golden fixtures, so no GPU is needed."""
+import numpy as np
+import pytest
+
+from conftest import assert_same_partition, golden_names, load_golden
+from partitionsolvers_b200 import host
+
+
+def _raw_from_golden(g, oracle):
+    """Walk the fixture's nextStart_ rows like the device backtrace does."""
+    dt = g["dtype"]
+    ns, perm = g["next_start"], g["perm"]
+    n = len(perm)
+    Tc = ns.shape[0] - 1
+    a_s, b_s = g["a"][perm], g["b"][perm]
+    sweep = bool(g["sweep"])
+    nS = Tc + 1 if sweep else 1
+    bounds = -np.ones((nS, Tc + 1), np.int32)
+    sc = np.zeros((nS, Tc), dt)
+    for row in range(nS):
+        S = row if sweep else Tc
+        cur = 0
+        bounds[row, 0] = 0
+        for t in range(S, 0, -1):
+            nxt = int(ns[t, cur])
+            bounds[row, S - t + 1] = nxt
+            sc[row, S - t] = oracle.range_score(a_s, b_s, int(g["dist"]), bool(g["rp"]), cur, nxt, dtype=dt)
+            cur = nxt
+    return dict(n=n, T=Tc, R=1, perm=perm, bounds=bounds, subset_scores=sc, max_score=None, next_start=None)
+
+
+class _FakeCtx:
+    def __init__(self, raw):
+        self.raw = raw
+
+    def solve_raw(self, *a, **k):
+        return self.raw
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_facade_finishing_matches_reference(oracle, name):
+    g = load_golden(name)
+    dt = g["dtype"]
+    raw = _raw_from_golden(g, oracle)
+    s = host.DPSolver(len(g["a"]), int(g["T"]), g["a"], g["b"], int(g["dist"]), bool(g["rp"]), True,
+                      float(g["gamma"]), int(g["reg_power"]), bool(g["sweep"]), False, dtype=dt, ctx=_FakeCtx(raw))
+    assert_same_partition(s.subsets, g["subsets"])
+    assert np.array_equal(s.get_score_by_subset_extern(), g["score_by_subset"])
+    assert s.get_optimal_score_extern() == g["score"]
+    assert dt(s.optimal_score) == g["optimal_score_member"]
+    if int(g["sweep"]):
+        allp = s.all
+        assert len(allp) == len(g["all"])
+        for (s1, v1), (s2, v2) in zip(allp, g["all"]):
+            assert v1 == v2
+            assert_same_partition(s1, s2)
+
+
+def test_ols_matches_oracle_restatement(oracle):
+    rs = np.random.RandomState(5)
+    for dt in (np.float32, np.float64):
+        for _ in range(50):
+            T = int(rs.randint(2, 30))
+            sc = np.concatenate([[0.0], np.cumsum(rs.uniform(0.01, 1.0, T) * np.arange(T, 0, -1) ** rs.uniform(0, 3))])
+            assert host.ols_num_clusters(sc.astype(dt), dt) == oracle.ols(sc, dtype=dt)
+
+
+def test_ols_degenerate_scores_default_to_one(oracle):
+    # non-increasing scores -> log of non-positive differences -> NaN/-inf everywhere -> index 0 -> t = 1
+    for dt in (np.float32, np.float64):
+        sc = np.array([0, 5, 5, 5, 5], dt)
+        assert oracle.ols(sc, dtype=dt) == host.ols_num_clusters(sc, dt)
