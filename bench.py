@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f64|f32]
+
+A "step" is ONE complete consecutive-partitions solve (priority sort, records, level 1, levels 2..T,
+backtrace) of the headline workload: synthetic n=100000, T=16 Poisson multiple clustering
+(BASELINE.json configs[2], synth.CONFIGS["C3"]).  metric = DP cell-updates/s = n^2*T / time (nominal
+count, BASELINE.json); `actual_cells_per_s` is the exact (i,k) count / time.
+
+  value   inputs resident in HBM, timed on the device (CUDA events on the library's stream)
+  e2e     same solve through the host-buffer C-ABI call: pinned host a,b in, sort index + boundaries +
+          subset scores out, copies inside the timed region (wall clock around the blocking call)
+  N > 1   one process per GPU (torchrun); every rank solves its own instance of the workload
+          (independent instances shard with no collective: SURVEY.md 8e) -> weak scaling,
+          value = N * n^2*T / max-over-ranks time.  The replica workload (configs[3]) is reported in
+          "mc_replicas" (4096 instances split over the ranks).
+
+--impl reference times the reference's own CPU solver (oracle/_ref = the unmodified reference headers;
+the port only if that library is absent) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from partitionsolvers_b200 import synth  # noqa: E402
+
+METRIC = "dp_cell_updates_per_s"
+UNIT = "cells/s"
+ALG_FLOPS_PER_CELL = {  # SURVEY.md 8d, (dist, risk_part) -> algorithmic flops per actual (i,k) cell
+    (1, False): 10, (1, True): 7, (0, False): 10, (0, True): 7, (2, False): 6, (2, True): 6}
+ALG_HBM_BYTES_PER_ROW = lambda w: 4 * w + 4  # noqa: E731  read prev,x,y; write value + int split (per level row)
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """nvidia-smi style clock / throttle-reason sampling DURING the timed region (pynvml)."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else \
+                    self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok and self.t.is_alive():
+            self.t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU baselines
+def cpu_reference_sample(dtype, target_s, quiet=True):
+    """Time the reference's own solver on a bounded sample of the headline workload: same score,
+    objective, T and input distribution, smaller n (its three n x n tables do not fit at n=100k)."""
+    from oracle import oracle_py as O
+    cfg = synth.CONFIGS["C3"]
+    kind = "reference" if O.have("ref") else "port"
+    if kind == "port":
+        O.build(("port",))
+    which = "ref" if kind == "reference" else "port"
+    n_cal = 3000
+    a, b = cfg["gen"](dtype, n_cal)
+    t_cal, _ = O.time_solve(which, a, b, cfg["T"], cfg["dist"], cfg["risk_part"], dtype=dtype)
+    w = np.dtype(dtype).itemsize
+    try:
+        import psutil
+        ram = psutil.virtual_memory().available
+    except Exception:
+        ram = 32 << 30
+    n_mem = int(np.sqrt(0.4 * ram / (3 * w))) if kind == "reference" else 10 ** 9
+    n_s = int(n_cal * np.sqrt(max(target_s, t_cal) / max(t_cal, 1e-4)))
+    n_s = max(n_cal, min(n_s, n_mem, 24000 if kind == "reference" else 60000))
+    n_s = (n_s // 500) * 500
+    return which, kind, n_s
+
+
+def run_cpu_solver(which, dtype, n_s):
+    from oracle import oracle_py as O
+    cfg = synth.CONFIGS["C3"]
+    a, b = cfg["gen"](dtype, n_s)
+    t, score = O.time_solve(which, a, b, cfg["T"], cfg["dist"], cfg["risk_part"], dtype=dtype)
+    return t, score
+
+
+def cpu_threads_used(kind):
+    # reference: <= 9 fill threads (score_impl.hpp:10-12,241,258-267) + single-threaded DP loop
+    hw = os.cpu_count() or 1
+    return min(9, hw) if kind == "reference" else hw
+
+
+def reference_arm(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    cfg = synth.CONFIGS["C3"]
+    budget = 150.0
+    per_step = max(1.0, min(8.0, budget / max(1, args.steps + args.warmup)))
+    which, kind, n_s = cpu_reference_sample(dtype, per_step)
+    for _ in range(args.warmup):
+        run_cpu_solver(which, dtype, n_s)
+    times = []
+    for _ in range(args.steps):
+        t, _ = run_cpu_solver(which, dtype, n_s)
+        times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    value = synth.nominal_cells(n_s, cfg["T"]) / (ms * 1e-3)
+    sample = (f"{'unmodified reference DPSolver' if kind == 'reference' else 'oracle port'}"
+              f"<{'double' if dtype == np.float64 else 'float'}> constructor at n={n_s}, T={cfg['T']} "
+              f"(same generator as the headline workload; n=100000 needs {3 * 1e10 * np.dtype(dtype).itemsize / 1e9:.0f} GB of tables)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "C3 sample: Poisson multiple clustering, T=16", "n": n_s, "T": cfg["T"],
+                       "host_cores": os.cpu_count()},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads_used(kind), "kind": kind,
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def measured_peaks():
+    """FP32/FP64/MUFU pipe peaks measured on this device by tools/peaks.cu (built by build())."""
+    exe = os.path.join(ROOT, "partitionsolvers_b200", "_lib", "ps_peaks")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=120).stdout
+        return json.loads(out.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--sum-mode", default="running", choices=["running", "prefix"])
+    ap.add_argument("--no-extras", action="store_true", help="skip variants, replicas and the CPU baseline")
+    ap.add_argument("--skip-peaks", action="store_true", help="do not run the pipe-peak microbenchmark (ncu runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    from partitionsolvers_b200 import capi
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cfg = synth.CONFIGS["C3"]
+    n, T, dist_id, rp = cfg["n"], cfg["T"], cfg["dist"], cfg["risk_part"]
+    sum_mode = capi.PS_SUM_RUNNING if args.sum_mode == "running" else capi.PS_SUM_PREFIX
+    ctx = capi.Context(local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def l2_flush():
+        flush.add_(1)
+        torch.cuda.synchronize()
+
+    def run_variant(dtype_name, steps, warmup, with_e2e=True, sm=sum_mode):
+        npdt = np.float64 if dtype_name == "f64" else np.float32
+        tdt = torch.float64 if dtype_name == "f64" else torch.float32
+        # every rank solves its own instance of the workload (rank-dependent seed)
+        a_h, b_h = synth.poisson_planted(n, 16, seed=synth.SEED + 3 + 1000 * rank, dtype=npdt)
+        a_pin = torch.from_numpy(a_h).pin_memory()
+        b_pin = torch.from_numpy(b_h).pin_memory()
+        a_d, b_d = a_pin.to(dev), b_pin.to(dev)
+        perm_d = torch.empty(n, dtype=torch.int32, device=dev)
+        bounds_d = torch.empty(T + 1, dtype=torch.int32, device=dev)
+        scores_d = torch.empty(T, dtype=tdt, device=dev)
+        perm_pin = torch.empty(n, dtype=torch.int32).pin_memory()
+        bounds_pin = torch.empty(T + 1, dtype=torch.int32).pin_memory()
+        scores_pin = torch.empty(T, dtype=tdt).pin_memory()
+
+        def step_resident():
+            ctx.solve_device(a_d.data_ptr(), b_d.data_ptr(), n, T, dist_id, rp, npdt, sum_mode=sm,
+                             d_perm_out=perm_d.data_ptr(), d_bounds=bounds_d.data_ptr(),
+                             d_scores=scores_d.data_ptr())
+
+        def step_e2e():
+            ctx.solve_into(a_pin.numpy(), b_pin.numpy(), T, dist_id, rp, npdt, perm_out=perm_pin.numpy(),
+                           bounds_out=bounds_pin.numpy(), scores_out=scores_pin.numpy(), sum_mode=sm)
+
+        for _ in range(warmup):
+            step_resident()
+        # ---- resident, device-timed
+        dev_ms, lev_ms, lev_cells, launches = [], [], [], 0
+        stage = {"sort_scan_ms": 0.0, "prepass_ms": 0.0, "levels_ms": 0.0, "backtrace_ms": 0.0}
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            l2_flush()
+            step_resident()
+            tm = ctx.timings()
+            dev_ms.append(tm["total_ms"])
+            lev_ms += tm["level_ms"]
+            lev_cells += tm["level_cells"]
+            launches += tm["kernel_launches"]
+            for k in stage:
+                stage[k] += tm[k] / steps
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - w0) / steps
+        ms = allmax(float(np.mean(dev_ms)))
+        out = {"ms_per_step": ms, "wall_ms_per_step": allmax(wall_ms), "launches": launches,
+               "value": world * synth.nominal_cells(n, T) / (ms * 1e-3),
+               "actual_cells_per_s": world * synth.actual_cells(n, T) / (ms * 1e-3),
+               "level_ms_sum": float(np.sum(lev_ms)), "level_cells_sum": float(np.sum(lev_cells)),
+               "level_launches": len(lev_ms), "stage_ms": stage,
+               "bounds": bounds_d.cpu().numpy().tolist()}
+        if with_e2e:
+            for _ in range(2):
+                step_e2e()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                l2_flush()
+                step_e2e()
+            barrier()
+            e2e_ms = allmax(1e3 * (time.perf_counter() - t0) / steps)
+            tm = ctx.timings()
+            out["e2e"] = {"value": world * synth.nominal_cells(n, T) / (e2e_ms * 1e-3), "unit": UNIT,
+                          "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
+                          "ms_per_step": e2e_ms}
+            assert np.array_equal(bounds_pin.numpy(), np.array(out["bounds"], np.int32)), "e2e and resident differ"
+        return out
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    main_res = run_variant(args.dtype, args.steps, args.warmup)
+    clocks = sampler.stop()
+
+    line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "C3: n=100000, T=16 Poisson multiple clustering, one instance per GPU",
+                       "n": n, "T": T, "score": "Poisson", "objective": "multiple_clustering",
+                       "sum_mode": args.sum_mode, "sort": "device radix (stable)",
+                       "l2": "flushed between timed steps (256 MB write)",
+                       "parallelism": f"{world} independent instance(s), no collective"},
+            "actual_cells_per_s": main_res["actual_cells_per_s"],
+            "wall_ms_per_step": main_res["wall_ms_per_step"], "stage_ms": main_res["stage_ms"],
+            "e2e": main_res["e2e"], "gpu_launches": int(main_res["launches"]), "clocks": clocks}
+
+    peaks = measured_peaks() if (rank == 0 and not args.skip_peaks) else None
+    w = 8 if args.dtype == "f64" else 4
+    flops_cell = ALG_FLOPS_PER_CELL[(dist_id, rp)]
+    lev_s = main_res["level_ms_sum"] * 1e-3
+    achieved = main_res["level_cells_sum"] * flops_cell / lev_s / 1e12
+    if peaks:
+        peak = (peaks["dadd_ops"] if args.dtype == "f64" else peaks["fadd_ops"]) / 1e12
+        peak_src = "measured by tools/peaks.cu on this device: non-fused FP add/mul issue rate (parity forbids FMA contraction of the score)"
+    else:
+        peak = (148 * 64 if args.dtype == "f64" else 148 * 128) * 1.965e9 / 1e12
+        peak_src = "fallback: lanes x 1.965 GHz (ps_peaks binary missing)"
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "level_kernel_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(args.dtype, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    avg_launch_ms = main_res["level_ms_sum"] / max(1, main_res["level_launches"])
+    hbm_peak = 6554.6
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    alg_bytes_per_launch = ALG_HBM_BYTES_PER_ROW(w) * n
+    line["roofline"] = {
+        "kernel": "level_tile_kernel", "bound": "fp64_pipe" if args.dtype == "f64" else "fp32_issue",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "alg_flops_per_cell": flops_cell, "cells_per_launch_avg": main_res["level_cells_sum"] / max(
+            1, main_res["level_launches"]), "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
+        "share_of_step": main_res["level_ms_sum"] / (args.steps * main_res["ms_per_step"]),
+        "hbm": {"alg_bytes_per_launch": alg_bytes_per_launch,
+                "achieved_gbs": alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "note": "not HBM-bound: algorithmic traffic is (4w+4)n bytes per level"},
+        "measured_pipe_peaks": peaks}
+
+    if not args.no_extras:
+        other = "f32" if args.dtype == "f64" else "f64"
+        v = run_variant(other, max(2, args.steps // 2), 3, with_e2e=True)
+        line["variants"] = {other: {"value": v["value"], "ms_per_step": v["ms_per_step"], "e2e": v["e2e"],
+                                    "actual_cells_per_s": v["actual_cells_per_s"]}}
+        vp = run_variant(args.dtype, 2, 3, with_e2e=False,
+                         sm=capi.PS_SUM_PREFIX if sum_mode == capi.PS_SUM_RUNNING else capi.PS_SUM_RUNNING)
+        line["variants"]["other_sum_mode"] = {"value": vp["value"], "ms_per_step": vp["ms_per_step"],
+                                              "same_partition": vp["bounds"] == main_res["bounds"]}
+        # ---- replica workload (BASELINE configs[3]): 4096 x (n=5000, T=8) split over the ranks
+        c4 = synth.CONFIGS["C4"]
+        R_total = c4["replicas"]
+        R_loc = R_total // world + (1 if rank < R_total % world else 0)
+        a4, b4 = synth.poisson_null(c4["n"], seed=synth.SEED + 4 + 1000 * rank, dtype=np.float32, replicas=R_loc)
+        a4p, b4p = torch.from_numpy(a4).pin_memory(), torch.from_numpy(b4).pin_memory()
+        bo = torch.empty((R_loc, c4["T"] + 1), dtype=torch.int32).pin_memory()
+        so = torch.empty((R_loc, c4["T"]), dtype=torch.float32).pin_memory()
+
+        def step_rep():
+            ctx.solve_into(a4p.numpy(), b4p.numpy(), c4["T"], c4["dist"], c4["risk_part"], np.float32,
+                           perm_out=None, bounds_out=bo.numpy(), scores_out=so.numpy())
+        step_rep()
+        barrier()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            step_rep()
+        barrier()
+        rep_s = allmax((time.perf_counter() - t0) / reps)
+        line["mc_replicas"] = {"value": R_total / rep_s, "unit": "replicas/s", "replicas": R_total,
+                               "n": c4["n"], "T": c4["T"], "dtype": "f32", "scaling": "strong",
+                               "seconds_per_pass": rep_s, "includes": "H2D of inputs, D2H of boundaries+scores",
+                               "cells_per_s_nominal": R_total * synth.nominal_cells(c4["n"], c4["T"]) / rep_s}
+        if rank == 0 and world == 1:
+            dtype = np.float64 if args.dtype == "f64" else np.float32
+            which, kind, n_s = cpu_reference_sample(dtype, 10.0)
+            t, _ = run_cpu_solver(which, dtype, n_s)
+            line["cpu_baseline"] = {
+                "value": synth.nominal_cells(n_s, T) / t, "unit": UNIT, "cores": cpu_threads_used(kind),
+                "kind": kind, "host_cores": os.cpu_count(),
+                "sample": f"one {'reference DPSolver' if kind == 'reference' else 'oracle port'} solve at n={n_s}, "
+                          f"T={T}, {args.dtype}, same generator ({t:.2f} s); the reference cannot allocate n=100000"}
+            try:
+                from oracle import oracle_py as O
+                n_p = 20000
+                ap_, bp_ = cfg["gen"](dtype, n_p)
+                tp, _ = O.time_solve("port", ap_, bp_, T, dist_id, rp, dtype=dtype, nthreads=0)
+                line["cpu_baseline_all_cores"] = {
+                    "value": synth.nominal_cells(n_p, T) / tp, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"streaming oracle port, all host threads, n={n_p}, T={T} ({tp:.2f} s)"}
+            except Exception as e:  # the port is optional extra context
+                line["cpu_baseline_all_cores"] = {"error": str(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,8 +74,18 @@ def build_proto(force=False):
     return target
 
 
+def build_peaks(force=False):
+    """tools/peaks.cu: pipe-rate microbenchmarks bench.py uses as roofline denominators."""
+    src = os.path.join(ROOT, "tools", "peaks.cu")
+    target = os.path.join(LIBDIR, "ps_peaks")
+    if force or _newer(target, [src]):
+        subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
+                        "-fmad=false", "-w", "-o", target, src], check=True)
+    return target
+
+
 def build_all(force=False, verbose=False):
-    out = [build_cuda(force, verbose)]
+    out = [build_cuda(force, verbose), build_peaks(force)]
     p = build_proto(force)
     if p:
         out.append(p)

@@ -183,6 +183,20 @@ class Context:
                     out[k] = out[k][0]
         return out
 
+    def solve_into(self, a, b, T, dist, risk_part, dtype, perm_out=None, bounds_out=None, scores_out=None,
+                   sum_mode=PS_SUM_RUNNING, sweep=False, chunk_len=0):
+        """Host-buffer call that writes into caller-provided numpy arrays (e.g. views of pinned memory);
+        nothing is allocated here, so the call is exactly the ABI call plus its copies."""
+        batched = a.ndim == 2
+        R = a.shape[0] if batched else 1
+        n = a.shape[-1]
+        p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode, sort_mode=PS_SORT_DEVICE,
+                      perm=None, sweep=int(sweep), batch=R, on_device=0, tile_rows=0, chunk_len=chunk_len)
+        r = PsResult(perm=_vp(perm_out), bounds=_vp(bounds_out), subset_scores=_vp(scores_out), max_score=None,
+                     next_start=None)
+        fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
+        self._check(fn(self._h, C.byref(p), _vp(a), _vp(b), C.byref(r)))
+
     def solve_device(self, d_a, d_b, n, T, dist, risk_part, dtype, R=1, sum_mode=PS_SUM_RUNNING, sweep=False,
                      d_perm_out=0, d_bounds=0, d_scores=0, d_perm_in=0, chunk_len=0):
         """Device-pointer call (inputs resident in HBM; integers are raw device addresses)."""
