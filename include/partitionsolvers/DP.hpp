@@ -1,0 +1,307 @@
+// partitionsolvers/DP.hpp -- host facade with the reference's DPSolver surface over the B200 engine.
+//
+// Same class template, constructors, default arguments and getters as the reference's
+// src/cpp/include/DP.hpp:35-198, so code written against it (python_dpsolver.cpp, the demos, the gtest
+// suite) compiles unchanged.  The constructor is the solve, as in the reference (DP.hpp:194-197):
+//   create()    sort_by_priority + range scores + DP fill   -> ONE call into the C ABI (ps_b200.h)
+//   optimize()  backtrace(s)                                -> boundaries and subset scores come back from
+//                                                              the device; the O(n+T) rest is done here
+// Host-side pieces and the reference lines they follow:
+//   build_partition   DP_impl.hpp:122-153   subsets from the sort index, objective accumulated in DataType,
+//                                           regulariser gamma*pow(S,reg_power) in double
+//   reorder           DP_impl.hpp:232-259   multiple clustering only: stable sort by ascending subset score
+//   sweep / OLS       DP_impl.hpp:200-230, 155-198 (OLS restated as closed-form least squares in float; the
+//                                           reference uses Eigen's colPivHouseholderQr on the same data)
+//   getters           DP_impl.hpp:261-294   incl. get_optimal_score_extern's multiple-clustering quirk
+// There is no CPU solver behind this class: without a CUDA device the constructor throws.
+#ifndef PARTITIONSOLVERS_DP_HPP
+#define PARTITIONSOLVERS_DP_HPP
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <limits>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../ps_b200.h"
+
+enum class objective_fn { Gaussian = 0, Poisson = 1, RationalScore = 2 };  // score.hpp:20-22
+
+struct distributionException : public std::exception {  // LTSS.hpp:21-25
+  const char* what() const throw() { return "Bad distributional assignment"; }
+};
+
+namespace partitionsolvers {
+
+struct engine_error : public std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// One lazily created engine context per host thread: solvers may be constructed concurrently from pool
+// threads (python_dpsolver.cpp:275-301) and from fork()ed workers (solverSWIG_DP.py:152-167).
+class ThreadContext {
+ public:
+  static ps_ctx* get() {
+    static thread_local ThreadContext tc;
+    if (!tc.ctx_) {
+      ps_status st = ps_create(&tc.ctx_, -1);
+      if (st != PS_OK) throw engine_error(std::string("ps_create: ") + ps_status_string(st));
+    }
+    return tc.ctx_;
+  }
+  ~ThreadContext() {
+    if (ctx_) ps_destroy(ctx_);
+  }
+
+ private:
+  ps_ctx* ctx_ = nullptr;
+};
+
+inline ps_status solve(ps_ctx* c, const ps_problem* p, const float* a, const float* b, ps_result* r) {
+  return ps_solve_f32(c, p, a, b, r);
+}
+inline ps_status solve(ps_ctx* c, const ps_problem* p, const double* a, const double* b, ps_result* r) {
+  return ps_solve_f64(c, p, a, b, r);
+}
+
+inline bool env_flag(const char* name) {
+  const char* v = std::getenv(name);
+  return v && *v && std::strcmp(v, "0") != 0;
+}
+
+// DP_impl.hpp:155-198 without Eigen.  scores[0..T], scores[0] = 0.
+template <typename DataType>
+int ols_num_clusters(const std::vector<DataType>& scores) {
+  const int m = static_cast<int>(scores.size()) - 2;
+  if (m <= 0) return 1;
+  std::vector<float> x(m), y(m);
+  for (int i = 0; i < m; ++i) {
+    DataType xv = static_cast<DataType>(i + 3);
+    DataType dv = scores[i + 2] - scores[i + 1];
+    x[i] = static_cast<float>(std::log(xv));
+    y[i] = static_cast<float>(std::log(dv));
+  }
+  double sx = 0, sy = 0, sxx = 0, sxy = 0;
+  for (int i = 0; i < m; ++i) {
+    sx += x[i];
+    sy += y[i];
+    sxx += static_cast<double>(x[i]) * x[i];
+    sxy += static_cast<double>(x[i]) * y[i];
+  }
+  const double den = m * sxx - sx * sx;
+  float b0, b1;
+  if (den != 0) {
+    b0 = static_cast<float>((m * sxy - sx * sy) / den);
+    b1 = static_cast<float>((sy - static_cast<double>(b0) * sx) / m);
+  } else {
+    const double nrm = static_cast<double>(x[0]) * x[0] + 1.0;
+    b0 = static_cast<float>(x[0] * y[0] / nrm);
+    b1 = static_cast<float>(y[0] / nrm);
+  }
+  int best = 0;
+  DataType minres = std::numeric_limits<DataType>::max();
+  for (int i = 0; i < m; ++i) {
+    float r = y[i] - b0 * x[i] - b1 * 1.f;
+    if (r < minres) {
+      best = i;
+      minres = r;
+    }
+  }
+  return best + 1;
+}
+
+}  // namespace partitionsolvers
+
+template <typename DataType>
+class DPSolver {
+  using all_scores = std::pair<std::vector<std::vector<int> >, DataType>;
+  using all_part_scores = std::vector<all_scores>;
+
+ public:
+  DPSolver() = default;
+
+  DPSolver(int n, int T, const std::vector<DataType>& a, const std::vector<DataType>& b,
+           objective_fn parametric_dist = objective_fn::Gaussian, bool risk_partitioning_objective = false,
+           bool use_rational_optimization = true, DataType gamma = 0., int reg_power = 1.,
+           bool sweep_down = false, bool find_optimal_t = false)
+      : n_{n}, T_{T}, a_{a}, b_{b}, optimal_score_{0.}, parametric_dist_{parametric_dist},
+        risk_partitioning_objective_{risk_partitioning_objective},
+        use_rational_optimization_{use_rational_optimization}, gamma_{gamma}, reg_power_{reg_power},
+        sweep_down_{sweep_down}, find_optimal_t_{find_optimal_t}, optimal_num_clusters_OLS_{0} {
+    _init();
+  }
+
+  DPSolver(int n, int T, std::vector<DataType>&& a, std::vector<DataType>&& b,
+           objective_fn parametric_dist = objective_fn::Gaussian, bool risk_partitioning_objective = false,
+           bool use_rational_optimization = true, DataType gamma = 0., int reg_power = 1.,
+           bool sweep_down = false, bool find_optimal_t = false)
+      : n_{n}, T_{T}, a_{std::move(a)}, b_{std::move(b)}, optimal_score_{0.}, parametric_dist_{parametric_dist},
+        risk_partitioning_objective_{risk_partitioning_objective},
+        use_rational_optimization_{use_rational_optimization}, gamma_{gamma}, reg_power_{reg_power},
+        sweep_down_{sweep_down}, find_optimal_t_{find_optimal_t}, optimal_num_clusters_OLS_{0} {
+    _init();
+  }
+
+  DPSolver(const std::vector<DataType>& a, const std::vector<DataType>& b, int T,
+           objective_fn parametric_dist = objective_fn::Gaussian, bool risk_partitioning_objective = false,
+           bool use_rational_optimization = true, DataType gamma = 0., int reg_power = 1.,
+           bool sweep_down = false, bool find_optimal_t = false)
+      : n_{static_cast<int>(a.size())}, T_{T}, a_{a}, b_{b}, optimal_score_{0.},
+        parametric_dist_{parametric_dist}, risk_partitioning_objective_{risk_partitioning_objective},
+        use_rational_optimization_{use_rational_optimization}, gamma_{gamma}, reg_power_{reg_power},
+        sweep_down_{sweep_down}, find_optimal_t_{find_optimal_t}, optimal_num_clusters_OLS_{0} {
+    _init();
+  }
+
+  DPSolver(std::vector<DataType>&& a, std::vector<DataType>&& b, int T,
+           objective_fn parametric_dist = objective_fn::Gaussian, bool risk_partitioning_objective = false,
+           bool use_rational_optimization = true, DataType gamma = 0, int reg_power = 1.,
+           bool sweep_down = false, bool find_optimal_t = false)
+      : n_{static_cast<int>(a.size())}, T_{T}, a_{std::move(a)}, b_{std::move(b)}, optimal_score_{0.},
+        parametric_dist_{parametric_dist}, risk_partitioning_objective_{risk_partitioning_objective},
+        use_rational_optimization_{use_rational_optimization}, gamma_{gamma}, reg_power_{reg_power},
+        sweep_down_{sweep_down}, find_optimal_t_{find_optimal_t}, optimal_num_clusters_OLS_{0} {
+    _init();
+  }
+
+  std::vector<std::vector<int> > get_optimal_subsets_extern() const { return subsets_; }
+
+  DataType get_optimal_score_extern() const {  // DP_impl.hpp:267-276
+    if (risk_partitioning_objective_) return optimal_score_;
+    double acc = 0.;
+    for (size_t q = 1; q < score_by_subset_.size(); ++q) acc += score_by_subset_[q];
+    return static_cast<DataType>(acc - gamma_ * std::pow(T_, reg_power_));
+  }
+
+  std::vector<DataType> get_score_by_subset_extern() const { return score_by_subset_; }
+  all_part_scores get_all_subsets_and_scores_extern() const { return subsets_and_scores_; }
+  int get_optimal_num_clusters_OLS_extern() const { return optimal_num_clusters_OLS_; }
+
+  // beyond the reference: what the engine measured for this construction (CUDA events)
+  const ps_timings& engine_timings() const { return timings_; }
+  const std::vector<int>& priority_sortind() const { return priority_sortind_; }
+
+ private:
+  int n_ = 0;
+  int T_ = 0;
+  std::vector<DataType> a_;
+  std::vector<DataType> b_;
+  std::vector<int> priority_sortind_;
+  DataType optimal_score_ = 0;
+  std::vector<std::vector<int> > subsets_;
+  std::vector<DataType> score_by_subset_;
+  objective_fn parametric_dist_ = objective_fn::Gaussian;
+  bool risk_partitioning_objective_ = false;
+  bool use_rational_optimization_ = true;  // accepted, never read by any arithmetic (as in the reference)
+  DataType gamma_ = 0;
+  int reg_power_ = 1;
+  bool sweep_down_ = false;
+  bool find_optimal_t_ = false;
+  all_part_scores subsets_and_scores_;
+  int optimal_num_clusters_OLS_ = 0;
+  ps_timings timings_{};
+
+  all_scores build_partition(int S, const int* bounds, const DataType* scores) {  // DP_impl.hpp:122-153
+    std::vector<std::vector<int> > subsets(S);
+    std::vector<DataType> sc(S, 0.);
+    DataType optimal = 0.;
+    for (int t = 0; t < S; ++t) {
+      const int lo = bounds[t], hi = bounds[t + 1];
+      if (lo >= 0 && hi >= lo && hi <= n_)
+        subsets[t].assign(priority_sortind_.begin() + lo, priority_sortind_.begin() + hi);
+      sc[t] = scores[t];
+      optimal += sc[t];
+    }
+    if (!risk_partitioning_objective_) {  // reorder_subsets, DP_impl.hpp:232-259
+      std::vector<int> ind(S);
+      std::iota(ind.begin(), ind.end(), 0);
+      std::stable_sort(ind.begin(), ind.end(), [&sc](int i, int j) { return sc[i] < sc[j]; });
+      std::vector<std::vector<int> > ss(S);
+      std::vector<DataType> sv(S);
+      for (int q = 0; q < S; ++q) {
+        ss[q].swap(subsets[ind[q]]);
+        sv[q] = sc[ind[q]];
+      }
+      subsets.swap(ss);
+      sc.swap(sv);
+    }
+    optimal -= gamma_ * std::pow(S, reg_power_);
+    if (S == T_) score_by_subset_ = sc;
+    return all_scores{subsets, optimal};
+  }
+
+  void _init() {
+    using namespace partitionsolvers;
+    n_ = (n_ <= static_cast<int>(a_.size())) ? n_ : static_cast<int>(a_.size());  // DP_impl.hpp:35
+    T_ = (T_ <= n_) ? T_ : n_;                                                    // DP_impl.hpp:38
+    const int dist = static_cast<int>(parametric_dist_);
+    if (dist < 0 || dist > 2) throw distributionException();  // DP_impl.hpp:62-64
+    if (n_ < 1 || T_ < 1) throw engine_error("DPSolver: n and T must be >= 1");
+    const bool sweep = sweep_down_ || find_optimal_t_;
+
+    ps_problem p;
+    std::memset(&p, 0, sizeof(p));
+    p.n = n_;
+    p.T = T_;
+    p.dist = dist;
+    p.risk_part = risk_partitioning_objective_ ? 1 : 0;
+    p.sum_mode = env_flag("PARTITIONSOLVERS_PREFIX_SUMS") ? PS_SUM_PREFIX : PS_SUM_RUNNING;
+    p.sweep = sweep ? 1 : 0;
+    p.batch = 1;
+    priority_sortind_.assign(n_, 0);
+    std::vector<int> host_perm;
+    if (env_flag("PARTITIONSOLVERS_HOST_SORT")) {
+      // parity mode: std::sort with the reference's comparator (DP_impl.hpp:13-16) so that tied priorities
+      // land exactly where the reference leaves them
+      host_perm.resize(n_);
+      std::iota(host_perm.begin(), host_perm.end(), 0);
+      const std::vector<DataType>&a = a_, &b = b_;
+      std::sort(host_perm.begin(), host_perm.end(), [&a, &b](int i, int j) { return (a[i] / b[i]) < (a[j] / b[j]); });
+      p.sort_mode = PS_SORT_GIVEN;
+      p.perm = host_perm.data();
+    }
+    const int nS = sweep ? T_ + 1 : 1;
+    std::vector<int> bounds(static_cast<size_t>(nS) * (T_ + 1));
+    std::vector<DataType> sc(static_cast<size_t>(nS) * T_);
+    ps_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.perm = priority_sortind_.data();
+    r.bounds = bounds.data();
+    r.subset_scores = sc.data();
+    ps_ctx* ctx = ThreadContext::get();
+    ps_status st = solve(ctx, &p, a_.data(), b_.data(), &r);
+    if (st == PS_ERR_DIST) throw distributionException();
+    if (st != PS_OK) throw engine_error(std::string("ps_solve: ") + ps_last_error(ctx));
+    ps_get_timings(ctx, &timings_);
+
+    // create() defaults, DP_impl.hpp:86-87
+    subsets_ = std::vector<std::vector<int> >(T_, std::vector<int>());
+    score_by_subset_ = std::vector<DataType>(T_, 0.);
+    optimal_score_ = 0.;
+    if (sweep) {  // optimize(), DP_impl.hpp:203-224
+      subsets_and_scores_ = all_part_scores{static_cast<size_t>(T_ + 1)};
+      for (int S = T_; S >= 1; --S)
+        subsets_and_scores_[S] = build_partition(S, &bounds[static_cast<size_t>(S) * (T_ + 1)],
+                                                 &sc[static_cast<size_t>(S) * T_]);
+      if (find_optimal_t_) {
+        std::vector<DataType> s(T_ + 1);
+        for (int S = 0; S <= T_; ++S) s[S] = subsets_and_scores_[S].second;
+        optimal_num_clusters_OLS_ = ols_num_clusters<DataType>(s);
+        subsets_ = subsets_and_scores_[optimal_num_clusters_OLS_].first;
+        optimal_score_ = subsets_and_scores_[optimal_num_clusters_OLS_].second;
+      }
+    } else {
+      all_scores opt = build_partition(T_, bounds.data(), sc.data());
+      subsets_ = opt.first;
+      optimal_score_ = opt.second;
+    }
+  }
+};
+
+#endif  // PARTITIONSOLVERS_DP_HPP

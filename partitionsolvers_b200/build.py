@@ -84,11 +84,26 @@ def build_peaks(force=False):
     return target
 
 
+def build_facade_test(force=False):
+    """tests/cpp/test_facade.cpp: the reference's gtest cases against the C++ facade (run by pytest -m gpu)."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_facade.cpp")
+    if not os.path.exists(src):
+        return None
+    target = os.path.join(LIBDIR, "test_facade")
+    srcs = [src] + _sources(HOSTSRC, (".cpp", ".hpp")) + _sources(INCLUDE, (".h", ".hpp"))
+    if force or _newer(target, srcs):
+        cxx = os.environ.get("CXX", "g++")
+        subprocess.run([cxx, "-O2", "-std=c++17", "-I", INCLUDE, src, os.path.join(HOSTSRC, "python_dpsolver.cpp"),
+                        "-L", LIBDIR, "-lps_b200", "-Wl,-rpath,$ORIGIN", "-pthread", "-o", target], check=True)
+    return target
+
+
 def build_all(force=False, verbose=False):
     out = [build_cuda(force, verbose), build_peaks(force)]
-    p = build_proto(force)
-    if p:
-        out.append(p)
+    for fn in (build_proto, build_facade_test):
+        p = fn(force)
+        if p:
+            out.append(p)
     return out
 
 

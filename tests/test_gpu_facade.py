@@ -1,0 +1,70 @@
+"""GPU tests of the reference-facing surfaces: the C++ facade (the reference's gtest cases, re-expressed in
+tests/cpp/test_facade.cpp) and the pybind11 `proto` module called exactly as solverSWIG_DP.OptimizerSWIG
+calls the SWIG one (src/python/solverSWIG_DP.py:57-97)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from partitionsolvers_b200 import host, synth
+
+pytestmark = pytest.mark.gpu
+
+LIBDIR = os.path.join(ROOT, "partitionsolvers_b200", "_lib")
+
+
+def test_cpp_facade_reference_gtest_cases():
+    exe = os.path.join(LIBDIR, "test_facade")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    env = dict(os.environ, LD_LIBRARY_PATH=LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
+@pytest.fixture(scope="module")
+def proto():
+    sys.path.insert(0, LIBDIR)
+    import proto as p
+    return p
+
+
+def test_proto_optimize_one_matches_python_mirror(proto, ctx):
+    a, b = synth.poisson_planted(1000, 5, seed=31, dtype=np.float32)
+    for dist, rp in ((1, False), (1, True), (0, True), (2, False)):
+        subsets, score = proto.optimize_one__DP(1000, 5, a.tolist(), b.tolist(), dist, rp, False, 0.0, 1)
+        s = host.DPSolver(1000, 5, a, b, dist, rp, dtype=np.float32, ctx=ctx)
+        assert isinstance(subsets, tuple) and isinstance(subsets[0], tuple)
+        assert [list(x) for x in subsets] == s.get_optimal_subsets_extern()
+        assert np.float32(score) == s.get_optimal_score_extern()
+
+
+def test_proto_sweeps_and_ols(proto, ctx):
+    rs = np.random.RandomState(0xC0FFEE3 % (2 ** 31))
+    n = 2000
+    b = rs.uniform(90, 110, n)
+    a = rs.normal(np.repeat([0.25, 0.75, 1.25, 1.75], n // 4) * b, 1.0)
+    allp, t = proto.compute_optimal_num_clusters_OLS_all(n, 12, a.tolist(), b.tolist(), 2, True, False, 0.0, 1)
+    assert t == 4 and len(allp) == 13 and all(len(allp[S][0]) == S for S in range(13))
+    assert proto.compute_optimal_num_clusters_OLS(n, 12, a.tolist(), b.tolist(), 2, True, False) == 4
+    sw = proto.optimize_all__DP(n, 6, a.tolist(), b.tolist(), 2, True, False, 0.0, 1)
+    par = proto.sweep_parallel__DP(n, 6, a.tolist(), b.tolist(), 2, True, False, 0.0, 1)
+    for S in range(1, 7):
+        assert par[S] == sw[S]
+    best = proto.sweep_best__DP(n, 6, a.tolist(), b.tolist(), 2, True, False, 0.0, 1)
+    assert best[1] == max(sw[S][1] for S in range(2, 7))
+    ols = proto.sweep_best_OLS__DP(n, 12, a.tolist(), b.tolist(), 2, True, False, 0.0, 1)
+    assert len(ols[0]) == 4
+    assert proto.find_optimal_partition__DP(n, 3, a.tolist(), b.tolist(), 2, True, False) == sw[3][0]
+    assert proto.find_optimal_score__DP(n, 3, a.tolist(), b.tolist(), 2, True, False) == sw[3][1]
+
+
+def test_proto_compute_score_and_errors(proto, oracle):
+    a, b = synth.uniform_ab(300, seed=2, dtype=np.float32)
+    got = proto.compute_score(a.tolist(), b.tolist(), 2, False, False)
+    assert np.float32(got) == oracle.range_score(a, b, 2, False, 0, 300, dtype=np.float32)
+    with pytest.raises(proto.distributionException):
+        proto.optimize_one__DP(300, 3, a.tolist(), b.tolist(), 5, True, False)

@@ -1,0 +1,49 @@
+"""GPU test of the row-sharded building blocks (ps_shard_*): a world of 2 and 3 ranks emulated on ONE device
+(the ranks' kernels run one after another, the all-gather is a concatenation), compared bit-for-bit with the
+unsharded solve.  The NCCL all-gather itself is exercised by bench.py --workload sharded on a multi-GPU box."""
+import numpy as np
+import pytest
+
+from partitionsolvers_b200 import capi, multigpu, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_sharded_levels_equal_unsharded(ctx, world, dt):
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    n, T, dist_id, rp = 3000, 6, 1, False
+    a, b = synth.poisson_planted(n, 6, seed=41, dtype=dt)
+    full = ctx.solve_raw(a, b, T, dist_id, rp, dtype=dt, levels=True)
+    engines = [multigpu.CudaShardEngine(ctx, dev) for _ in range(world)]
+    perm, a_s, b_s = engines[0].sort(a, b, dt)
+    assert np.array_equal(perm, full["perm"])
+    for r, e in enumerate(engines):
+        e.create(a_s, b_s, n, T, dist_id, rp, dt, r, world)
+    chunks = [e.new_chunk() for e in engines]
+
+    def exchange():
+        g = torch.cat(chunks)
+        return g, multigpu.natural_from_gathered(g.cpu().numpy(), n, world, engines[0].chunk_rows)
+
+    for e, c in zip(engines, chunks):
+        e.level1(c)
+    g, nat = exchange()
+    assert np.array_equal(nat, full["max_score"][1])
+    for j in range(2, T + 1):
+        for e, c in zip(engines, chunks):
+            e.set_prev(g)
+            e.level(j, c)
+        g, nat = exchange()
+        nrows = 1 if j == T else n - j + 1
+        assert np.array_equal(nat[:nrows], full["max_score"][j][:nrows]), j
+        for i in (0, 1, 127, 128, 129, 255, 256, nrows - 1):
+            if i < nrows:
+                own = multigpu.owner_of_row(i, world)
+                assert engines[own].next_start(j, i) == full["next_start"][j][i]
+                if own != 0:
+                    assert engines[0].next_start(j, i) == -2
+    for e in engines:
+        e.close()
