@@ -67,7 +67,7 @@ typedef struct ps_problem {
   int sweep;       /* 0: backtrace S=T only (DP_impl.hpp:226-228); 1: every S=T..1 (:203-214)         */
   int batch;       /* independent instances R>=1 (replicas); a,b are [R][n] row-major                 */
   int on_device;   /* 1: a, b, perm AND every ps_result pointer are device pointers on ctx's device   */
-  int tile_rows;   /* tuning, 0 = default                                                             */
+  int no_fast_math;   /* debug: 1 = never take the range-prechecked branch-free math path (csrc/math_fast.cuh) */
   int chunk_len;   /* tuning, 0 = default                                                             */
 } ps_problem;
 
@@ -130,6 +130,12 @@ ps_status ps_range_score_f32(ps_ctx* ctx, int n, const float* a, const float* b,
                              float* out);
 ps_status ps_range_score_f64(ps_ctx* ctx, int n, const double* a, const double* b, int dist, int risk_part,
                              double* out);
+
+/* Self-test of the branch-free division / logarithm used when a per-instance precheck proves the inputs
+ * well-scaled (csrc/math_fast.cuh): draws `samples` random operands in the safe range on the device and
+ * counts those where the routine differs from the CUDA math library.  which: 0 fdiv, 1 logf, 2 ddiv, 3 log. */
+ps_status ps_selftest_math(ps_ctx* ctx, int which, long long samples, unsigned long long seed,
+                           long long* mismatches);
 
 /* ---- row-sharded single instance: building blocks driven by a multi-process host ----
  * Rank `rank` of `world` owns row blocks rb with rb % world == rank.  The caller (one process per GPU)

@@ -25,14 +25,14 @@ ABI_SYMBOLS = [
     "ps_stream", "ps_solve_f32", "ps_solve_f64", "ps_get_timings", "ps_range_score_f32",
     "ps_range_score_f64", "ps_shard_create_f64", "ps_shard_create_f32", "ps_shard_chunk_rows",
     "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",
-    "ps_shard_destroy",
+    "ps_shard_destroy", "ps_selftest_math",
 ]
 
 
 class PsProblem(C.Structure):
     _fields_ = [("n", C.c_int), ("T", C.c_int), ("dist", C.c_int), ("risk_part", C.c_int),
                 ("sum_mode", C.c_int), ("sort_mode", C.c_int), ("perm", C.c_void_p), ("sweep", C.c_int),
-                ("batch", C.c_int), ("on_device", C.c_int), ("tile_rows", C.c_int), ("chunk_len", C.c_int)]
+                ("batch", C.c_int), ("on_device", C.c_int), ("no_fast_math", C.c_int), ("chunk_len", C.c_int)]
 
 
 class PsResult(C.Structure):
@@ -97,6 +97,7 @@ def load():
         L.ps_shard_owner.argtypes = [C.c_void_p, C.c_int]
         L.ps_shard_destroy.argtypes = [C.c_void_p]
         L.ps_shard_destroy.restype = None
+        L.ps_selftest_math.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
 
@@ -150,7 +151,7 @@ class Context:
                     kernel_launches=t.kernel_launches, h2d_bytes=t.h2d_bytes, d2h_bytes=t.d2h_bytes)
 
     def solve_raw(self, a, b, T, dist, risk_part, dtype=np.float32, sum_mode=PS_SUM_RUNNING, perm=None,
-                  sweep=False, levels=False, chunk_len=0, want_perm=True):
+                  sweep=False, levels=False, chunk_len=0, want_perm=True, no_fast=False):
         """Host-buffer call.  a, b: [n] or [R, n].  Returns the raw ABI outputs as numpy arrays."""
         a = np.ascontiguousarray(a, dtype=dtype)
         b = np.ascontiguousarray(b, dtype=dtype)
@@ -162,7 +163,7 @@ class Context:
         nS = Tc + 1 if sweep else 1
         p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode,
                       sort_mode=PS_SORT_GIVEN if perm is not None else PS_SORT_DEVICE, perm=None,
-                      sweep=int(sweep), batch=R, on_device=0, tile_rows=0, chunk_len=chunk_len)
+                      sweep=int(sweep), batch=R, on_device=0, no_fast_math=int(no_fast), chunk_len=chunk_len)
         if perm is not None:
             perm = np.ascontiguousarray(perm, dtype=np.int32).reshape(R, n)
             p.perm = perm.ctypes.data
@@ -191,7 +192,7 @@ class Context:
         R = a.shape[0] if batched else 1
         n = a.shape[-1]
         p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode, sort_mode=PS_SORT_DEVICE,
-                      perm=None, sweep=int(sweep), batch=R, on_device=0, tile_rows=0, chunk_len=chunk_len)
+                      perm=None, sweep=int(sweep), batch=R, on_device=0, no_fast_math=0, chunk_len=chunk_len)
         r = PsResult(perm=_vp(perm_out), bounds=_vp(bounds_out), subset_scores=_vp(scores_out), max_score=None,
                      next_start=None)
         fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
@@ -202,11 +203,16 @@ class Context:
         """Device-pointer call (inputs resident in HBM; integers are raw device addresses)."""
         p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode,
                       sort_mode=PS_SORT_GIVEN if d_perm_in else PS_SORT_DEVICE, perm=d_perm_in or None,
-                      sweep=int(sweep), batch=R, on_device=1, tile_rows=0, chunk_len=chunk_len)
+                      sweep=int(sweep), batch=R, on_device=1, no_fast_math=0, chunk_len=chunk_len)
         r = PsResult(perm=d_perm_out or None, bounds=d_bounds or None, subset_scores=d_scores or None,
                      max_score=None, next_start=None)
         fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
         self._check(fn(self._h, C.byref(p), C.c_void_p(d_a), C.c_void_p(d_b), C.byref(r)))
+
+    def selftest_math(self, which, samples, seed=1):
+        out = C.c_longlong(-1)
+        self._check(self.lib.ps_selftest_math(self._h, which, samples, seed, C.byref(out)))
+        return out.value
 
     def range_score(self, a, b, dist, risk_part, dtype=np.float32):
         a = np.ascontiguousarray(a, dtype=dtype)

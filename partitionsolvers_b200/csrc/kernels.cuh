@@ -71,7 +71,7 @@ __host__ __device__ inline int geom_count_tiles(int NRB_total_hint, int NCH, int
 // ---------------------------------------------------------------------------------------------
 // One (row block, k-chunk) tile of one level.
 // ---------------------------------------------------------------------------------------------
-template <typename D, int DIST, bool RP, bool RUNNING, int BR>
+template <typename D, int DIST, bool RP, bool RUNNING, bool FAST, int BR>
 __global__ void __launch_bounds__(BR)
 level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__ SA,
                   const D* __restrict__ SB, D* __restrict__ part_val, int* __restrict__ part_arg) {
@@ -157,7 +157,7 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
             A = sub_rn<D>(r.x, Xi);
             B = sub_rn<D>(r.y, Yi);
           }
-          const D v = add_rn<D>(ScoreFn<D, DIST, RP>::eval(A, B), r.p);
+          const D v = add_rn<D>(ScoreFn<D, DIST, RP, FAST>::eval(A, B), r.p);
           if (v > best) {
             best = v;
             arg = kb + kk;
@@ -173,7 +173,7 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
             A = sub_rn<D>(r.x, Xi);
             B = sub_rn<D>(r.y, Yi);
           }
-          const D v = add_rn<D>(ScoreFn<D, DIST, RP>::eval(A, B), r.p);
+          const D v = add_rn<D>(ScoreFn<D, DIST, RP, FAST>::eval(A, B), r.p);
           if (v > best) {
             best = v;
             arg = kb + kk;
@@ -193,7 +193,7 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
             A = sub_rn<D>(r.x, Xi);
             B = sub_rn<D>(r.y, Yi);
           }
-          const D v = add_rn<D>(ScoreFn<D, DIST, RP>::eval(A, B), r.p);
+          const D v = add_rn<D>(ScoreFn<D, DIST, RP, FAST>::eval(A, B), r.p);
           if (v > best) {
             best = v;
             arg = k;
@@ -364,6 +364,26 @@ __global__ void gather_kernel(long long total, int n, const int* __restrict__ pe
   bs[g] = b[base + p];
 }
 
+// Safe-range precheck for the FAST kernels (math_fast.cuh): flags[0] |= 1 if some element falls outside
+// "b in [2^-30, 2^30] and |a| in {0} U [2^-30, 2^30]"; flags[0] |= 2 if some a <= 0 (Poisson additionally
+// needs strictly positive sums).  NaNs fail every comparison and set bit 0.
+template <typename D>
+__global__ void range_check_kernel(long long total, const D* __restrict__ a, const D* __restrict__ b,
+                                   int* __restrict__ flags) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int f = 0;
+  if (g < total) {
+    const D lo = (D)9.313225746154785e-10, hi = (D)1073741824.0;  // 2^-30, 2^30
+    const D av = a[g], bv = b[g];
+    const D aa = av < 0 ? -av : av;
+    if (!(bv >= lo && bv <= hi)) f |= 1;
+    if (!(aa == 0 || (aa >= lo && aa <= hi))) f |= 1;
+    if (!(av > 0)) f |= 2;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
 // RUNNING records: rec[k] = {a[k-1], b[k-1]}; both level buffers.
 template <typename D>
 __global__ void build_rec_running_kernel(int n, long long rec_stride, const D* __restrict__ as,
@@ -526,6 +546,48 @@ __global__ void range_score_kernel(int n, int dist, int rp, const D* __restrict_
     B = add_rn<D>(B, b[k]);
   }
   *out = score_dyn<D>(dist, rp, A, B);
+}
+
+// Self-test of math_fast.cuh: counts operands (uniform in log-space over the safe range) on which the
+// branch-free routine differs from the CUDA math library.  which: 0 fdiv, 1 logf, 2 ddiv, 3 log.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& s) {
+  unsigned long long z = (s += 0x9e3779b97f4a7c15ULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float rand_safe_f32(unsigned long long& s, int emin, int emax) {
+  const unsigned long long r = splitmix64(s);
+  const int e = emin + (int)((r >> 40) % (unsigned)(emax - emin + 1));
+  return __int_as_float(((e + 127) << 23) | (int)(r & 0x7fffff));
+}
+__device__ __forceinline__ double rand_safe_f64(unsigned long long& s, int emin, int emax) {
+  const unsigned long long r = splitmix64(s);
+  const unsigned long long r2 = splitmix64(s);
+  const long long e = emin + (long long)((r >> 40) % (unsigned)(emax - emin + 1));
+  return __longlong_as_double(((e + 1023) << 52) | (long long)(r2 & 0xfffffffffffffULL));
+}
+__global__ void selftest_math_kernel(int which, long long per_thread, unsigned long long seed,
+                                     unsigned long long* __restrict__ mismatches) {
+  unsigned long long s = seed + 0x632be59bd9b4e019ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  unsigned long long bad = 0;
+  for (long long it = 0; it < per_thread; ++it) {
+    if (which == 0) {
+      const float a = rand_safe_f32(s, -30, 60), b = rand_safe_f32(s, -30, 60);
+      bad += __float_as_int(fast_fdiv(a, b)) != __float_as_int(__fdiv_rn(a, b));
+    } else if (which == 1) {
+      // half the samples near 1 (the common case for rate ratios), half over the whole quotient range
+      const float x = (it & 1) ? rand_safe_f32(s, -1, 0) : rand_safe_f32(s, -90, 90);
+      bad += __float_as_int(fast_logf(x)) != __float_as_int(logf(x));
+    } else if (which == 2) {
+      const double a = rand_safe_f64(s, -30, 60), b = rand_safe_f64(s, -30, 60);
+      bad += __double_as_longlong(fast_ddiv(a, b)) != __double_as_longlong(__ddiv_rn(a, b));
+    } else {
+      const double x = (it & 1) ? rand_safe_f64(s, -1, 0) : rand_safe_f64(s, -90, 90);
+      bad += __double_as_longlong(fast_log(x)) != __double_as_longlong(log(x));
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
 }
 
 // Sharded runs: scatter the all-gathered [world][chunk] level values back to natural row order

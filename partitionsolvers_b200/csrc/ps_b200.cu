@@ -43,6 +43,8 @@ struct ps_ctx {
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
   long long launches = 0;
+  int* pinned_flags = nullptr;
+  int last_fast = 0;
 };
 
 struct ps_shard {
@@ -58,6 +60,7 @@ struct ps_shard {
   int* part_arg = nullptr;
   int* ns = nullptr;     // [T+1][n] (owned rows filled)
   int cur = 0;           // record buffer holding the previous level in its p field
+  int fast = 0;          // inputs passed the safe-range precheck (math_fast.cuh)
 };
 
 namespace {
@@ -131,11 +134,13 @@ int choose_chunk(int n, int batch, int user) {
 template <typename D>
 struct LevelLaunch {
   using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const D*, const D*, D*, int*);
-  static Fn pick(int dist, int rp, int running) {
+  static Fn pick(int dist, int rp, int running, int fast) {
     using namespace ps;
-#define PS_PICK(DI, RPV)                                                               \
-  return running ? (Fn)level_tile_kernel<D, DI, RPV, true, BR>                         \
-                 : (Fn)level_tile_kernel<D, DI, RPV, false, BR>;
+#define PS_PICK(DI, RPV)                                                                              \
+  return fast ? (running ? (Fn)level_tile_kernel<D, DI, RPV, true, true, BR>                          \
+                         : (Fn)level_tile_kernel<D, DI, RPV, false, true, BR>)                        \
+              : (running ? (Fn)level_tile_kernel<D, DI, RPV, true, false, BR>                         \
+                         : (Fn)level_tile_kernel<D, DI, RPV, false, false, BR>);
     switch (dist * 2 + (rp ? 1 : 0)) {
       case 0: PS_PICK(DIST_GAUSSIAN, false)
       case 1: PS_PICK(DIST_GAUSSIAN, true)
@@ -278,6 +283,20 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   }
   PS_TRY(mark(ctx, &e_h2d));
 
+  // ---- safe-range precheck for the branch-free math path (math_fast.cuh); result read before the levels
+  int host_flags = 1;
+  cudaEvent_t e_flags = nullptr;
+  const bool want_fast = running && p.no_fast_math != 1;
+  if (want_fast) {
+    PS_TRY(ensure(ctx, ctx->scalar, 64));
+    PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, sizeof(int), st));
+    ps::range_check_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, d_a, d_b, (int*)ctx->scalar.p);
+    ctx->launches++;
+    if (!ctx->pinned_flags) PS_CUDA(ctx, cudaMallocHost((void**)&ctx->pinned_flags, 64));
+    PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags, ctx->scalar.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PS_TRY(mark(ctx, &e_flags));
+  }
+
   // ---- stage 1: sort by priority, gather, records
   PS_TRY(sort_stage<D>(ctx, p, d_a, d_b, R, n));
   const long long rec_stride = (long long)n + 1;
@@ -334,7 +353,14 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(mark(ctx, &e_pre));
 
   // ---- levels 2..Tc  (DP_impl.hpp:101-118)
-  auto fn = LevelLaunch<D>::pick(p.dist, rp, running);
+  int fast = 0;
+  if (want_fast) {
+    PS_CUDA(ctx, cudaEventSynchronize(e_flags));
+    host_flags = *ctx->pinned_flags;
+    fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
+  }
+  ctx->last_fast = fast;
+  auto fn = LevelLaunch<D>::pick(p.dist, rp, running, fast);
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lev_ev;
   for (int j = 2; j <= Tc; ++j) {
     ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1);
@@ -466,6 +492,15 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   else
     ps::build_rec_prefix_kernel<D, 1024><<<1, 1024, 0, st>>>(n, rec_stride, a_s, b_s, rec0, rec1);
   PS_CUDA(ctx, cudaGetLastError());
+  if (running && pp->no_fast_math != 1) {
+    PS_TRY(ensure(ctx, ctx->scalar, 64));
+    int flags = 1;
+    PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, sizeof(int), st));
+    ps::range_check_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, a_s, b_s, (int*)ctx->scalar.p);
+    PS_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->scalar.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PS_CUDA(ctx, cudaStreamSynchronize(st));
+    s->fast = ((flags & 1) == 0) && (pp->dist != PS_DIST_POISSON || (flags & 2) == 0);
+  }
   PS_CUDA(ctx, cudaStreamSynchronize(st));
   s->cur = 0;
   *out = s;
@@ -527,7 +562,7 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
   cudaStream_t st = ctx->stream;
   PS_CUDA(ctx, cudaMemsetAsync(my_chunk, 0, (size_t)s->chunk_rows * sizeof(D), st));
   if (g.ntiles > 0) {
-    auto fn = LevelLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, s->p.sum_mode == PS_SUM_RUNNING);
+    auto fn = LevelLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, s->p.sum_mode == PS_SUM_RUNNING, s->fast);
     fn<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, (const D*)s->SA, (const D*)s->SB, (D*)s->part_val,
                                          s->part_arg);
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
@@ -597,6 +632,7 @@ void ps_destroy(ps_ctx* ctx) {
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+  if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -625,6 +661,24 @@ ps_status ps_range_score_f32(ps_ctx* ctx, int n, const float* a, const float* b,
 ps_status ps_range_score_f64(ps_ctx* ctx, int n, const double* a, const double* b, int dist, int risk_part,
                              double* out) {
   return range_score_impl<double>(ctx, n, a, b, dist, risk_part ? 1 : 0, out);
+}
+
+ps_status ps_selftest_math(ps_ctx* ctx, int which, long long samples, unsigned long long seed,
+                           long long* mismatches) {
+  if (!ctx || !mismatches || which < 0 || which > 3 || samples < 1) return PS_ERR_INVALID;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  PS_TRY(ensure(ctx, ctx->scalar, 64));
+  cudaStream_t st = ctx->stream;
+  PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, sizeof(unsigned long long), st));
+  const int blocks = 148 * 8, threads = 256;
+  const long long per_thread = (samples + (long long)blocks * threads - 1) / ((long long)blocks * threads);
+  ps::selftest_math_kernel<<<blocks, threads, 0, st>>>(which, per_thread, seed, (unsigned long long*)ctx->scalar.p);
+  PS_CUDA(ctx, cudaGetLastError());
+  unsigned long long bad = 0;
+  PS_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->scalar.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  *mismatches = (long long)bad;
+  return PS_OK;
 }
 
 ps_status ps_shard_create_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, int rank,

@@ -15,84 +15,92 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "math_fast.cuh"
+
 namespace ps {
 
 enum { DIST_GAUSSIAN = 0, DIST_POISSON = 1, DIST_RATIONAL = 2 };
 
-// kind = dist*2 + risk_part
-template <typename D, int DIST, bool RP>
+// FAST = operands proven to be in the safe range of math_fast.cuh (per-instance precheck): the same
+// arithmetic, bit for bit, without the range checks and special-value handling.
+template <typename D, int DIST, bool RP, bool FAST = false>
 struct ScoreFn;
 
+template <bool FAST> __device__ __forceinline__ float div_f(float a, float b) { return FAST ? fast_fdiv(a, b) : __fdiv_rn(a, b); }
+template <bool FAST> __device__ __forceinline__ double div_d(double a, double b) { return FAST ? fast_ddiv(a, b) : __ddiv_rn(a, b); }
+template <bool FAST> __device__ __forceinline__ float log_f(float x) { return FAST ? fast_logf(x) : logf(x); }
+template <bool FAST> __device__ __forceinline__ double log_d(double x) { return FAST ? fast_log(x) : log(x); }
+
 // ------------------------------------------------------------------ float
-template <>
-struct ScoreFn<float, DIST_POISSON, false> {
+template <bool FAST>
+struct ScoreFn<float, DIST_POISSON, false, FAST> {
   static __device__ __forceinline__ float eval(float A, float B) {
-    float q = __fdiv_rn(A, B);
-    float s = __fsub_rn(__fadd_rn(__fmul_rn(A, logf(q)), B), A);
+    float q = div_f<FAST>(A, B);
+    float s = __fsub_rn(__fadd_rn(__fmul_rn(A, log_f<FAST>(q)), B), A);
     return (A > B) ? s : 0.f;
   }
 };
-template <>
-struct ScoreFn<float, DIST_POISSON, true> {
+template <bool FAST>
+struct ScoreFn<float, DIST_POISSON, true, FAST> {
   static __device__ __forceinline__ float eval(float A, float B) {
-    return __fmul_rn(A, logf(__fdiv_rn(A, B)));
+    return __fmul_rn(A, log_f<FAST>(div_f<FAST>(A, B)));
   }
 };
-template <>
-struct ScoreFn<float, DIST_GAUSSIAN, false> {
+template <bool FAST>
+struct ScoreFn<float, DIST_GAUSSIAN, false, FAST> {
   static __device__ __forceinline__ float eval(float A, float B) {
     double a = (double)A, b = (double)B;
-    double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(__ddiv_rn(__dmul_rn(a, a), b), b)), a);
+    double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(div_d<FAST>(__dmul_rn(a, a), b), b)), a);
     return (A > B) ? __double2float_rn(s) : 0.f;
   }
 };
-template <>
-struct ScoreFn<float, DIST_GAUSSIAN, true> {
+template <bool FAST>
+struct ScoreFn<float, DIST_GAUSSIAN, true, FAST> {
   static __device__ __forceinline__ float eval(float A, float B) {
     float sq = __fmul_rn(A, A);
-    return __double2float_rn(__ddiv_rn(__ddiv_rn((double)sq, 2.), (double)B));
+    return __double2float_rn(div_d<FAST>(__ddiv_rn((double)sq, 2.), (double)B));
   }
 };
-template <bool RP>
-struct ScoreFn<float, DIST_RATIONAL, RP> {
+template <bool RP, bool FAST>
+struct ScoreFn<float, DIST_RATIONAL, RP, FAST> {
   static __device__ __forceinline__ float eval(float A, float B) {
     double a = (double)A;
-    return __double2float_rn(__ddiv_rn(__dmul_rn(a, a), (double)B));
+    return __double2float_rn(div_d<FAST>(__dmul_rn(a, a), (double)B));
   }
 };
 
 // ------------------------------------------------------------------ double
-template <>
-struct ScoreFn<double, DIST_POISSON, false> {
+template <bool FAST>
+struct ScoreFn<double, DIST_POISSON, false, FAST> {
   static __device__ __forceinline__ double eval(double A, double B) {
-    double q = __ddiv_rn(A, B);
-    double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log(q)), B), A);
+    double q = div_d<FAST>(A, B);
+    double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log_d<FAST>(q)), B), A);
     return (A > B) ? s : 0.;
   }
 };
-template <>
-struct ScoreFn<double, DIST_POISSON, true> {
+template <bool FAST>
+struct ScoreFn<double, DIST_POISSON, true, FAST> {
   static __device__ __forceinline__ double eval(double A, double B) {
-    return __dmul_rn(A, log(__ddiv_rn(A, B)));
+    return __dmul_rn(A, log_d<FAST>(div_d<FAST>(A, B)));
   }
 };
-template <>
-struct ScoreFn<double, DIST_GAUSSIAN, false> {
+template <bool FAST>
+struct ScoreFn<double, DIST_GAUSSIAN, false, FAST> {
   static __device__ __forceinline__ double eval(double A, double B) {
-    double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(__ddiv_rn(__dmul_rn(A, A), B), B)), A);
+    double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(div_d<FAST>(__dmul_rn(A, A), B), B)), A);
     return (A > B) ? s : 0.;
   }
 };
-template <>
-struct ScoreFn<double, DIST_GAUSSIAN, true> {
+template <bool FAST>
+struct ScoreFn<double, DIST_GAUSSIAN, true, FAST> {
   static __device__ __forceinline__ double eval(double A, double B) {
-    return __ddiv_rn(__ddiv_rn(__dmul_rn(A, A), 2.), B);
+    return div_d<FAST>(__ddiv_rn(__dmul_rn(A, A), 2.), B);
   }
 };
-template <bool RP>
-struct ScoreFn<double, DIST_RATIONAL, RP> {
+template <bool RP, bool FAST>
+struct ScoreFn<double, DIST_RATIONAL, RP, FAST> {
   static __device__ __forceinline__ double eval(double A, double B) {
-    return __ddiv_rn(__dmul_rn(A, A), B);
+    return div_d<FAST>(__dmul_rn(A, A), B);
   }
 };
 
