@@ -67,7 +67,8 @@ typedef struct ps_problem {
   int sweep;       /* 0: backtrace S=T only (DP_impl.hpp:226-228); 1: every S=T..1 (:203-214)         */
   int batch;       /* independent instances R>=1 (replicas); a,b are [R][n] row-major                 */
   int on_device;   /* 1: a, b, perm AND every ps_result pointer are device pointers on ctx's device   */
-  int no_fast_math;   /* debug: 1 = never take the range-prechecked branch-free math path (csrc/math_fast.cuh) */
+  int no_fast_math;/* debug: 1 = never take the range-prechecked branch-free math path (csrc/math_fast.cuh);  */
+                   /*        2 = take it, but not the packed two-rows-per-thread float kernel               */
   int chunk_len;   /* tuning, 0 = default                                                             */
 } ps_problem;
 

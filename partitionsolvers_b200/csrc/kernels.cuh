@@ -209,6 +209,138 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Poisson, float, RUNNING sums, safe-range inputs: TWO rows per thread (i and i+128) so that the whole
+// cell pipeline runs on packed f32x2 instructions (FADD2/FMUL2/FFMA2) -- the kernel is issue-bound, and
+// a packed instruction retires two IEEE operations per issue slot (operand negation, immediates and
+// scalar broadcast are free modifiers of the packed forms).  Lane-wise the arithmetic is the scalar
+// kernel's, bit for bit.  Tile = 256 rows x L columns.
+// ---------------------------------------------------------------------------------------------
+template <bool RP>
+__global__ void __launch_bounds__(128)
+level_tile_kernel_pois_f32x2(Geom g, const Rec4<float>* __restrict__ rec, const float* __restrict__ SA,
+                             const float* __restrict__ SB, float* __restrict__ part_val,
+                             int* __restrict__ part_arg) {
+  constexpr int BK = 128, BRT = 256;
+  __shared__ Rec4<float> sbuf[2][BK];
+
+  const int inst = blockIdx.y;
+  rec += (long long)inst * g.rec_stride;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  part_val += inst * pstride;
+  part_arg += inst * pstride;
+  SA += inst * pstride;
+  SB += inst * pstride;
+
+  int t = blockIdx.x;
+  int d = g.NCH - 1;
+  for (;;) {
+    long long lim = (long long)(g.NCH - d) * g.G;
+    long long cnt = lim < g.NRB ? lim : g.NRB;
+    if (t < cnt) break;
+    t -= (int)cnt;
+    --d;
+  }
+  const int rb = t;
+  const int c = rb / g.G + d;
+  const int tid = threadIdx.x;
+  const int i0 = rb * BRT;
+  const int ia = i0 + tid, ib = i0 + 128 + tid;
+  const int k_lo = max(c * g.L + 1, i0 + 1);
+  const int k_hi = min((c + 1) * g.L, g.kmax);
+  const bool diag = (c == rb / g.G);
+
+  float2 A = make_float2(0.f, 0.f), B = A;
+  if (!diag) {
+    const int la = min(ia, g.n - 1), lb = min(ib, g.n - 1);
+    A = make_float2(SA[(long long)c * g.n + la], SA[(long long)c * g.n + lb]);
+    B = make_float2(SB[(long long)c * g.n + la], SB[(long long)c * g.n + lb]);
+  }
+  float best0 = Lim<float>::lowest(), best1 = best0;
+  int arg0 = -1, arg1 = -1;
+
+  const int nk = k_hi - k_lo + 1;
+  const int nstages = (nk + BK - 1) / BK;
+  {
+    Rec4<float> r;
+    r.x = r.y = r.p = r.w = 0;
+    if (k_lo + tid <= k_hi) r = rec[k_lo + tid];
+    sbuf[0][tid] = r;
+  }
+  for (int s = 0; s < nstages; ++s) {
+    __syncthreads();
+    const int kb = k_lo + s * BK;
+    const int kn = kb + BK + tid;
+    Rec4<float> nx;
+    nx.x = nx.y = nx.p = nx.w = 0;
+    const bool has_next = (s + 1 < nstages);
+    if (has_next && kn <= k_hi) nx = rec[kn];
+    const int cnt = min(BK, k_hi - kb + 1);
+    const Rec4<float>* __restrict__ sb = sbuf[s & 1];
+    if (kb > i0 + BRT - 1 && cnt == BK) {
+#pragma unroll 2
+      for (int kk = 0; kk < BK; ++kk) {
+        const Rec4<float> r = sb[kk];
+        A = __fadd2_rn(A, make_float2(r.x, r.x));
+        B = __fadd2_rn(B, make_float2(r.y, r.y));
+        const float2 l = fast_logf2(fast_fdiv2(A, B));
+        // A*l with two scalar multiplies: ptxas (12.9) contracts mul.rn.f32x2 (and fma.rn.f32x2 with a -0 addend)
+        // followed by add.rn.f32x2 into one FFMA2 despite the explicit rounding modifiers and --fmad=false, which
+        // would skip the reference's intermediate rounding of the product
+        float2 sc = make_float2(__fmul_rn(A.x, l.x), __fmul_rn(A.y, l.y));
+        if (!RP) {
+          sc = __fadd2_rn(sc, B);
+          sc = __fadd2_rn(sc, make_float2(-A.x, -A.y));
+          sc.x = (A.x > B.x) ? sc.x : 0.f;
+          sc.y = (A.y > B.y) ? sc.y : 0.f;
+        }
+        const float2 v = __fadd2_rn(sc, make_float2(r.p, r.p));
+        if (v.x > best0) {
+          best0 = v.x;
+          arg0 = kb + kk;
+        }
+        if (v.y > best1) {
+          best1 = v.y;
+          arg1 = kb + kk;
+        }
+      }
+    } else {
+      // diagonal or ragged stage: scalar, masked (row i only sees k > i)
+      for (int kk = 0; kk < cnt; ++kk) {
+        const int k = kb + kk;
+        const Rec4<float> r = sb[kk];
+        if (k > ia) {
+          A.x = __fadd_rn(A.x, r.x);
+          B.x = __fadd_rn(B.x, r.y);
+          const float v = __fadd_rn(ScoreFn<float, DIST_POISSON, RP, true>::eval(A.x, B.x), r.p);
+          if (v > best0) {
+            best0 = v;
+            arg0 = k;
+          }
+        }
+        if (k > ib) {
+          A.y = __fadd_rn(A.y, r.x);
+          B.y = __fadd_rn(B.y, r.y);
+          const float v = __fadd_rn(ScoreFn<float, DIST_POISSON, RP, true>::eval(A.y, B.y), r.p);
+          if (v > best1) {
+            best1 = v;
+            arg1 = k;
+          }
+        }
+      }
+    }
+    if (has_next) sbuf[(s + 1) & 1][tid] = nx;
+  }
+  if (ia < g.nrows) {
+    part_val[(long long)c * g.n + ia] = best0;
+    part_arg[(long long)c * g.n + ia] = arg0;
+  }
+  if (ib < g.nrows) {
+    part_val[(long long)c * g.n + ib] = best1;
+    part_arg[(long long)c * g.n + ib] = arg1;
+  }
+}
+
 // Fold the per-chunk partials of row i in ascending chunk order (= ascending k): strict > keeps the
 // first maximum, exactly like the reference's scan over k.  Writes maxScore_[j][i], nextStart_[j][i]
 // and the p field of the NEXT level's records.  Sharded runs also emit the value in block-cyclic
@@ -222,9 +354,15 @@ __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int
   part_val += inst * pstride;
   part_arg += inst * pstride;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;  // index among owned rows
-  if (m >= g.NRB * BR) return;
-  const int rb = g.rb_first + g.rb_step * (m / BR);
-  const int i = rb * BR + (m % BR);
+  int i;
+  if (g.rb_step == 1 && g.rb_first == 0) {
+    i = m;  // unsharded: rows are contiguous whatever the tile height of the level kernel
+    if (i >= g.nrows) return;
+  } else {
+    if (m >= g.NRB * BR) return;
+    const int rb = g.rb_first + g.rb_step * (m / BR);
+    i = rb * BR + (m % BR);
+  }
   D best = Lim<D>::lowest();
   int arg = -1;
   if (i < g.nrows) {

@@ -118,17 +118,19 @@ ps_status mark(ps_ctx* ctx, cudaEvent_t* out) {
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // k-chunk length: a multiple of BR giving enough equal tiles to balance 148 SMs (SURVEY.md hard part 5)
+// (always a multiple of 256 so that both the 128-row and the 256-row tile kernels can use it)
 int choose_chunk(int n, int batch, int user) {
-  if (user > 0) return std::max(BR, (user / BR) * BR);
+  const int Q = 2 * BR;
+  if (user > 0) return std::max(Q, (user / Q) * Q);
   const long long want_tiles = 148LL * 64;
   const int nrb = cdiv(n, BR);
   long long nch = (2 * want_tiles + (long long)batch * nrb - 1) / ((long long)batch * nrb);
   nch = std::max(1LL, std::min(64LL, nch));
-  long long L = ((cdiv(n, nch) + BR - 1) / BR) * (long long)BR;
-  L = std::max<long long>(L, 4 * BR);
+  long long L = ((cdiv(n, nch) + Q - 1) / Q) * (long long)Q;
+  L = std::max<long long>(L, 2 * Q);
   L = std::min<long long>(L, 16384);
-  L = std::min<long long>(L, ((n + BR - 1) / BR) * (long long)BR);
-  return (int)std::max<long long>(L, BR);
+  L = std::min<long long>(L, ((n + Q - 1) / Q) * (long long)Q);
+  return (int)std::max<long long>(L, Q);
 }
 
 template <typename D>
@@ -152,15 +154,15 @@ struct LevelLaunch {
   }
 };
 
-ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int rb_step) {
+ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int rb_step, int tile_rows = BR) {
   ps::Geom g;
   g.n = n;
   g.kmax = n - j + 1;
   g.nrows = (j == Tc) ? 1 : (n - j + 1);  // DP_impl.hpp:114-116: last level needs row 0 only
   g.L = L;
   g.NCH = cdiv(g.kmax, L);
-  g.G = L / BR;
-  const int nrb_total = cdiv(g.nrows, BR);
+  g.G = L / tile_rows;
+  const int nrb_total = cdiv(g.nrows, tile_rows);
   g.NRB = nrb_total > rb_first ? (nrb_total - rb_first + rb_step - 1) / rb_step : 0;
   g.nch_alloc = nch_alloc;
   g.rec_stride = (long long)n + 1;
@@ -361,9 +363,17 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   }
   ctx->last_fast = fast;
   auto fn = LevelLaunch<D>::pick(p.dist, rp, running, fast);
+  // float Poisson on the fast path: two rows per thread, packed f32x2 pipeline, 256-row tiles
+  int tile_rows = BR;
+  if constexpr (sizeof(D) == 4) {
+    if (fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2) {
+      tile_rows = 2 * BR;
+      fn = rp ? ps::level_tile_kernel_pois_f32x2<true> : ps::level_tile_kernel_pois_f32x2<false>;
+    }
+  }
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lev_ev;
   for (int j = 2; j <= Tc; ++j) {
-    ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1);
+    ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, tile_rows);
     const ps::Rec4<D>* rin = recs[(j - 1) & 1];
     ps::Rec4<D>* rout = recs[j & 1];
     const bool timed = (j - 2) < PS_MAX_TIMED_LEVELS;
@@ -371,7 +381,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (timed) PS_TRY(mark(ctx, &e0));
     fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
     if (timed) PS_TRY(mark(ctx, &e1));
-    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), R), 256, 0, st>>>(
+    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
         g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr);
     ctx->launches += 2;
     if (timed) {

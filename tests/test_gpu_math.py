@@ -21,9 +21,11 @@ def test_fast_and_generic_level_kernels_agree_bitwise(ctx, dt, dist, rp):
                 lambda: synth.uniform_ab(2000, seed=62, dtype=dt, a_lo=0.01, b_lo=0.01)):
         a, b = gen()
         r_fast = ctx.solve_raw(a, b, 7, dist, rp, dtype=dt, levels=True)
-        r_gen = ctx.solve_raw(a, b, 7, dist, rp, dtype=dt, levels=True, no_fast=True)
+        r_gen = ctx.solve_raw(a, b, 7, dist, rp, dtype=dt, levels=True, no_fast=1)
+        r_scalar = ctx.solve_raw(a, b, 7, dist, rp, dtype=dt, levels=True, no_fast=2, chunk_len=512)
         for k in ("perm", "bounds", "subset_scores", "max_score", "next_start"):
             assert np.array_equal(r_fast[k], r_gen[k], equal_nan=True), k
+            assert np.array_equal(r_fast[k], r_scalar[k], equal_nan=True), k
 
 
 def test_out_of_range_inputs_fall_back_to_generic_path(ctx, oracle):
