@@ -132,11 +132,16 @@ ps_status ps_range_score_f32(ps_ctx* ctx, int n, const float* a, const float* b,
 ps_status ps_range_score_f64(ps_ctx* ctx, int n, const double* a, const double* b, int dist, int risk_part,
                              double* out);
 
-/* Self-test of the branch-free division / logarithm used when a per-instance precheck proves the inputs
- * well-scaled (csrc/math_fast.cuh): draws `samples` random operands in the safe range on the device and
- * counts those where the routine differs from the CUDA math library.  which: 0 fdiv, 1 logf, 2 ddiv, 3 log. */
+/* Self-test of the branch-free routines used when a per-instance precheck proves the inputs well-scaled
+ * (csrc/math_fast.cuh, csrc/glibc_log.cuh): draws `samples` random operands in the safe range on the device and
+ * counts those where the fast routine differs from the general one.  which: 0 float division vs div.rn,
+ * 1 logf fast vs general entry, 2 double division vs div.rn, 3 log fast vs general entry. */
 ps_status ps_selftest_math(ps_ctx* ctx, int which, long long samples, unsigned long long seed,
                            long long* mismatches);
+/* Device log()/logf() (the restatement of glibc's routines the Poisson scores use) evaluated on n host
+ * arguments; y_general takes the entry point that handles every input, y_fast the safe-range one. */
+ps_status ps_eval_log_f64(ps_ctx* ctx, long long n, const double* x, double* y_general, double* y_fast);
+ps_status ps_eval_log_f32(ps_ctx* ctx, long long n, const float* x, float* y_general, float* y_fast);
 
 /* ---- row-sharded single instance: building blocks driven by a multi-process host ----
  * Rank `rank` of `world` owns row blocks rb with rb % world == rank.  The caller (one process per GPU)

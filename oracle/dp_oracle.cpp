@@ -522,6 +522,14 @@ int oracle_ltss_f32(int n, const float* a_in, const float* b_in, int dist, int* 
   return 0;
 }
 
+// The host libm's log / logf on arrays: what the reference's std::log calls resolve to on this machine.
+void oracle_log_f64(long long n, const double* x, double* y) {
+  for (long long i = 0; i < n; ++i) y[i] = std::log(x[i]);
+}
+void oracle_log_f32(long long n, const float* x, float* y) {
+  for (long long i = 0; i < n; ++i) y[i] = std::log(x[i]);
+}
+
 int oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -213,6 +213,17 @@ def ols(scores, dtype=np.float32):
     return int(fn(C.c_int(s.shape[0]), _ptr(s, ct)))
 
 
+def host_log(x, dtype=np.float64):
+    """libm log/logf of the host (the function the reference's Poisson scores call)."""
+    x = np.ascontiguousarray(x, dtype=dtype)
+    y = np.empty_like(x)
+    ct = C.c_float if dtype == np.float32 else C.c_double
+    fn = lib("port").oracle_log_f32 if dtype == np.float32 else lib("port").oracle_log_f64
+    fn.restype = None
+    fn(C.c_longlong(x.shape[0]), _ptr(x, ct), _ptr(y, ct))
+    return y
+
+
 def hardware_threads():
     fn = lib("port").oracle_hardware_threads
     fn.restype = C.c_int

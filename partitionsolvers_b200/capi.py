@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "ps_stream", "ps_solve_f32", "ps_solve_f64", "ps_get_timings", "ps_range_score_f32",
     "ps_range_score_f64", "ps_shard_create_f64", "ps_shard_create_f32", "ps_shard_chunk_rows",
     "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",
-    "ps_shard_destroy", "ps_selftest_math",
+    "ps_shard_destroy", "ps_selftest_math", "ps_eval_log_f64", "ps_eval_log_f32",
 ]
 
 
@@ -98,6 +98,8 @@ def load():
         L.ps_shard_destroy.argtypes = [C.c_void_p]
         L.ps_shard_destroy.restype = None
         L.ps_selftest_math.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
+        for nm in ("ps_eval_log_f64", "ps_eval_log_f32"):
+            getattr(L, nm).argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -213,6 +215,14 @@ class Context:
         out = C.c_longlong(-1)
         self._check(self.lib.ps_selftest_math(self._h, which, samples, seed, C.byref(out)))
         return out.value
+
+    def eval_log(self, x, dtype=np.float64):
+        """Device log/logf on host arguments -> (general entry, safe-range entry)."""
+        x = np.ascontiguousarray(x, dtype=dtype)
+        yg, yf = np.empty_like(x), np.empty_like(x)
+        fn = self.lib.ps_eval_log_f64 if dtype == np.float64 else self.lib.ps_eval_log_f32
+        self._check(fn(self._h, x.shape[0], _vp(x), _vp(yg), _vp(yf)))
+        return yg, yf
 
     def range_score(self, a, b, dist, risk_part, dtype=np.float32):
         a = np.ascontiguousarray(a, dtype=dtype)

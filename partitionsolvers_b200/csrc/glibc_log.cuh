@@ -1,0 +1,146 @@
+// glibc_log.cuh -- device restatement of glibc's log() and logf(), operation for operation.
+//
+// The reference's Poisson scores call std::log (score_impl.hpp:374-390), which on the reference's platform is
+// glibc's table-driven log/logf (2.28 and later; sysdeps/ieee754/dbl-64/e_log.c, sysdeps/ieee754/flt-32/e_logf.c,
+// the x86-64 multiarch variant built with FMA that every AVX2-class CPU selects).  IEEE add/mul/fma are
+// deterministic, so executing the SAME sequence of operations on the SAME coefficient tables gives the SAME
+// bits on the GPU as on the host: with these routines the Poisson path is bit-identical to the reference
+// instead of "within 1 ulp of log".  The operation order below (in particular which products are fused) was
+// read off the disassembly of the library's *_fma variants and checked on the host against libm itself on
+// 2*10^8 arguments before being ported (tools/check_glibc_log.c keeps that check runnable).
+//
+//   log  : N=128 table {1/c, log c}; r = fma(z, 1/c, -1); degree-5 polynomial in r; explicit hi/lo sums.
+//          |x-1| < ~2^-4 takes a separate degree-11 polynomial with a split of r for the r^2/2 term.
+//   logf : N=16 table, evaluated in double: y = fma(r^2, fma(r^2, A0, fma(r, A1, A2)), fma(k, ln2, log c) + r).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "glibc_log_data.inc"
+
+namespace ps {
+
+struct __align__(16) GlogEntry {
+  double invc, logc;
+};
+__device__ const GlogEntry g_glog_tab[128] = PS_GLOG_TAB_INIT;
+__device__ const GlogEntry g_glogf_tab[16] = PS_GLOGF_TAB_INIT;
+
+__device__ __forceinline__ double int_to_double_exact(int k) {
+  // (double)k without the conversion pipe: 2^52 + 2^31 + k is exact, then subtract the bias
+  return __dadd_rn(__hiloint2double(0x43300000, k ^ 0x80000000), -__longlong_as_double(0x4330000080000000LL));
+}
+
+// x positive, normal, finite (hi/lo are its two words; the subnormal path passes rescaled words).
+__device__ __forceinline__ double glibc_log_core(double x, int hi, int lo) {
+  if ((unsigned)(hi - 0x3FEE0000) < 0x30900u) {
+    // 1 - 2^-4 <= x < 1 + 0x1.09p-4
+    const double r = __dadd_rn(x, -1.0);
+    double t2 = __fma_rn(r, PS_GLOG_B2, PS_GLOG_B1);
+    double t3 = __fma_rn(r, PS_GLOG_B5, PS_GLOG_B4);
+    const double r2 = __dmul_rn(r, r);
+    const double t5 = __fma_rn(r, PS_GLOG_B8, PS_GLOG_B7);
+    t2 = __fma_rn(r2, PS_GLOG_B3, t2);
+    t3 = __fma_rn(r2, PS_GLOG_B6, t3);
+    const double r3 = __dmul_rn(r, r2);
+    double t1 = __fma_rn(r2, PS_GLOG_B9, t5);
+    t1 = __fma_rn(r3, PS_GLOG_B10, t1);
+    t1 = __fma_rn(t1, r3, t3);
+    t1 = __fma_rn(t1, r3, t2);
+    const double w = __fma_rn(r, 0x1p27, r);
+    const double rhi = __fma_rn(-0x1p27, r, w);
+    const double rhi2 = __dmul_rn(rhi, rhi);
+    const double rlo = __dadd_rn(r, -rhi);
+    const double h = __fma_rn(rhi2, PS_GLOG_B0, r);
+    const double d = __dadd_rn(r, -h);
+    const double s = __dadd_rn(r, rhi);
+    double l = __fma_rn(rhi2, PS_GLOG_B0, d);
+    const double m = __dmul_rn(PS_GLOG_B0, rlo);
+    l = __fma_rn(m, s, l);
+    const double y = __fma_rn(t1, r3, l);
+    return __dadd_rn(h, y);
+  }
+  const int thi = hi - 0x3fe60000;
+  const int i = (thi >> 13) & 127;
+  const int k = thi >> 20;
+  const double z = __hiloint2double(hi - (thi & 0xfff00000), lo);
+  const GlogEntry e = g_glog_tab[i];
+  const double kd = int_to_double_exact(k);
+  const double w = __fma_rn(kd, PS_GLOG_LN2HI, e.logc);
+  const double r = __fma_rn(z, e.invc, -1.0);
+  const double p12 = __fma_rn(r, PS_GLOG_A2, PS_GLOG_A1);
+  const double h = __dadd_rn(r, w);
+  const double r2 = __dmul_rn(r, r);
+  double l = __dadd_rn(__dadd_rn(w, -h), r);
+  l = __fma_rn(kd, PS_GLOG_LN2LO, l);
+  const double r3 = __dmul_rn(r, r2);
+  const double p34 = __fma_rn(r, PS_GLOG_A4, PS_GLOG_A3);
+  l = __fma_rn(r2, PS_GLOG_A0, l);
+  const double p = __fma_rn(p34, r2, p12);
+  const double y = __fma_rn(r3, p, l);
+  return __dadd_rn(y, h);
+}
+
+// operands proven positive and normal by the safe-range precheck
+__device__ __forceinline__ double glibc_log_fast(double x) {
+  return glibc_log_core(x, __double2hiint(x), __double2loint(x));
+}
+
+// every double: zero -> -inf, negative / NaN -> NaN, +inf -> +inf, subnormals rescaled by 2^52
+__device__ __forceinline__ double glibc_log(double x) {
+  int hi = __double2hiint(x), lo = __double2loint(x);
+  if ((unsigned)(hi - 0x3FEE0000) >= 0x30900u && (unsigned)(((unsigned)hi >> 16) - 0x0010u) >= 0x7ff0u - 0x0010u) {
+    if (((hi & 0x7fffffff) | lo) == 0) return -__longlong_as_double(0x7ff0000000000000LL);
+    if (hi == 0x7ff00000 && lo == 0) return x;
+    if (hi < 0 || (hi & 0x7ff00000) == 0x7ff00000) return __longlong_as_double(0x7ff8000000000000LL);
+    const double xs = __dmul_rn(x, 0x1p52);
+    hi = __double2hiint(xs) - (52 << 20);
+    lo = __double2loint(xs);
+    x = __hiloint2double(hi, lo);
+  }
+  return glibc_log_core(x, hi, lo);
+}
+
+// ---- logf -------------------------------------------------------------------------------------------
+__device__ __forceinline__ double float_to_double_exact(int bits) {
+  // positive normal float -> double by re-biasing the exponent (no conversion pipe)
+  return __hiloint2double(((unsigned)bits >> 3) + 0x38000000, bits << 29);
+}
+
+// tab = the 16-entry table, in global memory (g_glogf_tab) or a shared-memory copy of it
+__device__ __forceinline__ float glibc_logf_core(int ix, const GlogEntry* __restrict__ tab = g_glogf_tab) {
+  const int tmp = ix - 0x3f330000;
+  // k = tmp >> 23 (arithmetic), written as a signed bit-field extract: ptxas 12.9 was seen to fold
+  // "(ix + c) >> 23, then ^ 0x80000000" into a single add for one of two inlined copies, dropping the shift
+  int k;
+  asm("bfe.s32 %0, %1, 23, 9;" : "=r"(k) : "r"(tmp));
+  const int iz = ix - (tmp & 0xff800000);
+  const GlogEntry e = *reinterpret_cast<const GlogEntry*>(reinterpret_cast<const char*>(tab) + ((tmp >> 15) & 0xf0));
+  const double z = (double)__int_as_float(iz);  // exact (cvt.f64.f32)
+  const double r = __fma_rn(z, e.invc, -1.0);
+  const double y0 = __fma_rn(int_to_double_exact(k), PS_GLOGF_LN2, e.logc);
+  double y = __fma_rn(r, PS_GLOGF_A1, PS_GLOGF_A2);
+  const double r2 = __dmul_rn(r, r);
+  const double q = __dadd_rn(r, y0);
+  y = __fma_rn(r2, PS_GLOGF_A0, y);
+  y = __fma_rn(r2, y, q);
+  return __double2float_rn(y);
+}
+
+__device__ __forceinline__ float glibc_logf_fast(float x, const GlogEntry* __restrict__ tab = g_glogf_tab) {
+  // x == 1 needs no special case here: k = 0, the table entry around 1 is {1, 0}, r = 0 and the sum is +0
+  return glibc_logf_core(__float_as_int(x), tab);
+}
+
+__device__ __forceinline__ float glibc_logf(float x) {
+  int ix = __float_as_int(x);
+  if (ix == 0x3f800000) return 0.0f;
+  if ((unsigned)(ix - 0x00800000) >= 0x7f800000u - 0x00800000u) {
+    if ((ix & 0x7fffffff) == 0) return -__int_as_float(0x7f800000);
+    if (ix == 0x7f800000) return x;
+    if (ix < 0 || (ix & 0x7f800000) == 0x7f800000) return __int_as_float(0x7fc00000);
+    ix = __float_as_int(__fmul_rn(x, 0x1p23f)) - (23 << 23);
+  }
+  return glibc_logf_core(ix);
+}
+
+}  // namespace ps

@@ -223,6 +223,8 @@ level_tile_kernel_pois_f32x2(Geom g, const Rec4<float>* __restrict__ rec, const 
                              int* __restrict__ part_arg) {
   constexpr int BK = 128, BRT = 256;
   __shared__ Rec4<float> sbuf[2][BK];
+  __shared__ GlogEntry s_logf[16];
+  if (threadIdx.x < 16) s_logf[threadIdx.x] = g_glogf_tab[threadIdx.x];
 
   const int inst = blockIdx.y;
   rec += (long long)inst * g.rec_stride;
@@ -283,7 +285,8 @@ level_tile_kernel_pois_f32x2(Geom g, const Rec4<float>* __restrict__ rec, const 
         const Rec4<float> r = sb[kk];
         A = __fadd2_rn(A, make_float2(r.x, r.x));
         B = __fadd2_rn(B, make_float2(r.y, r.y));
-        const float2 l = fast_logf2(fast_fdiv2(A, B));
+        const float2 q = fast_fdiv2(A, B);
+        const float2 l = make_float2(glibc_logf_fast(q.x, s_logf), glibc_logf_fast(q.y, s_logf));
         // A*l with two scalar multiplies: ptxas (12.9) contracts mul.rn.f32x2 (and fma.rn.f32x2 with a -0 addend)
         // followed by add.rn.f32x2 into one FFMA2 despite the explicit rounding modifiers and --fmad=false, which
         // would skip the reference's intermediate rounding of the product
@@ -714,18 +717,34 @@ __global__ void selftest_math_kernel(int which, long long per_thread, unsigned l
       const float a = rand_safe_f32(s, -30, 60), b = rand_safe_f32(s, -30, 60);
       bad += __float_as_int(fast_fdiv(a, b)) != __float_as_int(__fdiv_rn(a, b));
     } else if (which == 1) {
-      // half the samples near 1 (the common case for rate ratios), half over the whole quotient range
+      // fast and general entry points of the glibc logf restatement agree on the safe range
       const float x = (it & 1) ? rand_safe_f32(s, -1, 0) : rand_safe_f32(s, -90, 90);
-      bad += __float_as_int(fast_logf(x)) != __float_as_int(logf(x));
+      bad += __float_as_int(glibc_logf_fast(x)) != __float_as_int(glibc_logf(x));
     } else if (which == 2) {
       const double a = rand_safe_f64(s, -30, 60), b = rand_safe_f64(s, -30, 60);
       bad += __double_as_longlong(fast_ddiv(a, b)) != __double_as_longlong(__ddiv_rn(a, b));
     } else {
       const double x = (it & 1) ? rand_safe_f64(s, -1, 0) : rand_safe_f64(s, -90, 90);
-      bad += __double_as_longlong(fast_log(x)) != __double_as_longlong(log(x));
+      bad += __double_as_longlong(glibc_log_fast(x)) != __double_as_longlong(glibc_log(x));
     }
   }
   if (bad) atomicAdd(mismatches, bad);
+}
+
+// Evaluate the device log routines on caller-supplied arguments (tests compare the bits with the host's libm).
+template <typename D>
+__global__ void eval_log_kernel(long long n, const D* __restrict__ x, D* __restrict__ y_general,
+                                D* __restrict__ y_fast) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const D v = x[g];
+  if (sizeof(D) == 4) {
+    y_general[g] = (D)glibc_logf((float)v);
+    y_fast[g] = (D)glibc_logf_fast((float)v);
+  } else {
+    y_general[g] = (D)glibc_log((double)v);
+    y_fast[g] = (D)glibc_log_fast((double)v);
+  }
 }
 
 // Sharded runs: scatter the all-gathered [world][chunk] level values back to natural row order

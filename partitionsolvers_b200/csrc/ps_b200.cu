@@ -459,6 +459,23 @@ ps_status range_score_impl(ps_ctx* ctx, int n, const D* a, const D* b, int dist,
   return PS_OK;
 }
 
+template <typename D>
+ps_status eval_log_impl(ps_ctx* ctx, long long n, const D* x, D* yg, D* yf) {
+  if (!ctx || !x || !yg || !yf || n < 1) return PS_ERR_INVALID;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  PS_TRY(ensure(ctx, ctx->a_in, n * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->a_s, n * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->b_s, n * sizeof(D)));
+  PS_CUDA(ctx, cudaMemcpyAsync(ctx->a_in.p, x, n * sizeof(D), cudaMemcpyHostToDevice, st));
+  ps::eval_log_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, (const D*)ctx->a_in.p, (D*)ctx->a_s.p, (D*)ctx->b_s.p);
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaMemcpyAsync(yg, ctx->a_s.p, n * sizeof(D), cudaMemcpyDeviceToHost, st));
+  PS_CUDA(ctx, cudaMemcpyAsync(yf, ctx->b_s.p, n * sizeof(D), cudaMemcpyDeviceToHost, st));
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  return PS_OK;
+}
+
 // ------------------------------------------------------------------------------- row sharding
 template <typename D>
 ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, const D* b_s, int rank,
@@ -689,6 +706,13 @@ ps_status ps_selftest_math(ps_ctx* ctx, int which, long long samples, unsigned l
   PS_CUDA(ctx, cudaStreamSynchronize(st));
   *mismatches = (long long)bad;
   return PS_OK;
+}
+
+ps_status ps_eval_log_f64(ps_ctx* ctx, long long n, const double* x, double* y_general, double* y_fast) {
+  return eval_log_impl<double>(ctx, n, x, y_general, y_fast);
+}
+ps_status ps_eval_log_f32(ps_ctx* ctx, long long n, const float* x, float* y_general, float* y_fast) {
+  return eval_log_impl<float>(ctx, n, x, y_general, y_fast);
 }
 
 ps_status ps_shard_create_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, int rank,

@@ -10,11 +10,12 @@
 //   * DataType=double: everything in double.
 //   * no fused multiply-add (reference build: -O3 -mavx2, no -mfma): every product/sum below is an
 //     explicit round-to-nearest intrinsic so nvcc cannot contract it; divisions are IEEE (div.rn).
-// log/logf are CUDA's (<= 1 ulp); glibc's differ in the last bit on a fraction of arguments, which
-// is the tolerance clause of the parity contract (DESIGN.md "Parity").
+// log/logf are restatements of glibc's routines (glibc_log.cuh), so the Poisson scores carry the same bits
+// as the reference's std::log calls.
 #pragma once
 #include <cuda_runtime.h>
 
+#include "glibc_log.cuh"
 #include "math_fast.cuh"
 
 namespace ps {
@@ -28,8 +29,9 @@ struct ScoreFn;
 
 template <bool FAST> __device__ __forceinline__ float div_f(float a, float b) { return FAST ? fast_fdiv(a, b) : __fdiv_rn(a, b); }
 template <bool FAST> __device__ __forceinline__ double div_d(double a, double b) { return FAST ? fast_ddiv(a, b) : __ddiv_rn(a, b); }
-template <bool FAST> __device__ __forceinline__ float log_f(float x) { return FAST ? fast_logf(x) : logf(x); }
-template <bool FAST> __device__ __forceinline__ double log_d(double x) { return FAST ? fast_log(x) : log(x); }
+// log = glibc's algorithm (glibc_log.cuh): bit-identical to the std::log the reference calls
+template <bool FAST> __device__ __forceinline__ float log_f(float x) { return FAST ? glibc_logf_fast(x) : glibc_logf(x); }
+template <bool FAST> __device__ __forceinline__ double log_d(double x) { return FAST ? glibc_log_fast(x) : glibc_log(x); }
 
 // ------------------------------------------------------------------ float
 template <bool FAST>

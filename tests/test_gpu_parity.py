@@ -2,11 +2,12 @@
 against the reference-written golden fixtures, against the oracle port on seeded inputs, and -- at
 BASELINE.json's full sizes -- through size-independent properties plus oracle-checked sampled rows.
 
-Tolerances (DESIGN.md "Parity"):
-  * Gaussian and RationalScore, RUNNING sums: bit-exact (every maxScore_/nextStart_ cell, every output).
-  * Poisson: CUDA log/logf vs glibc differ by <= 1 ulp on some arguments -> maxScore_ within
-    1e-9 (f64) / 2e-4 (f32) relative; split indices identical except where the two candidates tie
-    within 1e-12 (f64) / 1e-5 (f32) relative under the oracle's own arithmetic.
+Tolerances (DESIGN.md "Parity"), RUNNING sums (the default):
+  * every score, f32 and f64: bit-exact -- every maxScore_/nextStart_ cell, subsets, per-subset scores, objective.
+    Gaussian/Rational need only IEEE arithmetic; Poisson additionally needs log/logf to carry the host libm's
+    bits, which csrc/glibc_log.cuh provides (conftest.device_log_matches_host verifies it on the machine at hand;
+    only if that probe fails do the Poisson checks fall back to 1e-9 (f64) / 2e-4 (f32) with tie-aware splits).
+  * PREFIX sums: bit-identical to RUNNING when all partial sums are exact, else prefix-difference rounding.
 """
 import numpy as np
 import pytest
@@ -222,6 +223,7 @@ def test_full_size_C3_properties_and_sampled_rows(oracle, ctx, dt):
     a_s, b_s = a[perm], b[perm]
     rs = np.random.RandomState(1)
     rtol, tie = tol_for(dt, True), TIE[dt]
+    exact = rtol == 0.0
     for j in (2, 9, T):
         kmax = n - j + 1
         rows = np.array([0], np.int32) if j == T else np.unique(
@@ -230,6 +232,8 @@ def test_full_size_C3_properties_and_sampled_rows(oracle, ctx, dt):
         best, arg = oracle.dp_rows(a_s, b_s, r1["max_score"][j - 1], kmax, 1, False, rows, dtype=dt)
         got_v, got_k = r1["max_score"][j][rows], r1["next_start"][j][rows]
         scale = np.max(np.abs(r1["max_score"][j][:kmax if j < T else 1].astype(np.float64)))
+        if exact:
+            assert np.array_equal(got_v, best) and np.array_equal(got_k, arg), f"level {j}: sampled rows differ"
         assert np.all(np.abs(got_v.astype(np.float64) - best.astype(np.float64)) <= rtol * scale)
         for q in np.nonzero(got_k != arg)[0]:
             i = int(rows[q])
