@@ -113,11 +113,12 @@ __device__ __forceinline__ float glibc_logf_core(int ix, const GlogEntry* __rest
   // "(ix + c) >> 23, then ^ 0x80000000" into a single add for one of two inlined copies, dropping the shift
   int k;
   asm("bfe.s32 %0, %1, 23, 9;" : "=r"(k) : "r"(tmp));
+  const double kd = int_to_double_exact(k);
   const int iz = ix - (tmp & 0xff800000);
   const GlogEntry e = *reinterpret_cast<const GlogEntry*>(reinterpret_cast<const char*>(tab) + ((tmp >> 15) & 0xf0));
   const double z = (double)__int_as_float(iz);  // exact (cvt.f64.f32)
   const double r = __fma_rn(z, e.invc, -1.0);
-  const double y0 = __fma_rn(int_to_double_exact(k), PS_GLOGF_LN2, e.logc);
+  const double y0 = __fma_rn(kd, PS_GLOGF_LN2, e.logc);
   double y = __fma_rn(r, PS_GLOGF_A1, PS_GLOGF_A2);
   const double r2 = __dmul_rn(r, r);
   const double q = __dadd_rn(r, y0);

@@ -639,7 +639,9 @@ template <typename D>
 __global__ void backtrace_scores_kernel(int R, int n, int Tc, int sweep, int dist, int rp, int running,
                                         const int* __restrict__ bounds, const D* __restrict__ as,
                                         const D* __restrict__ bs, const Rec4<D>* __restrict__ rec,
-                                        long long rec_stride, D* __restrict__ scores) {
+                                        long long rec_stride, const D* __restrict__ SA,
+                                        const D* __restrict__ SB, int L, int nch_alloc,
+                                        D* __restrict__ scores) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int nS = sweep ? Tc + 1 : 1;
   const long long total = (long long)R * nS * Tc;
@@ -657,8 +659,20 @@ __global__ void backtrace_scores_kernel(int R, int n, int Tc, int sweep, int dis
       if (running) {
         const D* ap = as + (long long)inst * n;
         const D* bp = bs + (long long)inst * n;
+        // left-to-right sum from lo, like the reference; the level-1 pass already holds that running sum at
+        // every chunk boundary c*L > lo (SA/SB), so only the tail after the last boundary is walked here
+        int k = lo;
+        if (SA) {
+          const int c = min(hi / L, nch_alloc - 1);
+          if (c >= 1 && (long long)c * L > lo) {
+            const long long pstride = (long long)nch_alloc * n;
+            A = SA[inst * pstride + (long long)c * n + lo];
+            B = SB[inst * pstride + (long long)c * n + lo];
+            k = c * L;
+          }
+        }
 #pragma unroll 8
-        for (int k = lo; k < hi; ++k) {
+        for (; k < hi; ++k) {
           A = add_rn<D>(A, ap[k]);
           B = add_rn<D>(B, bp[k]);
         }

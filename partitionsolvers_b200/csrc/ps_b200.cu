@@ -401,7 +401,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   ps::backtrace_bounds_kernel<<<cdiv((long long)R * nS, 128), 128, 0, st>>>(R, n, Tc, p.sweep ? 1 : 0, d_ns,
                                                                            d_bounds);
   ps::backtrace_scores_kernel<D><<<cdiv((long long)R * nS * Tc, 128), 128, 0, st>>>(
-      R, n, Tc, p.sweep ? 1 : 0, p.dist, rp, running, d_bounds, d_as, d_bs, rec0, rec_stride, d_scores);
+      R, n, Tc, p.sweep ? 1 : 0, p.dist, rp, running, d_bounds, d_as, d_bs, rec0, rec_stride, d_SA, d_SB, L,
+      nch_alloc, d_scores);
   ctx->launches += 2;
   PS_CUDA(ctx, cudaGetLastError());
   PS_TRY(mark(ctx, &e_bt));

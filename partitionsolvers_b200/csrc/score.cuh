@@ -77,7 +77,10 @@ struct ScoreFn<double, DIST_POISSON, false, FAST> {
   static __device__ __forceinline__ double eval(double A, double B) {
     double q = div_d<FAST>(A, B);
     double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log_d<FAST>(q)), B), A);
-    return (A > B) ? s : 0.;
+    // FAST: A, B are positive normal doubles, for which the order of the bit patterns is the numeric order;
+    // the integer compare keeps one instruction off the FP64 pipe, which is the pipe that bounds this kernel
+    const bool gt = FAST ? (__double_as_longlong(A) > __double_as_longlong(B)) : (A > B);
+    return gt ? s : 0.;
   }
 };
 template <bool FAST>
