@@ -132,6 +132,12 @@ ps_status ps_range_score_f32(ps_ctx* ctx, int n, const float* a, const float* b,
 ps_status ps_range_score_f64(ps_ctx* ctx, int n, const double* a, const double* b, int dist, int risk_part,
                              double* out);
 
+/* LTSSSolver<float> (reference LTSS_impl.hpp:14-35,73-111): stable priority sort, then the best single subset
+ * among all prefixes and suffixes of the sorted order under the multiple-clustering score.  The subset is
+ * perm[lo:hi]; score is float.  perm may be NULL.  If no candidate beats -FLT_MAX (all scores NaN), lo=hi=0. */
+ps_status ps_ltss_f32(ps_ctx* ctx, int n, const float* a, const float* b, int dist, int* perm, int* lo, int* hi,
+                      float* score);
+
 /* Self-test of the branch-free routines used when a per-instance precheck proves the inputs well-scaled
  * (csrc/math_fast.cuh, csrc/glibc_log.cuh): draws `samples` random operands in the safe range on the device and
  * counts those where the fast routine differs from the general one.  which: 0 float division vs div.rn,

@@ -68,8 +68,8 @@ def build_proto(force=False):
         cxx = os.environ.get("CXX", "g++")
         cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I", INCLUDE, "-I",
                pybind11.get_include(), "-I", sysconfig.get_paths()["include"], src,
-               os.path.join(HOSTSRC, "python_dpsolver.cpp"), "-L", LIBDIR, "-lps_b200",
-               "-Wl,-rpath,$ORIGIN", "-pthread", "-o", target]
+               os.path.join(HOSTSRC, "python_dpsolver.cpp"), os.path.join(HOSTSRC, "python_ltsssolver.cpp"),
+               "-L", LIBDIR, "-lps_b200", "-Wl,-rpath,$ORIGIN", "-pthread", "-o", target]
         subprocess.run(cmd, check=True)
     return target
 
@@ -94,7 +94,7 @@ def build_facade_test(force=False):
     if force or _newer(target, srcs):
         cxx = os.environ.get("CXX", "g++")
         subprocess.run([cxx, "-O2", "-std=c++17", "-I", INCLUDE, src, os.path.join(HOSTSRC, "python_dpsolver.cpp"),
-                        "-L", LIBDIR, "-lps_b200", "-Wl,-rpath,$ORIGIN", "-pthread", "-o", target], check=True)
+                        os.path.join(HOSTSRC, "python_ltsssolver.cpp"), "-L", LIBDIR, "-lps_b200", "-Wl,-rpath,$ORIGIN", "-pthread", "-o", target], check=True)
     return target
 
 

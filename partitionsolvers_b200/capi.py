@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "ps_range_score_f64", "ps_shard_create_f64", "ps_shard_create_f32", "ps_shard_chunk_rows",
     "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",
     "ps_shard_destroy", "ps_selftest_math", "ps_eval_log_f64", "ps_eval_log_f32",
+    "ps_ltss_f32",
 ]
 
 
@@ -100,6 +101,8 @@ def load():
         L.ps_selftest_math.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
         for nm in ("ps_eval_log_f64", "ps_eval_log_f32"):
             getattr(L, nm).argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ps_ltss_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -215,6 +218,17 @@ class Context:
         out = C.c_longlong(-1)
         self._check(self.lib.ps_selftest_math(self._h, which, samples, seed, C.byref(out)))
         return out.value
+
+    def ltss(self, a, b, dist):
+        """LTSSSolver<float>: returns dict(perm, subset, score)."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        n = a.shape[0]
+        perm = np.empty(n, np.int32)
+        lo, hi, sc = C.c_int(0), C.c_int(0), C.c_float(0)
+        self._check(self.lib.ps_ltss_f32(self._h, n, _vp(a), _vp(b), int(dist), _vp(perm), C.byref(lo), C.byref(hi),
+                                         C.byref(sc)))
+        return dict(perm=perm, subset=perm[lo.value:hi.value].copy(), score=np.float32(sc.value))
 
     def eval_log(self, x, dtype=np.float64):
         """Device log/logf on host arguments -> (general entry, safe-range entry)."""

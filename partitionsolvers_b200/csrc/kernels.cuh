@@ -745,6 +745,59 @@ __global__ void selftest_math_kernel(int which, long long per_thread, unsigned l
   if (bad) atomicAdd(mismatches, bad);
 }
 
+// ---------------------------------------------------------------------------------------------
+// LTSS (reference LTSS_impl.hpp:73-111): best single subset among the prefixes S(0,i), i = 1..n, then the
+// suffixes S(i,n), i = n-1..0, of the priority-sorted sequence under the multiple-clustering score; the first
+// strictly greater candidate in that visiting order wins.  Suffix scores are exactly level 1 of the DP
+// (level1_running_kernel); prefix sums are one sequential walk (two dependent adds per element).
+// ---------------------------------------------------------------------------------------------
+template <typename D>
+__global__ void ltss_prefix_sums_kernel(int n, const D* __restrict__ as, const D* __restrict__ bs,
+                                        D* __restrict__ PA, D* __restrict__ PB) {
+  // thread 0 walks a, thread 1 walks b: left to right from 0, like a_sums_[0][j] (score_impl.hpp:248-256)
+  if (blockIdx.x || threadIdx.x > 1) return;
+  const D* src = threadIdx.x ? bs : as;
+  D* dst = threadIdx.x ? PB : PA;
+  D acc = 0;
+#pragma unroll 8
+  for (int k = 0; k < n; ++k) {
+    acc = add_rn<D>(acc, src[k]);
+    dst[k] = acc;
+  }
+}
+
+__device__ __forceinline__ unsigned int float_order_key(float v) {
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// key = (orderable score << 32) | (0xffffffff - visiting order): atomicMax picks the largest score and, among
+// equal scores, the candidate visited first.  Scores are float whatever D is (LTSS.hpp:53,59).
+template <typename D>
+__global__ void ltss_argmax_kernel(int n, int dist, const D* __restrict__ PA, const D* __restrict__ PB,
+                                   const D* __restrict__ suffix_score, unsigned long long* __restrict__ best) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long key = 0;
+  if (g < n) {
+    // prefix [0, g+1): visiting order g
+    const float sp = (float)score_dyn<D>(dist, 0, PA[g], PB[g]);
+    if (sp > -3.402823466e+38f)
+      key = ((unsigned long long)float_order_key(sp) << 32) | (0xffffffffu - (unsigned)g);
+    // suffix [g, n): visited after every prefix, from i = n-1 down to 0
+    const float ss = (float)suffix_score[g];
+    if (ss > -3.402823466e+38f) {
+      const unsigned long long k2 =
+          ((unsigned long long)float_order_key(ss) << 32) | (0xffffffffu - (unsigned)(n + (n - 1 - g)));
+      key = k2 > key ? k2 : key;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
+}
+
 // Evaluate the device log routines on caller-supplied arguments (tests compare the bits with the host's libm).
 template <typename D>
 __global__ void eval_log_kernel(long long n, const D* __restrict__ x, D* __restrict__ y_general,

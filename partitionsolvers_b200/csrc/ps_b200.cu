@@ -460,6 +460,76 @@ ps_status range_score_impl(ps_ctx* ctx, int n, const D* a, const D* b, int dist,
   return PS_OK;
 }
 
+ps_status ltss_impl(ps_ctx* ctx, int n, const float* a, const float* b, int dist, int* perm_out, int* lo, int* hi,
+                    float* score) {
+  using D = float;
+  if (!ctx) return PS_ERR_INVALID;
+  ctx->err.clear();
+  if (!a || !b || !lo || !hi || !score || n < 1) {
+    ctx->err = "ps_ltss_f32: bad argument";
+    return PS_ERR_INVALID;
+  }
+  if (dist < 0 || dist > 2) {
+    ctx->err = "Bad distributional assignment";
+    return PS_ERR_DIST;
+  }
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ctx->tm.h2d_bytes = 0;
+  PS_TRY(ensure(ctx, ctx->a_in, (size_t)n * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->b_in, (size_t)n * sizeof(D)));
+  PS_CUDA(ctx, cudaMemcpyAsync(ctx->a_in.p, a, (size_t)n * sizeof(D), cudaMemcpyHostToDevice, st));
+  PS_CUDA(ctx, cudaMemcpyAsync(ctx->b_in.p, b, (size_t)n * sizeof(D), cudaMemcpyHostToDevice, st));
+  ps_problem p;
+  memset(&p, 0, sizeof(p));
+  p.n = n;
+  p.sort_mode = PS_SORT_DEVICE;  // stable, like LTSS's std::stable_sort (LTSS_impl.hpp:19)
+  PS_TRY(sort_stage<D>(ctx, p, (const D*)ctx->a_in.p, (const D*)ctx->b_in.p, 1, n));
+  const long long rec_stride = (long long)n + 1;
+  PS_TRY(ensure(ctx, ctx->rec, 2 * rec_stride * sizeof(ps::Rec4<D>)));
+  ps::Rec4<D>* rec0 = (ps::Rec4<D>*)ctx->rec.p;
+  ps::Rec4<D>* rec1 = rec0 + rec_stride;
+  const D* d_as = (const D*)ctx->a_s.p;
+  const D* d_bs = (const D*)ctx->b_s.p;
+  ps::build_rec_running_kernel<D><<<dim3(cdiv(n + 1, 256), 1), 256, 0, st>>>(n, rec_stride, d_as, d_bs, rec0, rec1);
+  // suffix scores S(i,n) under the mult-clust objective == level 1 of the DP
+  PS_TRY(ensure(ctx, ctx->ms, (size_t)n * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->ns, (size_t)n * sizeof(int)));
+  ps::level1_running_kernel<D, BR><<<dim3(cdiv(n, BR), 1), BR, 0, st>>>(
+      n, n + BR, 1, rec_stride, dist, 0, rec0, (D*)nullptr, (D*)nullptr, (D*)ctx->ms.p, (int*)ctx->ns.p, 0,
+      (ps::Rec4<D>*)nullptr, 0, 1, (D*)nullptr);
+  PS_TRY(ensure(ctx, ctx->part_val, 2 * (size_t)n * sizeof(D)));
+  D* PA = (D*)ctx->part_val.p;
+  D* PB = PA + n;
+  ps::ltss_prefix_sums_kernel<D><<<1, 32, 0, st>>>(n, d_as, d_bs, PA, PB);
+  PS_TRY(ensure(ctx, ctx->scalar, 64));
+  PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, sizeof(unsigned long long), st));
+  ps::ltss_argmax_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, dist, PA, PB, (const D*)ctx->ms.p,
+                                                          (unsigned long long*)ctx->scalar.p);
+  PS_CUDA(ctx, cudaGetLastError());
+  unsigned long long key = 0;
+  PS_CUDA(ctx, cudaMemcpyAsync(&key, ctx->scalar.p, sizeof(key), cudaMemcpyDeviceToHost, st));
+  if (perm_out) PS_CUDA(ctx, cudaMemcpyAsync(perm_out, ctx->perm.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (key == 0) {
+    *lo = *hi = 0;
+    *score = -3.402823466e+38f;
+    return PS_OK;
+  }
+  const unsigned int order = 0xffffffffu - (unsigned int)(key & 0xffffffffu);
+  unsigned int u = (unsigned int)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  memcpy(score, &u, sizeof(float));
+  if (order < (unsigned)n) {
+    *lo = 0;
+    *hi = (int)order + 1;
+  } else {
+    *lo = n - 1 - (int)(order - (unsigned)n);
+    *hi = n;
+  }
+  return PS_OK;
+}
+
 template <typename D>
 ps_status eval_log_impl(ps_ctx* ctx, long long n, const D* x, D* yg, D* yf) {
   if (!ctx || !x || !yg || !yf || n < 1) return PS_ERR_INVALID;
@@ -707,6 +777,11 @@ ps_status ps_selftest_math(ps_ctx* ctx, int which, long long samples, unsigned l
   PS_CUDA(ctx, cudaStreamSynchronize(st));
   *mismatches = (long long)bad;
   return PS_OK;
+}
+
+ps_status ps_ltss_f32(ps_ctx* ctx, int n, const float* a, const float* b, int dist, int* perm, int* lo, int* hi,
+                      float* score) {
+  return ltss_impl(ctx, n, a, b, dist, perm, lo, hi, score);
 }
 
 ps_status ps_eval_log_f64(ps_ctx* ctx, long long n, const double* x, double* y_general, double* y_fast) {

@@ -6,6 +6,8 @@
 %{
 #include <partitionsolvers/DP.hpp>
 #include "python_dpsolver.hpp"
+#include <partitionsolvers/LTSS.hpp>
+#include "python_ltsssolver.hpp"
 %}
 
 %include "std_vector.i"
@@ -30,3 +32,4 @@ namespace std {
 }
 
 %include "python_dpsolver.hpp"
+%include "python_ltsssolver.hpp"

@@ -5,6 +5,7 @@
 #include <pybind11/stl.h>
 
 #include "python_dpsolver.hpp"
+#include "python_ltsssolver.hpp"
 
 namespace py = pybind11;
 
@@ -80,6 +81,22 @@ PYBIND11_MODULE(proto, m) {
   }, py::arg("a"), py::arg("b"), py::arg("parametric_dist"), py::arg("risk_partitioning_objective"),
         py::arg("use_rational_optimization"));
 #undef PS_ARGS
+  // LTSS entry points (reference python_ltsssolver.hpp:10-23)
+  auto ints_to_tuple = [](const std::vector<int>& v) {
+    py::tuple out(v.size());
+    for (size_t i = 0; i < v.size(); ++i) out[i] = py::int_(v[i]);
+    return out;
+  };
+  m.def("find_optimal_partition__LTSS", [ints_to_tuple](int n, fvec a, fvec b, int d) {
+    return ints_to_tuple(find_optimal_partition__LTSS(n, std::move(a), std::move(b), d));
+  }, py::arg("n"), py::arg("a"), py::arg("b"), py::arg("parametric_dist"));
+  m.def("find_optimal_score__LTSS", [](int n, fvec a, fvec b, int d) {
+    return find_optimal_score__LTSS(n, std::move(a), std::move(b), d);
+  }, py::arg("n"), py::arg("a"), py::arg("b"), py::arg("parametric_dist"));
+  m.def("optimize_one__LTSS", [ints_to_tuple](int n, fvec a, fvec b, int d) {
+    auto r = optimize_one__LTSS(n, std::move(a), std::move(b), d);
+    return py::make_tuple(ints_to_tuple(r.first), py::float_(r.second));
+  }, py::arg("n"), py::arg("a"), py::arg("b"), py::arg("parametric_dist"));
   // SWIG template names used by callers as constructors (solverSWIG_DP.py:31-32)
   m.def("FArray", []() { return py::list(); });
   m.def("IArray", []() { return py::list(); });

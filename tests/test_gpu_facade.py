@@ -68,3 +68,28 @@ def test_proto_compute_score_and_errors(proto, oracle):
     assert np.float32(got) == oracle.range_score(a, b, 2, False, 0, 300, dtype=np.float32)
     with pytest.raises(proto.distributionException):
         proto.optimize_one__DP(300, 3, a.tolist(), b.tolist(), 5, True, False)
+
+
+def test_ltss_matches_oracle_and_dp(oracle, ctx, proto):
+    """LTSSSolver<float> on the device == the oracle restatement of LTSS_impl.hpp:73-111 (bit for bit), and the
+    reference's cross-solver property TestHighestScoringSetOf2TieOutAllDists (gtest_all.cpp:500-559): the top
+    subset of the T=2 multiple-clustering partition is the LTSS subset."""
+    rs = np.random.RandomState(33)
+    for dist in (0, 1, 2):
+        for n in (1, 2, 37, 300, 4097):
+            a = (rs.uniform(0.1, 10, n) if dist == 1 else rs.uniform(-10, 10, n)).astype(np.float32)
+            b = rs.uniform(0.1, 10, n).astype(np.float32)
+            want = oracle.ltss("port", a, b, dist)
+            got = ctx.ltss(a, b, dist)
+            assert np.array_equal(got["perm"], want["perm"])
+            assert got["subset"].tolist() == want["subset"].tolist(), (dist, n)
+            assert got["score"] == want["score"]
+            sub, sc = proto.optimize_one__LTSS(n, a.tolist(), b.tolist(), dist)
+            assert list(sub) == want["subset"].tolist() and np.float32(sc) == want["score"]
+            assert list(proto.find_optimal_partition__LTSS(n, a.tolist(), b.tolist(), dist)) == list(sub)
+            assert proto.find_optimal_score__LTSS(n, a.tolist(), b.tolist(), dist) == sc
+    for dist in (0, 1):
+        a = rs.uniform(0.1, 10, 500).astype(np.float32)
+        b = rs.uniform(0.1, 10, 500).astype(np.float32)
+        dp = host.DPSolver(500, 2, a, b, dist, False, True, dtype=np.float32, ctx=ctx)
+        assert sorted(dp.subsets[1].tolist()) == sorted(ctx.ltss(a, b, dist)["subset"].tolist())
