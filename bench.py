@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--sum-mode", default="running", choices=["running", "prefix"])
     ap.add_argument("--no-extras", action="store_true", help="skip variants, replicas and the CPU baseline")
     ap.add_argument("--skip-peaks", action="store_true", help="do not run the pipe-peak microbenchmark (ncu runs)")
+    ap.add_argument("--sharded-n", type=int, default=200000, help="N>1 only: size of the row-sharded instance")
+    ap.add_argument("--sharded-T", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -391,6 +393,30 @@ def main():
                                "n": c4["n"], "T": c4["T"], "dtype": "f32", "scaling": "strong",
                                "seconds_per_pass": rep_s, "includes": "H2D of inputs, D2H of boundaries+scores",
                                "cells_per_s_nominal": R_total * synth.nominal_cells(c4["n"], c4["T"]) / rep_s}
+        if world > 1:
+            # ---- one large instance, rows of every level sharded block-cyclically over the ranks with an NCCL
+            # all-gather of the level vector per level (BASELINE configs[4] shape at a size that runs in seconds)
+            from partitionsolvers_b200 import multigpu
+            n_s, T_s = args.sharded_n, args.sharded_T
+            a_s, b_s = synth.poisson_planted(n_s, T_s, seed=synth.SEED + 5, dtype=np.float64)
+            barrier()
+            t0 = time.perf_counter()
+            sh = multigpu.ShardedSolver(multigpu.CudaShardEngine(ctx, dev), a_s, b_s, T_s, 1, False, dtype=np.float64)
+            barrier()
+            sh_s = allmax(time.perf_counter() - t0)
+            lev_s = allmax(sh.seconds["levels_with_allgather"])
+            line["sharded"] = {"n": n_s, "T": T_s, "dtype": "f64", "seconds": sh_s, "scaling": "strong",
+                               "phase_seconds_rank0": sh.seconds, "levels_seconds_max_over_ranks": lev_s,
+                               "value": synth.nominal_cells(n_s, T_s) / sh_s, "unit": UNIT,
+                               "collective": "all_gather_into_tensor of the level vector per level (NCCL)",
+                               "ranks": world}
+            if rank == 0:
+                t0 = time.perf_counter()
+                one = ctx.solve_raw(a_s, b_s, T_s, 1, False, dtype=np.float64)
+                line["sharded"]["single_gpu_seconds"] = time.perf_counter() - t0
+                line["sharded"]["single_gpu_levels_seconds"] = ctx.timings()["levels_ms"] * 1e-3
+                line["sharded"]["same_partition_as_single_gpu"] = bool(
+                    np.array_equal(one["bounds"].ravel(), sh.bounds) and np.array_equal(one["perm"], sh.perm))
         if rank == 0 and world == 1:
             dtype = np.float64 if args.dtype == "f64" else np.float32
             which, kind, n_s = cpu_reference_sample(dtype, 10.0)

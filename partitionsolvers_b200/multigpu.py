@@ -138,9 +138,11 @@ class ShardedSolver:
         import torch.distributed as dist
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        import time
         n = len(a)
         Tc = min(T, n)
         self.n, self.T = n, Tc
+        t_start = time.perf_counter()
         perm, a_s, b_s = engine.sort(a, b, dtype)
         self.perm = perm
         eng = engine.create(a_s, b_s, n, Tc, dist_id, risk_part, dtype, self.rank, self.world)
@@ -153,15 +155,21 @@ class ShardedSolver:
                 dist.all_gather_into_tensor(gathered, chunk, group=group)
             else:
                 gathered.copy_(chunk)
+            if gathered.is_cuda:
+                # the engine runs on its own stream: finish the collective before the next engine call reads it
+                torch.cuda.current_stream(gathered.device).synchronize()
             if keep_levels:
                 self.levels.append(natural_from_gathered(gathered.cpu().numpy(), n, self.world, eng.chunk_rows))
 
+        t_setup = time.perf_counter()
         eng.level1(chunk)
         exchange()
+        t_l1 = time.perf_counter()
         for j in range(2, Tc + 1):
             eng.set_prev(gathered)
             eng.level(j, chunk)
             exchange()
+        t_levels = time.perf_counter()
         # backtrace: T point look-ups, each answered by the row's owner (DP_impl.hpp:131-139)
         bounds = [0]
         cur = 0
@@ -190,3 +198,7 @@ class ShardedSolver:
              for lo, hi in zip(bounds[:-1], bounds[1:])], dtype) if self.rank == 0 else None
         self.subsets = [perm[lo:hi] for lo, hi in zip(bounds[:-1], bounds[1:])]
         eng.close()
+        t_end = time.perf_counter()
+        # host wall-clock per phase on this rank (every engine call blocks on its stream)
+        self.seconds = {"sort_and_setup": t_setup - t_start, "level1": t_l1 - t_setup,
+                        "levels_with_allgather": t_levels - t_l1, "backtrace": t_end - t_levels}
