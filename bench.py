@@ -355,6 +355,10 @@ def main():
         "alg_flops_per_cell": flops_cell, "cells_per_launch_avg": main_res["level_cells_sum"] / max(
             1, main_res["level_launches"]), "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
         "share_of_step": main_res["level_ms_sum"] / (args.steps * main_res["ms_per_step"]),
+        "sfu": {"ops_per_cell": 1, "what": "one MUFU reciprocal per cell (division seed); log is table-driven, no MUFU",
+                "achieved_tops": main_res["level_cells_sum"] / lev_s / 1e12,
+                "peak_tops": (peaks["mufu_lg2_ops"] / 1e12) if peaks else 148 * 16 * 1.965e9 / 1e12,
+                "frac": (main_res["level_cells_sum"] / lev_s) / (peaks["mufu_lg2_ops"] if peaks else 148 * 16 * 1.965e9)},
         "hbm": {"alg_bytes_per_launch": alg_bytes_per_launch,
                 "achieved_gbs": alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "note": "not HBM-bound: algorithmic traffic is (4w+4)n bytes per level"},
@@ -393,6 +397,19 @@ def main():
                                "n": c4["n"], "T": c4["T"], "dtype": "f32", "scaling": "strong",
                                "seconds_per_pass": rep_s, "includes": "H2D of inputs, D2H of boundaries+scores",
                                "cells_per_s_nominal": R_total * synth.nominal_cells(c4["n"], c4["T"]) / rep_s}
+        # ---- the reference's own small configurations (BASELINE configs[0], [1]): latency of one host-buffer call
+        small = {}
+        for nm, dt_small in (("C1", np.float32), ("C2", np.float64)):
+            c = synth.CONFIGS[nm]
+            a_c, b_c = c["gen"](dt_small)
+            for _ in range(3):
+                ctx.solve_raw(a_c, b_c, c["T"], c["dist"], c["risk_part"], dtype=dt_small)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                ctx.solve_raw(a_c, b_c, c["T"], c["dist"], c["risk_part"], dtype=dt_small)
+            small[nm] = {"n": c["n"], "T": c["T"], "dtype": np.dtype(dt_small).name,
+                         "ms_per_call_host_buffers": 1e3 * (time.perf_counter() - t0) / 20}
+        line["small_configs"] = small
         if world > 1:
             # ---- one large instance, rows of every level sharded block-cyclically over the ranks with an NCCL
             # all-gather of the level vector per level (BASELINE configs[4] shape at a size that runs in seconds)

@@ -240,6 +240,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     ctx->err = "n, T and batch must be >= 1";
     return PS_ERR_INVALID;
   }
+  if (p.batch > 65535) {
+    ctx->err = "batch > 65535 instances per call: split the batch";
+    return PS_ERR_UNSUPPORTED;
+  }
   if (p.dist < 0 || p.dist > 2) {
     ctx->err = "Bad distributional assignment";
     return PS_ERR_DIST;
