@@ -25,64 +25,78 @@ struct __align__(16) GlogEntry {
 __device__ const GlogEntry g_glog_tab[128] = PS_GLOG_TAB_INIT;
 __device__ const GlogEntry g_glogf_tab[16] = PS_GLOGF_TAB_INIT;
 
+// Polynomial coefficients live in the constant bank: an FP64 instruction can take a c[bank][offset] operand
+// directly, whereas a 64-bit literal costs two uniform-register moves every time it is rematerialised
+// (12 of the 78 instructions per cell before this change; FP64 instructions hold the issue port for two
+// cycles each, so every other instruction is on the critical path of this kernel).
+struct GlogCoef {
+  double ln2hi, ln2lo, a[5], b[11], fln2, fa[3], one27, neg_one27, magic;
+};
+__constant__ GlogCoef c_glog = {
+    PS_GLOG_LN2HI, PS_GLOG_LN2LO,
+    {PS_GLOG_A0, PS_GLOG_A1, PS_GLOG_A2, PS_GLOG_A3, PS_GLOG_A4},
+    {PS_GLOG_B0, PS_GLOG_B1, PS_GLOG_B2, PS_GLOG_B3, PS_GLOG_B4, PS_GLOG_B5, PS_GLOG_B6, PS_GLOG_B7, PS_GLOG_B8,
+     PS_GLOG_B9, PS_GLOG_B10},
+    PS_GLOGF_LN2, {PS_GLOGF_A0, PS_GLOGF_A1, PS_GLOGF_A2}, 0x1p27, -0x1p27, 0x1.000008p52};
+
 __device__ __forceinline__ double int_to_double_exact(int k) {
   // (double)k without the conversion pipe: 2^52 + 2^31 + k is exact, then subtract the bias
-  return __dadd_rn(__hiloint2double(0x43300000, k ^ 0x80000000), -__longlong_as_double(0x4330000080000000LL));
+  return __dadd_rn(__hiloint2double(0x43300000, k ^ 0x80000000), -c_glog.magic);
 }
 
 // x positive, normal, finite (hi/lo are its two words; the subnormal path passes rescaled words).
-__device__ __forceinline__ double glibc_log_core(double x, int hi, int lo) {
+// tab = the 128-entry table: g_glog_tab in global memory, or a shared-memory copy (2 KB) in the level kernels.
+__device__ __forceinline__ double glibc_log_core(double x, int hi, int lo,
+                                                 const GlogEntry* __restrict__ tab = g_glog_tab) {
   if ((unsigned)(hi - 0x3FEE0000) < 0x30900u) {
     // 1 - 2^-4 <= x < 1 + 0x1.09p-4
     const double r = __dadd_rn(x, -1.0);
-    double t2 = __fma_rn(r, PS_GLOG_B2, PS_GLOG_B1);
-    double t3 = __fma_rn(r, PS_GLOG_B5, PS_GLOG_B4);
+    double t2 = __fma_rn(r, c_glog.b[2], c_glog.b[1]);
+    double t3 = __fma_rn(r, c_glog.b[5], c_glog.b[4]);
     const double r2 = __dmul_rn(r, r);
-    const double t5 = __fma_rn(r, PS_GLOG_B8, PS_GLOG_B7);
-    t2 = __fma_rn(r2, PS_GLOG_B3, t2);
-    t3 = __fma_rn(r2, PS_GLOG_B6, t3);
+    const double t5 = __fma_rn(r, c_glog.b[8], c_glog.b[7]);
+    t2 = __fma_rn(r2, c_glog.b[3], t2);
+    t3 = __fma_rn(r2, c_glog.b[6], t3);
     const double r3 = __dmul_rn(r, r2);
-    double t1 = __fma_rn(r2, PS_GLOG_B9, t5);
-    t1 = __fma_rn(r3, PS_GLOG_B10, t1);
+    double t1 = __fma_rn(r2, c_glog.b[9], t5);
+    t1 = __fma_rn(r3, c_glog.b[10], t1);
     t1 = __fma_rn(t1, r3, t3);
     t1 = __fma_rn(t1, r3, t2);
-    const double w = __fma_rn(r, 0x1p27, r);
-    const double rhi = __fma_rn(-0x1p27, r, w);
+    const double w = __fma_rn(r, c_glog.one27, r);
+    const double rhi = __fma_rn(c_glog.neg_one27, r, w);
     const double rhi2 = __dmul_rn(rhi, rhi);
     const double rlo = __dadd_rn(r, -rhi);
-    const double h = __fma_rn(rhi2, PS_GLOG_B0, r);
+    const double h = __fma_rn(rhi2, c_glog.b[0], r);
     const double d = __dadd_rn(r, -h);
     const double s = __dadd_rn(r, rhi);
-    double l = __fma_rn(rhi2, PS_GLOG_B0, d);
-    const double m = __dmul_rn(PS_GLOG_B0, rlo);
+    double l = __fma_rn(rhi2, c_glog.b[0], d);
+    const double m = __dmul_rn(c_glog.b[0], rlo);
     l = __fma_rn(m, s, l);
     const double y = __fma_rn(t1, r3, l);
     return __dadd_rn(h, y);
   }
   const int thi = hi - 0x3fe60000;
-  const int i = (thi >> 13) & 127;
-  const int k = thi >> 20;
   const double z = __hiloint2double(hi - (thi & 0xfff00000), lo);
-  const GlogEntry e = g_glog_tab[i];
-  const double kd = int_to_double_exact(k);
-  const double w = __fma_rn(kd, PS_GLOG_LN2HI, e.logc);
+  const GlogEntry e = *reinterpret_cast<const GlogEntry*>(reinterpret_cast<const char*>(tab) + ((thi >> 9) & 0x7f0));
+  const double kd = __int2double_rn(thi >> 20);  // conversion pipe (idle in this kernel) instead of an FP64 add
+  const double w = __fma_rn(kd, c_glog.ln2hi, e.logc);
   const double r = __fma_rn(z, e.invc, -1.0);
-  const double p12 = __fma_rn(r, PS_GLOG_A2, PS_GLOG_A1);
+  const double p12 = __fma_rn(r, c_glog.a[2], c_glog.a[1]);
   const double h = __dadd_rn(r, w);
   const double r2 = __dmul_rn(r, r);
   double l = __dadd_rn(__dadd_rn(w, -h), r);
-  l = __fma_rn(kd, PS_GLOG_LN2LO, l);
+  l = __fma_rn(kd, c_glog.ln2lo, l);
   const double r3 = __dmul_rn(r, r2);
-  const double p34 = __fma_rn(r, PS_GLOG_A4, PS_GLOG_A3);
-  l = __fma_rn(r2, PS_GLOG_A0, l);
+  const double p34 = __fma_rn(r, c_glog.a[4], c_glog.a[3]);
+  l = __fma_rn(r2, c_glog.a[0], l);
   const double p = __fma_rn(p34, r2, p12);
   const double y = __fma_rn(r3, p, l);
   return __dadd_rn(y, h);
 }
 
 // operands proven positive and normal by the safe-range precheck
-__device__ __forceinline__ double glibc_log_fast(double x) {
-  return glibc_log_core(x, __double2hiint(x), __double2loint(x));
+__device__ __forceinline__ double glibc_log_fast(double x, const GlogEntry* __restrict__ tab = g_glog_tab) {
+  return glibc_log_core(x, __double2hiint(x), __double2loint(x), tab);
 }
 
 // every double: zero -> -inf, negative / NaN -> NaN, +inf -> +inf, subnormals rescaled by 2^52
@@ -118,11 +132,11 @@ __device__ __forceinline__ float glibc_logf_core(int ix, const GlogEntry* __rest
   const GlogEntry e = *reinterpret_cast<const GlogEntry*>(reinterpret_cast<const char*>(tab) + ((tmp >> 15) & 0xf0));
   const double z = (double)__int_as_float(iz);  // exact (cvt.f64.f32)
   const double r = __fma_rn(z, e.invc, -1.0);
-  const double y0 = __fma_rn(kd, PS_GLOGF_LN2, e.logc);
-  double y = __fma_rn(r, PS_GLOGF_A1, PS_GLOGF_A2);
+  const double y0 = __fma_rn(kd, c_glog.fln2, e.logc);
+  double y = __fma_rn(r, c_glog.fa[1], c_glog.fa[2]);
   const double r2 = __dmul_rn(r, r);
   const double q = __dadd_rn(r, y0);
-  y = __fma_rn(r2, PS_GLOGF_A0, y);
+  y = __fma_rn(r2, c_glog.fa[0], y);
   y = __fma_rn(r2, y, q);
   return __double2float_rn(y);
 }

@@ -77,6 +77,14 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
                   const D* __restrict__ SB, D* __restrict__ part_val, int* __restrict__ part_arg) {
   constexpr int BK = BR;
   __shared__ Rec4<D> sbuf[2][BK];
+  // double Poisson on the fast path: a shared-memory copy of glibc's 128-entry log table (2 KB), so the
+  // per-cell lookup is one LDS at a 32-bit offset instead of a 64-bit address computation + global load
+  constexpr bool kLogTab = (sizeof(D) == 8) && (DIST == DIST_POISSON) && FAST;
+  __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
+  if (kLogTab) {
+    static_assert(BR >= 128, "one table entry per thread");
+    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
+  }
 
   const int inst = blockIdx.y;
   rec += (long long)inst * g.rec_stride;
@@ -124,6 +132,12 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
   }
   D best = Lim<D>::lowest();
   int arg = -1;
+  auto score_of = [&](D a_sum, D b_sum) -> D {
+    if constexpr (kLogTab)
+      return ScoreFn<D, DIST, RP, FAST>::eval(a_sum, b_sum, s_log);
+    else
+      return ScoreFn<D, DIST, RP, FAST>::eval(a_sum, b_sum);
+  };
 
   const int nk = k_hi - k_lo + 1;
   const int nstages = (nk + BK - 1) / BK;
@@ -157,7 +171,7 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
             A = sub_rn<D>(r.x, Xi);
             B = sub_rn<D>(r.y, Yi);
           }
-          const D v = add_rn<D>(ScoreFn<D, DIST, RP, FAST>::eval(A, B), r.p);
+          const D v = add_rn<D>(score_of(A, B), r.p);
           if (v > best) {
             best = v;
             arg = kb + kk;
@@ -173,7 +187,7 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
             A = sub_rn<D>(r.x, Xi);
             B = sub_rn<D>(r.y, Yi);
           }
-          const D v = add_rn<D>(ScoreFn<D, DIST, RP, FAST>::eval(A, B), r.p);
+          const D v = add_rn<D>(score_of(A, B), r.p);
           if (v > best) {
             best = v;
             arg = kb + kk;
@@ -193,7 +207,7 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
             A = sub_rn<D>(r.x, Xi);
             B = sub_rn<D>(r.y, Yi);
           }
-          const D v = add_rn<D>(ScoreFn<D, DIST, RP, FAST>::eval(A, B), r.p);
+          const D v = add_rn<D>(score_of(A, B), r.p);
           if (v > best) {
             best = v;
             arg = k;

@@ -31,7 +31,9 @@ template <bool FAST> __device__ __forceinline__ float div_f(float a, float b) { 
 template <bool FAST> __device__ __forceinline__ double div_d(double a, double b) { return FAST ? fast_ddiv(a, b) : __ddiv_rn(a, b); }
 // log = glibc's algorithm (glibc_log.cuh): bit-identical to the std::log the reference calls
 template <bool FAST> __device__ __forceinline__ float log_f(float x) { return FAST ? glibc_logf_fast(x) : glibc_logf(x); }
-template <bool FAST> __device__ __forceinline__ double log_d(double x) { return FAST ? glibc_log_fast(x) : glibc_log(x); }
+template <bool FAST> __device__ __forceinline__ double log_d(double x, const GlogEntry* tab = g_glog_tab) {
+  return FAST ? glibc_log_fast(x, tab) : glibc_log(x);
+}
 
 // ------------------------------------------------------------------ float
 template <bool FAST>
@@ -74,9 +76,9 @@ struct ScoreFn<float, DIST_RATIONAL, RP, FAST> {
 // ------------------------------------------------------------------ double
 template <bool FAST>
 struct ScoreFn<double, DIST_POISSON, false, FAST> {
-  static __device__ __forceinline__ double eval(double A, double B) {
+  static __device__ __forceinline__ double eval(double A, double B, const GlogEntry* tab = g_glog_tab) {
     double q = div_d<FAST>(A, B);
-    double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log_d<FAST>(q)), B), A);
+    double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log_d<FAST>(q, tab)), B), A);
     // FAST: A, B are positive normal doubles, for which the order of the bit patterns is the numeric order;
     // the integer compare keeps one instruction off the FP64 pipe, which is the pipe that bounds this kernel
     const bool gt = FAST ? (__double_as_longlong(A) > __double_as_longlong(B)) : (A > B);
@@ -85,8 +87,8 @@ struct ScoreFn<double, DIST_POISSON, false, FAST> {
 };
 template <bool FAST>
 struct ScoreFn<double, DIST_POISSON, true, FAST> {
-  static __device__ __forceinline__ double eval(double A, double B) {
-    return __dmul_rn(A, log_d<FAST>(div_d<FAST>(A, B)));
+  static __device__ __forceinline__ double eval(double A, double B, const GlogEntry* tab = g_glog_tab) {
+    return __dmul_rn(A, log_d<FAST>(div_d<FAST>(A, B), tab));
   }
 };
 template <bool FAST>
