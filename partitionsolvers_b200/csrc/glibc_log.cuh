@@ -30,19 +30,14 @@ __device__ const GlogEntry g_glogf_tab[16] = PS_GLOGF_TAB_INIT;
 // (12 of the 78 instructions per cell before this change; FP64 instructions hold the issue port for two
 // cycles each, so every other instruction is on the critical path of this kernel).
 struct GlogCoef {
-  double ln2hi, ln2lo, a[5], b[11], fln2, fa[3], one27, neg_one27, magic;
+  double ln2hi, ln2lo, a[5], b[11], one27, neg_one27;
 };
 __constant__ GlogCoef c_glog = {
     PS_GLOG_LN2HI, PS_GLOG_LN2LO,
     {PS_GLOG_A0, PS_GLOG_A1, PS_GLOG_A2, PS_GLOG_A3, PS_GLOG_A4},
     {PS_GLOG_B0, PS_GLOG_B1, PS_GLOG_B2, PS_GLOG_B3, PS_GLOG_B4, PS_GLOG_B5, PS_GLOG_B6, PS_GLOG_B7, PS_GLOG_B8,
      PS_GLOG_B9, PS_GLOG_B10},
-    PS_GLOGF_LN2, {PS_GLOGF_A0, PS_GLOGF_A1, PS_GLOGF_A2}, 0x1p27, -0x1p27, 0x1.000008p52};
-
-__device__ __forceinline__ double int_to_double_exact(int k) {
-  // (double)k without the conversion pipe: 2^52 + 2^31 + k is exact, then subtract the bias
-  return __dadd_rn(__hiloint2double(0x43300000, k ^ 0x80000000), -c_glog.magic);
-}
+    0x1p27, -0x1p27};
 
 // x positive, normal, finite (hi/lo are its two words; the subnormal path passes rescaled words).
 // tab = the 128-entry table: g_glog_tab in global memory, or a shared-memory copy (2 KB) in the level kernels.
@@ -115,28 +110,24 @@ __device__ __forceinline__ double glibc_log(double x) {
 }
 
 // ---- logf -------------------------------------------------------------------------------------------
-__device__ __forceinline__ double float_to_double_exact(int bits) {
-  // positive normal float -> double by re-biasing the exponent (no conversion pipe)
-  return __hiloint2double(((unsigned)bits >> 3) + 0x38000000, bits << 29);
-}
-
 // tab = the 16-entry table, in global memory (g_glogf_tab) or a shared-memory copy of it
 __device__ __forceinline__ float glibc_logf_core(int ix, const GlogEntry* __restrict__ tab = g_glogf_tab) {
   const int tmp = ix - 0x3f330000;
-  // k = tmp >> 23 (arithmetic), written as a signed bit-field extract: ptxas 12.9 was seen to fold
-  // "(ix + c) >> 23, then ^ 0x80000000" into a single add for one of two inlined copies, dropping the shift
+  // k = tmp >> 23 (arithmetic), written as a signed bit-field extract: with the plain shift feeding an
+  // integer->double bit trick, ptxas 12.9 was seen to fold "(ix + c) >> 23, then ^ 0x80000000" into a single
+  // add for one of two inlined copies, dropping the shift (caught by the bit-exactness tests)
   int k;
   asm("bfe.s32 %0, %1, 23, 9;" : "=r"(k) : "r"(tmp));
-  const double kd = int_to_double_exact(k);
+  const double kd = __int2double_rn(k);  // conversion pipe; keeps an FP64 add (two issue cycles) out of the cell
   const int iz = ix - (tmp & 0xff800000);
   const GlogEntry e = *reinterpret_cast<const GlogEntry*>(reinterpret_cast<const char*>(tab) + ((tmp >> 15) & 0xf0));
   const double z = (double)__int_as_float(iz);  // exact (cvt.f64.f32)
   const double r = __fma_rn(z, e.invc, -1.0);
-  const double y0 = __fma_rn(kd, c_glog.fln2, e.logc);
-  double y = __fma_rn(r, c_glog.fa[1], c_glog.fa[2]);
+  const double y0 = __fma_rn(kd, PS_GLOGF_LN2, e.logc);
+  double y = __fma_rn(r, PS_GLOGF_A1, PS_GLOGF_A2);
   const double r2 = __dmul_rn(r, r);
   const double q = __dadd_rn(r, y0);
-  y = __fma_rn(r2, c_glog.fa[0], y);
+  y = __fma_rn(r2, PS_GLOGF_A0, y);
   y = __fma_rn(r2, y, q);
   return __double2float_rn(y);
 }

@@ -53,9 +53,7 @@ struct Geom {
   int rb_first, rb_step;
 };
 
-__host__ __device__ inline int geom_count_tiles(int NRB_total_hint, int NCH, int G, int NRB, int rb_first,
-                                                int rb_step) {
-  (void)NRB_total_hint;
+__host__ __device__ inline int geom_count_tiles(int NCH, int G, int NRB, int rb_first, int rb_step) {
   // number of owned row blocks whose diagonal chunk s satisfies s + d <= NCH-1, summed over d
   long long t = 0;
   for (int d = 0; d < NCH; ++d) {

@@ -168,7 +168,7 @@ ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int
   g.rec_stride = (long long)n + 1;
   g.rb_first = rb_first;
   g.rb_step = rb_step;
-  g.ntiles = ps::geom_count_tiles(0, g.NCH, g.G, g.NRB, rb_first, rb_step);
+  g.ntiles = ps::geom_count_tiles(g.NCH, g.G, g.NRB, rb_first, rb_step);
   return g;
 }
 
@@ -258,9 +258,6 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   }
   const int n = p.n, R = p.batch;
   const int Tc = std::min(p.T, n);  // DP_impl.hpp:37-38
-  if (Tc - 1 > PS_MAX_TIMED_LEVELS) {
-    // timing slots only; the solve itself has no such limit
-  }
   const int running = (p.sum_mode == PS_SUM_RUNNING);
   const int rp = p.risk_part ? 1 : 0;
   PS_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -256,3 +256,35 @@ def test_full_size_C4_replica_shape(oracle, ctx):
         check_levels(raw["max_score"][r], raw["next_start"][r], refs[r]["max_score"], refs[r]["next_start"],
                      tol_for(np.float32, True), TIE[np.float32],
                      _recompute_fn(oracle, a_s, b_s, refs[r]["max_score"], 1, True, np.float32))
+
+
+def test_device_pointer_call_equals_host_buffer_call(ctx):
+    """ps_problem.on_device = 1 (inputs and outputs resident in HBM, what bench.py's `value` times) gives the
+    same boundaries, scores and sort index as the host-buffer call."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    a, b = synth.poisson_planted(6000, 9, seed=71, dtype=np.float64)
+    want = ctx.solve_raw(a, b, 9, 1, False, dtype=np.float64, sweep=True)
+    a_d, b_d = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    perm_d = torch.empty(6000, dtype=torch.int32, device=dev)
+    bounds_d = torch.empty((10, 10), dtype=torch.int32, device=dev)
+    sc_d = torch.empty((10, 9), dtype=torch.float64, device=dev)
+    ctx.solve_device(a_d.data_ptr(), b_d.data_ptr(), 6000, 9, 1, False, np.float64, sweep=True,
+                     d_perm_out=perm_d.data_ptr(), d_bounds=bounds_d.data_ptr(), d_scores=sc_d.data_ptr())
+    assert np.array_equal(perm_d.cpu().numpy(), want["perm"])
+    assert np.array_equal(bounds_d.cpu().numpy(), want["bounds"])
+    assert np.array_equal(sc_d.cpu().numpy(), want["subset_scores"])
+
+
+def test_batched_sweep_prefix_mode_and_limits(oracle, ctx):
+    a, b = synth.poisson_null(400, seed=72, dtype=np.float32, replicas=5)
+    rb = ctx.solve_raw(a, b, 6, 1, True, dtype=np.float32, sweep=True, sum_mode=capi.PS_SUM_PREFIX)
+    for r in range(5):
+        ref = oracle.solve("port", a[r], b[r], 6, 1, True, dtype=np.float32, sweep=True)
+        if np.array_equal(rb["perm"][r], ref["perm"]):  # tie order may differ (stable vs std::sort)
+            s = host.DPSolver(400, 6, a[r], b[r], 1, True, True, 0.0, 1, True, False, dtype=np.float32, ctx=ctx,
+                              sum_mode=capi.PS_SUM_PREFIX)
+            for S in range(1, 7):
+                assert s.all[S][1] == ref["all"][S][1]
+    with pytest.raises(capi.PsError):
+        ctx.solve_raw(np.ones((65536, 4), np.float32), np.ones((65536, 4), np.float32), 2, 2, False)
