@@ -397,6 +397,19 @@ def main():
                                "n": c4["n"], "T": c4["T"], "dtype": "f32", "scaling": "strong",
                                "seconds_per_pass": rep_s, "includes": "H2D of inputs, D2H of boundaries+scores",
                                "cells_per_s_nominal": R_total * synth.nominal_cells(c4["n"], c4["T"]) / rep_s}
+        # ---- paper-scale null table (SimulatedExperiments.py:339-345: n=5000, 1000 replicas, T in {2,3,5,10}, both
+        # objectives): replicas generated on the device, two batched sweep solves (randomization.py)
+        if rank == 0:
+            from partitionsolvers_b200 import randomization as rz
+            rz.create_null_scores(64, 5000, 100.0, (2, 3, 5, 10), ctx=ctx, seed=1)  # warm-up (allocations)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tab = rz.create_null_scores(1000, 5000, 100.0, (2, 3, 5, 10), ctx=ctx, seed=1869)
+            torch.cuda.synchronize()
+            line["null_table_paper_scale"] = {
+                "seconds": time.perf_counter() - t0, "replicas": 1000, "n": 5000, "cluster_list": [2, 3, 5, 10],
+                "columns": sorted(tab.keys()), "dtype": "f32",
+                "what": "device-side replica generation + rp and mcd scores for every T (8 reference solves per replica)"}
         # ---- the reference's own small configurations (BASELINE configs[0], [1]): latency of one host-buffer call
         small = {}
         for nm, dt_small in (("C1", np.float32), ("C2", np.float64)):
