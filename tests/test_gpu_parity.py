@@ -288,3 +288,24 @@ def test_batched_sweep_prefix_mode_and_limits(oracle, ctx):
                 assert s.all[S][1] == ref["all"][S][1]
     with pytest.raises(capi.PsError):
         ctx.solve_raw(np.ones((65536, 4), np.float32), np.ones((65536, 4), np.float32), 2, 2, False)
+
+
+def test_one_million_elements_sampled_rows(oracle, ctx):
+    """BASELINE configs[4] size on one GPU (n = 1,000,000; T = 3 keeps it to one full level): sampled rows of level 2
+    and the final row, recomputed by the oracle from the GPU's own level-1 row, must agree bit for bit -- guards the
+    64-bit index arithmetic, the 16384-wide chunks and the 62-chunk SA/SB tables."""
+    n, T = 1_000_000, 3
+    a, b = synth.poisson_planted(n, 8, seed=81, dtype=np.float64)
+    r = ctx.solve_raw(a, b, T, 1, False, dtype=np.float64, levels=True)
+    a_s, b_s = a[r["perm"]], b[r["perm"]]
+    bd = r["bounds"][0]
+    assert bd[0] == 0 and bd[-1] == n and np.all(np.diff(bd) > 0)
+    rows = np.array([0, 1, 127, 128, 16383, 16384, 16385, 500_000, 999_000, n - 3, n - 2], np.int32)
+    best, arg = oracle.dp_rows(a_s, b_s, r["max_score"][1], n - 1, 1, False, rows, dtype=np.float64)
+    assert np.array_equal(r["max_score"][2][rows], best)
+    assert np.array_equal(r["next_start"][2][rows], arg)
+    best, arg = oracle.dp_rows(a_s, b_s, r["max_score"][2], n - 2, 1, False, np.array([0], np.int32), dtype=np.float64)
+    assert r["max_score"][3][0] == best[0] and r["next_start"][3][0] == arg[0]
+    # level 1 itself: S(i, n) for a few i
+    for i in (0, 12345, n - 1):
+        assert r["max_score"][1][i] == oracle.range_score(a_s, b_s, 1, False, i, n, dtype=np.float64)
