@@ -489,22 +489,8 @@ __global__ void level1_prefix_kernel(int n, long long rec_stride, int dist, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 1: priority keys, gather, level records.
+// Stage 1 (after the radix sort in radix_sort.cuh): gather, level records.
 // ---------------------------------------------------------------------------------------------
-template <typename D>
-__global__ void keys_kernel(long long total, int n, const D* __restrict__ a, const D* __restrict__ b,
-                            D* __restrict__ key, int* __restrict__ idx) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
-  key[g] = a[g] / b[g];  // IEEE divide in D, as the comparator of DP_impl.hpp:14-15
-  idx[g] = (int)(g % n);
-}
-
-__global__ void offsets_kernel(int R, int n, int* __restrict__ off) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g <= R) off[g] = g * n;
-}
-
 template <typename D>
 __global__ void gather_kernel(long long total, int n, const int* __restrict__ perm,
                               const D* __restrict__ a, const D* __restrict__ b, D* __restrict__ as,

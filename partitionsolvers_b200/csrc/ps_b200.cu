@@ -1,15 +1,12 @@
 // ps_b200.cu -- C ABI (include/ps_b200.h) over the sm_100a kernels in kernels.cuh.
 //
 // Host-side orchestration of one DPSolver construction (reference DP_impl.hpp:69-230):
-//   sort_by_priority  -> keys_kernel + device radix sort + gather_kernel
+//   sort_by_priority  -> sort_keys_kernel + stable LSD radix sort (radix_sort.cuh) + gather_kernel
 //   createContext     -> build_rec_* (no n x n tables)
 //   create()          -> level-1 kernel, then per level j=2..T: level_tile_kernel + combine_kernel
 //   optimize()        -> backtrace_bounds_kernel + backtrace_scores_kernel
 // Everything runs on the context's own non-blocking stream; the call blocks on that stream only.
 #include <cuda_runtime.h>
-
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -20,6 +17,7 @@
 
 #include "../../include/ps_b200.h"
 #include "kernels.cuh"
+#include "radix_sort.cuh"
 
 namespace {
 
@@ -39,7 +37,7 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, cub_tmp, seg_off, scalar;
+      bounds, scores, sort_hist, scalar;
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
   long long launches = 0;
@@ -190,35 +188,27 @@ ps_status sort_stage(ps_ctx* ctx, const ps_problem& p, const D* d_a, const D* d_
                                  p.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     if (!p.on_device) ctx->tm.h2d_bytes += total * sizeof(int);
   } else {
-    PS_TRY(ensure(ctx, ctx->key_in, total * sizeof(D)));
-    PS_TRY(ensure(ctx, ctx->key_out, total * sizeof(D)));
+    // stable LSD radix sort of (a/b, index), all instances at once (radix_sort.cuh)
+    using U = typename ps::SortKey<D>::U;
+    const int tiles = cdiv(n, ps::SORT_TILE);
+    PS_TRY(ensure(ctx, ctx->key_in, total * sizeof(U)));
+    PS_TRY(ensure(ctx, ctx->key_out, total * sizeof(U)));
     PS_TRY(ensure(ctx, ctx->idx_in, total * sizeof(int)));
-    D* kin = (D*)ctx->key_in.p;
-    D* kout = (D*)ctx->key_out.p;
-    int* iin = (int*)ctx->idx_in.p;
-    ps::keys_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, n, d_a, d_b, kin, iin);
+    PS_TRY(ensure(ctx, ctx->sort_hist, (size_t)R * 256 * tiles * sizeof(unsigned int)));
+    U* kbuf[2] = {(U*)ctx->key_in.p, (U*)ctx->key_out.p};
+    int* ibuf[2] = {d_perm, (int*)ctx->idx_in.p};  // an even number of passes ends in d_perm
+    unsigned int* hist = (unsigned int*)ctx->sort_hist.p;
+    ps::sort_keys_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, n, d_a, d_b, kbuf[0], ibuf[0]);
     ctx->launches++;
-    size_t tmp = 0;
-    if (R == 1) {
-      PS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, iin, d_perm, (int)total, 0,
-                                                   (int)sizeof(D) * 8, st));
-      PS_TRY(ensure(ctx, ctx->cub_tmp, tmp));
-      PS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, kin, kout, iin, d_perm,
-                                                   (int)total, 0, (int)sizeof(D) * 8, st));
-    } else {
-      PS_TRY(ensure(ctx, ctx->seg_off, (size_t)(R + 1) * sizeof(int)));
-      int* off = (int*)ctx->seg_off.p;
-      ps::offsets_kernel<<<cdiv(R + 1, 256), 256, 0, st>>>(R, n, off);
-      ctx->launches++;
-      PS_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, kin, kout, iin, d_perm,
-                                                            (int)total, R, off, off + 1, 0,
-                                                            (int)sizeof(D) * 8, st));
-      PS_TRY(ensure(ctx, ctx->cub_tmp, tmp));
-      PS_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortPairs(ctx->cub_tmp.p, tmp, kin, kout, iin, d_perm,
-                                                            (int)total, R, off, off + 1, 0,
-                                                            (int)sizeof(D) * 8, st));
+    static_assert(ps::SortKey<D>::PASSES % 2 == 0, "result must land in the first buffer");
+    for (int pass = 0; pass < ps::SortKey<D>::PASSES; ++pass) {
+      const int src = pass & 1, dst = src ^ 1;
+      ps::sort_histogram_kernel<U><<<dim3(tiles, R), ps::SORT_THREADS, 0, st>>>(n, tiles, 8 * pass, kbuf[src], hist);
+      ps::sort_scan_kernel<<<R, ps::SORT_THREADS, 0, st>>>(tiles, hist);
+      ps::sort_scatter_kernel<U><<<dim3(tiles, R), ps::SORT_THREADS, 0, st>>>(n, tiles, 8 * pass, kbuf[src], ibuf[src],
+                                                                             kbuf[dst], ibuf[dst], hist);
+      ctx->launches += 3;
     }
-    ctx->launches += 8;  // radix passes (histogram + onesweep); library kernels, counted approximately
   }
   ps::gather_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, n, d_perm, d_a, d_b, (D*)ctx->a_s.p,
                                                          (D*)ctx->b_s.p);
@@ -726,8 +716,8 @@ void ps_destroy(ps_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->a_in,  &ctx->b_in,     &ctx->key_in,   &ctx->key_out, &ctx->idx_in, &ctx->perm,
                     &ctx->a_s,   &ctx->b_s,      &ctx->rec,      &ctx->SA,      &ctx->SB,     &ctx->part_val,
-                    &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->cub_tmp,
-                    &ctx->seg_off,  &ctx->scalar};
+                    &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->sort_hist,
+                    &ctx->scalar};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
