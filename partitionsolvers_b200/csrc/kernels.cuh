@@ -131,6 +131,12 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
   D best = Lim<D>::lowest();
   int arg = -1;
   auto score_of = [&](D a_sum, D b_sum) -> D {
+    // The multiple-clustering Poisson and Gaussian scores are 0 unless A > B (score_impl.hpp:385-388, 429-431).
+    // The reference's ternary skips the division and the log there, and so does this branch: lanes are adjacent
+    // rows at the same k, so a warp is uniformly on one side of the A = B frontier except along the frontier itself.
+    if constexpr (!RP && DIST != DIST_RATIONAL) {
+      if (!gt_ab<FAST>(a_sum, b_sum)) return (D)0;
+    }
     if constexpr (kLogTab)
       return ScoreFn<D, DIST, RP, FAST>::eval(a_sum, b_sum, s_log);
     else
@@ -297,17 +303,22 @@ level_tile_kernel_pois_f32x2(Geom g, const Rec4<float>* __restrict__ rec, const 
         const Rec4<float> r = sb[kk];
         A = __fadd2_rn(A, make_float2(r.x, r.x));
         B = __fadd2_rn(B, make_float2(r.y, r.y));
-        const float2 q = fast_fdiv2(A, B);
-        const float2 l = make_float2(glibc_logf_fast(q.x, s_logf), glibc_logf_fast(q.y, s_logf));
-        // A*l with two scalar multiplies: ptxas (12.9) contracts mul.rn.f32x2 (and fma.rn.f32x2 with a -0 addend)
-        // followed by add.rn.f32x2 into one FFMA2 despite the explicit rounding modifiers and --fmad=false, which
-        // would skip the reference's intermediate rounding of the product
-        float2 sc = make_float2(__fmul_rn(A.x, l.x), __fmul_rn(A.y, l.y));
-        if (!RP) {
-          sc = __fadd2_rn(sc, B);
-          sc = __fadd2_rn(sc, make_float2(-A.x, -A.y));
-          sc.x = (A.x > B.x) ? sc.x : 0.f;
-          sc.y = (A.y > B.y) ? sc.y : 0.f;
+        float2 sc = make_float2(0.f, 0.f);
+        // mult-clust: the score is 0 unless A > B (score_impl.hpp:385-388); like the reference's ternary, skip the
+        // division and the log when neither of the thread's two rows is past the A = B frontier
+        if (RP || (A.x > B.x) || (A.y > B.y)) {
+          const float2 q = fast_fdiv2(A, B);
+          const float2 l = make_float2(glibc_logf_fast(q.x, s_logf), glibc_logf_fast(q.y, s_logf));
+          // A*l with two scalar multiplies: ptxas (12.9) contracts mul.rn.f32x2 (and fma.rn.f32x2 with a -0
+          // addend) followed by add.rn.f32x2 into one FFMA2 despite the explicit rounding modifiers and
+          // --fmad=false, which would skip the reference's intermediate rounding of the product
+          sc = make_float2(__fmul_rn(A.x, l.x), __fmul_rn(A.y, l.y));
+          if (!RP) {
+            sc = __fadd2_rn(sc, B);
+            sc = __fadd2_rn(sc, make_float2(-A.x, -A.y));
+            sc.x = (A.x > B.x) ? sc.x : 0.f;
+            sc.y = (A.y > B.y) ? sc.y : 0.f;
+          }
         }
         const float2 v = __fadd2_rn(sc, make_float2(r.p, r.p));
         if (v.x > best0) {

@@ -35,6 +35,13 @@ template <bool FAST> __device__ __forceinline__ double log_d(double x, const Glo
   return FAST ? glibc_log_fast(x, tab) : glibc_log(x);
 }
 
+// A > B.  On the fast path both are positive normal numbers, for which the order of the bit patterns is the
+// numeric order: the double compare then runs on the integer pipe instead of the FP64 pipe.
+template <bool FAST> __device__ __forceinline__ bool gt_ab(float a, float b) { return a > b; }
+template <bool FAST> __device__ __forceinline__ bool gt_ab(double a, double b) {
+  return FAST ? (__double_as_longlong(a) > __double_as_longlong(b)) : (a > b);
+}
+
 // ------------------------------------------------------------------ float
 template <bool FAST>
 struct ScoreFn<float, DIST_POISSON, false, FAST> {
@@ -79,10 +86,7 @@ struct ScoreFn<double, DIST_POISSON, false, FAST> {
   static __device__ __forceinline__ double eval(double A, double B, const GlogEntry* tab = g_glog_tab) {
     double q = div_d<FAST>(A, B);
     double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log_d<FAST>(q, tab)), B), A);
-    // FAST: A, B are positive normal doubles, for which the order of the bit patterns is the numeric order;
-    // the integer compare keeps one instruction off the FP64 pipe, which is the pipe that bounds this kernel
-    const bool gt = FAST ? (__double_as_longlong(A) > __double_as_longlong(B)) : (A > B);
-    return gt ? s : 0.;
+    return gt_ab<FAST>(A, B) ? s : 0.;
   }
 };
 template <bool FAST>
