@@ -14,8 +14,8 @@
 // Work decomposition of one level (DP_impl.hpp:101-118, the O(n^2) part): the upper-triangular
 // (i,k) space is cut into tiles of BR rows x L columns.  One CTA = one tile, one thread = one row;
 // the k loop streams records through a double-buffered shared-memory stage, so the three per-k
-// operands are loaded from L2 once per CTA and broadcast to all rows.  Tiles are enumerated far from
-// the diagonal first so the half-empty diagonal tiles fill the tail of the launch.  A second, tiny
+// operands are loaded from L2 once per CTA and broadcast to all rows.  Tiles are launched highest rows
+// first (decode_tile).  A second, tiny
 // kernel folds the per-chunk partials in ascending k, which preserves the reference's
 // "first maximum wins" rule (strict >, DP_impl.hpp:107).
 #pragma once
@@ -54,16 +54,42 @@ struct Geom {
 };
 
 __host__ __device__ inline int geom_count_tiles(int NCH, int G, int NRB, int rb_first, int rb_step) {
-  // number of owned row blocks whose diagonal chunk s satisfies s + d <= NCH-1, summed over d
+  // every owned row block rb has one tile per chunk from its diagonal chunk rb/G to NCH-1
   long long t = 0;
-  for (int d = 0; d < NCH; ++d) {
-    long long lim = (long long)(NCH - d) * G;  // global row blocks rb < lim
-    // owned blocks: rb = rb_first + rb_step*m < lim
-    long long m = lim > rb_first ? (lim - rb_first + rb_step - 1) / rb_step : 0;
-    if (m > NRB) m = NRB;
-    t += m;
-  }
+  for (int m = 0; m < NRB; ++m) t += NCH - (rb_first + rb_step * m) / G;
   return (int)t;
+}
+
+// Launch order of the tiles of a level: HIGHEST rows first.  Rows are sorted by priority a/b, so the high rows
+// are the ones whose range sums are past the A = B frontier -- the cells that actually evaluate division and log
+// in the multiple-clustering scores -- and a 128 x L tile of such cells runs for a fifth of the whole launch when
+// it shares an SM with eight others.  Starting the expensive tiles first and letting the cheap low rows fill the
+// tail keeps the SMs level (first-fit in decreasing cost); with uniform cost (risk partitioning) the order is
+// harmless.  Tile t -> (row block rb, chunk c), c from the row block's diagonal chunk rb/G up to NCH-1.
+__device__ __forceinline__ void decode_tile(const Geom& g, int t, int& rb, int& c) {
+  if (g.rb_step == 1 && g.rb_first == 0) {
+    int s = (g.NRB - 1) / g.G;  // super-block = G row blocks sharing a diagonal chunk
+    for (;;) {
+      const int rbs = min(g.G, g.NRB - s * g.G);
+      const int cnt = rbs * (g.NCH - s);
+      if (t < cnt) {
+        rb = s * g.G + t % rbs;
+        c = s + t / rbs;
+        return;
+      }
+      t -= cnt;
+      --s;
+    }
+  }
+  for (int m = g.NRB - 1;; --m) {  // row-sharded run: owned blocks rb_first + rb_step * m
+    rb = g.rb_first + g.rb_step * m;
+    const int cnt = g.NCH - rb / g.G;
+    if (t < cnt) {
+      c = rb / g.G + t;
+      return;
+    }
+    t -= cnt;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -94,19 +120,9 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
     SB += inst * pstride;
   }
 
-  // ---- tile decode: distance from the diagonal d = NCH-1 .. 0, then owned row block m
-  int t = blockIdx.x;
-  int d = g.NCH - 1;
-  for (;;) {
-    long long lim = (long long)(g.NCH - d) * g.G;
-    long long cnt = lim > g.rb_first ? (lim - g.rb_first + g.rb_step - 1) / g.rb_step : 0;
-    if (cnt > g.NRB) cnt = g.NRB;
-    if (t < cnt) break;
-    t -= (int)cnt;
-    --d;
-  }
-  const int rb = g.rb_first + g.rb_step * t;
-  const int c = rb / g.G + d;
+  // ---- tile decode
+  int rb, c;
+  decode_tile(g, blockIdx.x, rb, c);
 
   const int tid = threadIdx.x;
   const int i0 = rb * BR;
@@ -252,17 +268,8 @@ level_tile_kernel_pois_f32x2(Geom g, const Rec4<float>* __restrict__ rec, const 
   SA += inst * pstride;
   SB += inst * pstride;
 
-  int t = blockIdx.x;
-  int d = g.NCH - 1;
-  for (;;) {
-    long long lim = (long long)(g.NCH - d) * g.G;
-    long long cnt = lim < g.NRB ? lim : g.NRB;
-    if (t < cnt) break;
-    t -= (int)cnt;
-    --d;
-  }
-  const int rb = t;
-  const int c = rb / g.G + d;
+  int rb, c;
+  decode_tile(g, blockIdx.x, rb, c);
   const int tid = threadIdx.x;
   const int i0 = rb * BRT;
   const int ia = i0 + tid, ib = i0 + 128 + tid;
