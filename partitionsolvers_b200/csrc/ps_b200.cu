@@ -319,7 +319,17 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(mark(ctx, &e_sort));
 
   // ---- level 1
-  const int L = choose_chunk(n, R, p.chunk_len);
+  int fast = 0;
+  if (want_fast) {  // the precheck ran right after the inputs arrived; its flag is on the host by now
+    PS_CUDA(ctx, cudaEventSynchronize(e_flags));
+    host_flags = *ctx->pinned_flags;
+    fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
+  }
+  // float Poisson on the fast path runs the two-rows-per-thread kernel (256-row tiles): halve the chunk so that
+  // its tiles hold as many cells as the 128-row ones and the launch balances as finely
+  const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2;
+  int L = choose_chunk(n, R, p.chunk_len);
+  if (use_x2 && p.chunk_len <= 0 && L >= 8 * BR) L = ((L / 2 + 2 * BR - 1) / (2 * BR)) * (2 * BR);
   const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
   const long long pstride = (long long)nch_alloc * n;
   PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
@@ -346,18 +356,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(mark(ctx, &e_pre));
 
   // ---- levels 2..Tc  (DP_impl.hpp:101-118)
-  int fast = 0;
-  if (want_fast) {
-    PS_CUDA(ctx, cudaEventSynchronize(e_flags));
-    host_flags = *ctx->pinned_flags;
-    fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
-  }
   ctx->last_fast = fast;
   auto fn = LevelLaunch<D>::pick(p.dist, rp, running, fast);
   // float Poisson on the fast path: two rows per thread, packed f32x2 pipeline, 256-row tiles
   int tile_rows = BR;
   if constexpr (sizeof(D) == 4) {
-    if (fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2) {
+    if (use_x2) {
       tile_rows = 2 * BR;
       fn = rp ? ps::level_tile_kernel_pois_f32x2<true> : ps::level_tile_kernel_pois_f32x2<false>;
     }
