@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--sum-mode", default="running", choices=["running", "prefix"])
     ap.add_argument("--no-extras", action="store_true", help="skip variants, replicas and the CPU baseline")
     ap.add_argument("--skip-peaks", action="store_true", help="do not run the pipe-peak microbenchmark (ncu runs)")
+    ap.add_argument("--chunk-len", type=int, default=0, help="tuning: k-chunk length of the level tiles (0 = library default)")
     ap.add_argument("--sharded-n", type=int, default=200000, help="N>1 only: size of the row-sharded instance")
     ap.add_argument("--sharded-T", type=int, default=8)
     args = ap.parse_args()
@@ -258,11 +259,12 @@ def main():
         def step_resident():
             ctx.solve_device(a_d.data_ptr(), b_d.data_ptr(), n, T, dist_id, rp, npdt, sum_mode=sm,
                              d_perm_out=perm_d.data_ptr(), d_bounds=bounds_d.data_ptr(),
-                             d_scores=scores_d.data_ptr())
+                             d_scores=scores_d.data_ptr(), chunk_len=args.chunk_len)
 
         def step_e2e():
             ctx.solve_into(a_pin.numpy(), b_pin.numpy(), T, dist_id, rp, npdt, perm_out=perm_pin.numpy(),
-                           bounds_out=bounds_pin.numpy(), scores_out=scores_pin.numpy(), sum_mode=sm)
+                           bounds_out=bounds_pin.numpy(), scores_out=scores_pin.numpy(), sum_mode=sm,
+                           chunk_len=args.chunk_len)
 
         for _ in range(warmup):
             step_resident()
