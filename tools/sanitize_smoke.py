@@ -1,0 +1,51 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel of the library on small inputs.
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from partitionsolvers_b200 import capi, synth  # noqa: E402
+
+ctx = capi.Context()
+for dt in (np.float32, np.float64):
+    a, b = synth.poisson_planted(1537, 5, seed=3, dtype=dt)
+    for dist, rp in ((1, False), (1, True), (0, False), (2, False)):
+        for sm in (capi.PS_SUM_RUNNING, capi.PS_SUM_PREFIX):
+            ctx.solve_raw(a, b, 6, dist, rp, dtype=dt, sum_mode=sm, sweep=True, levels=True, chunk_len=256)
+            ctx.solve_raw(a, b, 6, dist, rp, dtype=dt, sum_mode=sm, no_fast=1)
+    ab, bb = synth.poisson_null(301, seed=4, dtype=dt, replicas=5)
+    ctx.solve_raw(ab, bb, 4, 1, False, dtype=dt, sweep=True)
+    ctx.solve_raw(a[:1], b[:1], 1, 1, False, dtype=dt)
+    ctx.solve_raw(a[:129], b[:129], 129, 2, False, dtype=dt, levels=True)
+    ctx.range_score(a, b, 1, False, dtype=dt)
+    ctx.eval_log(np.abs(a) + 0.1, dtype=dt)
+ctx.ltss(a.astype(np.float32), b.astype(np.float32), 1)
+ctx.selftest_math(0, 1 << 16)
+ctx.selftest_math(3, 1 << 16)
+try:
+    import torch
+    from partitionsolvers_b200 import multigpu
+    dev = torch.device("cuda", ctx.device)
+    a, b = synth.poisson_planted(1000, 4, seed=5, dtype=np.float64)
+    engines = [multigpu.CudaShardEngine(ctx, dev) for _ in range(2)]
+    perm, a_s, b_s = engines[0].sort(a, b, np.float64)
+    for r, e in enumerate(engines):
+        e.create(a_s, b_s, 1000, 4, 1, False, np.float64, r, 2)
+    chunks = [e.new_chunk() for e in engines]
+    for e, c in zip(engines, chunks):
+        e.level1(c)
+    g = torch.cat(chunks)
+    for j in range(2, 5):
+        for e, c in zip(engines, chunks):
+            e.set_prev(g)
+            e.level(j, c)
+        g = torch.cat(chunks)
+    for e in engines:
+        e.close()
+except ImportError:
+    pass
+ctx.close()
+print("sanitize_smoke: done")
