@@ -15,7 +15,7 @@ import sysconfig
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-HOSTSRC = os.path.join(HERE, "host")
+HOSTSRC = os.path.join(HERE, "cxx")
 LIBDIR = os.path.join(HERE, "_lib")
 INCLUDE = os.path.join(ROOT, "include")
 

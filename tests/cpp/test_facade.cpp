@@ -7,7 +7,7 @@
 #include <random>
 #include <thread>
 
-#include "../../partitionsolvers_b200/host/python_dpsolver.hpp"
+#include "../../partitionsolvers_b200/cxx/python_dpsolver.hpp"
 
 static int g_fail = 0;
 #define CHECK(cond)                                                         \
