@@ -98,8 +98,37 @@ def build_facade_test(force=False):
     return target
 
 
+def build_reference_programs(force=False, ref="/root/reference/src/cpp"):
+    """Drop-in demonstration: the reference's OWN demo / timer programs (DP_solver_demo.cpp, LTSS_solver_demo.cpp,
+    solver_timer.cpp), compiled UNCHANGED from where they lie against the facade headers and linked to the engine.
+    Only where the reference checkout exists (the binaries travel to the GPU box with the snapshot; no reference
+    source enters the repository).  The six solver headers are shadowed through a temporary include directory."""
+    import tempfile
+    if not os.path.isdir(os.path.join(ref, "include")):
+        return []
+    outs = []
+    with tempfile.TemporaryDirectory() as tmp:
+        replaced = {"DP.hpp", "DP_impl.hpp", "score.hpp", "score_impl.hpp", "LTSS.hpp", "LTSS_impl.hpp"}
+        for f in os.listdir(os.path.join(ref, "include")):
+            if f not in replaced:
+                os.symlink(os.path.join(ref, "include", f), os.path.join(tmp, f))
+        compat = os.path.join(INCLUDE, "partitionsolvers", "compat")
+        for f in os.listdir(compat):
+            os.symlink(os.path.join(compat, f), os.path.join(tmp, f))
+        deps = _sources(INCLUDE, (".h", ".hpp")) + [os.path.join(LIBDIR, "libps_b200.so")]
+        for prog in ("DP_solver_demo", "LTSS_solver_demo", "solver_timer"):
+            src = os.path.join(ref, prog + ".cpp")
+            target = os.path.join(LIBDIR, "ref_" + prog)
+            if force or _newer(target, deps + [src]):
+                subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-w", "-I", tmp, "-I", INCLUDE, src,
+                                "-L", LIBDIR, "-lps_b200", "-Wl,-rpath,$ORIGIN", "-pthread", "-o", target], check=True)
+            outs.append(target)
+    return outs
+
+
 def build_all(force=False, verbose=False):
     out = [build_cuda(force, verbose), build_peaks(force)]
+    out += build_reference_programs(force)
     for fn in (build_proto, build_facade_test):
         p = fn(force)
         if p:

@@ -86,3 +86,28 @@ def test_product_does_not_import_the_oracle():
                     if re.search(r"(from|import)\s+oracle|oracle_py|libps_oracle|libps_ref|dp_oracle", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_reference_sources_compile_against_the_facade(tmp_path):
+    """Source compatibility of the drop-in boundary: the reference's OWN callers of the hot path
+    (python_dpsolver.cpp, python_ltsssolver.cpp, the two demos, solver_timer.cpp) must compile unchanged when the
+    six solver headers are replaced by include/partitionsolvers/compat/*.  The include directory is assembled in a
+    temporary directory from symlinks into /root/reference (nothing is copied into the repository)."""
+    ref_inc = "/root/reference/src/cpp/include"
+    if not os.path.isdir(ref_inc):
+        pytest.skip("/root/reference not present on this machine")
+    inc = tmp_path / "include"
+    inc.mkdir()
+    replaced = {"DP.hpp", "DP_impl.hpp", "score.hpp", "score_impl.hpp", "LTSS.hpp", "LTSS_impl.hpp"}
+    for f in os.listdir(ref_inc):
+        if f not in replaced:
+            os.symlink(os.path.join(ref_inc, f), inc / f)
+    compat = os.path.join(ROOT, "include", "partitionsolvers", "compat")
+    for f in os.listdir(compat):
+        os.symlink(os.path.join(compat, f), inc / f)
+    for src in ("python_dpsolver.cpp", "python_ltsssolver.cpp", "DP_solver_demo.cpp", "LTSS_solver_demo.cpp",
+                "solver_timer.cpp"):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", str(inc), "-I",
+                            os.path.join(ROOT, "include"), os.path.join("/root/reference/src/cpp", src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, f"{src}:\n{r.stderr[:2000]}"

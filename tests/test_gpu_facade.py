@@ -93,3 +93,20 @@ def test_ltss_matches_oracle_and_dp(oracle, ctx, proto):
         b = rs.uniform(0.1, 10, 500).astype(np.float32)
         dp = host.DPSolver(500, 2, a, b, dist, False, True, dtype=np.float32, ctx=ctx)
         assert sorted(dp.subsets[1].tolist()) == sorted(ctx.ltss(a, b, dist)["subset"].tolist())
+
+
+@pytest.mark.parametrize("prog,args", [("ref_DP_solver_demo", []), ("ref_LTSS_solver_demo", []),
+                                       ("ref_solver_timer", ["400", "20", "100", "5"])])
+def test_reference_programs_run_on_the_engine(prog, args):
+    """The reference's own demo / timer sources, compiled unchanged against the facade (build.py:
+    build_reference_programs) and executed on the B200.  Skipped where the binaries were not built (no reference
+    checkout at build time)."""
+    exe = os.path.join(LIBDIR, prog)
+    if not os.path.exists(exe):
+        pytest.skip(f"{prog} not built")
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    if prog == "ref_solver_timer":  # CSV of constructor times in microseconds, (n+1) rows x (T+1) columns
+        rows = [l for l in r.stdout.strip().splitlines() if "," in l]
+        assert len(rows) == 401 and all(len(l.rstrip(",").split(",")) == 21 for l in rows)
+        assert int(rows[400].rstrip(",").split(",")[20]) > 0
