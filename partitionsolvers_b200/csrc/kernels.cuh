@@ -374,6 +374,99 @@ level_tile_kernel_pois_f32x2(Geom g, const Rec4<float>* __restrict__ rec, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Level T needs row 0 only (DP_impl.hpp:114-116).  One thread per row would leave a single lane walking a
+// whole chunk with nothing to hide its latency, so this kernel turns the k axis into the parallel one: per
+// sub-block of 1024 k's, thread 0 forms the running sums left to right (the reference's order; two dependent adds
+// per k), all threads then evaluate their cells, and a shuffle/shared-memory reduction keeps the largest value and,
+// among equals, the smallest k -- the reference's first-maximum rule.  One CTA per k-chunk; the result goes through
+// the same per-chunk partials and combine_kernel as every other level.
+// ---------------------------------------------------------------------------------------------
+template <typename D, int DIST, bool RP, bool RUNNING, bool FAST, int NT>
+__global__ void __launch_bounds__(NT)
+last_level_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__ SA, const D* __restrict__ SB,
+                  D* __restrict__ part_val, int* __restrict__ part_arg) {
+  constexpr int SUB = 1024;
+  __shared__ D sA[SUB], sB[SUB];
+  __shared__ D red_v[NT / 32];
+  __shared__ int red_k[NT / 32];
+  __shared__ D carry[2];
+  const int inst = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
+  rec += (long long)inst * g.rec_stride;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  const int k_lo = c * g.L + 1, k_hi = min((c + 1) * g.L, g.kmax);
+  const D X0 = rec[0].x, Y0 = rec[0].y;  // PREFIX: scan values at row 0 (= 0)
+  if (tid == 0) {
+    carry[0] = (RUNNING && c > 0) ? SA[inst * pstride + (long long)c * g.n] : (D)0;
+    carry[1] = (RUNNING && c > 0) ? SB[inst * pstride + (long long)c * g.n] : (D)0;
+  }
+  D best = Lim<D>::lowest();
+  int arg = -1;
+  for (int kb = k_lo; kb <= k_hi; kb += SUB) {
+    const int cnt = min(SUB, k_hi - kb + 1);
+    __syncthreads();
+    if (RUNNING) {
+      if (tid == 0) {
+        D A = carry[0], B = carry[1];
+        for (int q = 0; q < cnt; ++q) {
+          const Rec4<D> r = rec[kb + q];
+          A = add_rn<D>(A, r.x);
+          B = add_rn<D>(B, r.y);
+          sA[q] = A;
+          sB[q] = B;
+        }
+        carry[0] = A;
+        carry[1] = B;
+      }
+      __syncthreads();
+    }
+    for (int q = tid; q < cnt; q += NT) {  // ascending k per thread
+      const int k = kb + q;
+      D A, B;
+      if (RUNNING) {
+        A = sA[q];
+        B = sB[q];
+      } else {
+        A = sub_rn<D>(rec[k].x, X0);
+        B = sub_rn<D>(rec[k].y, Y0);
+      }
+      const D v = add_rn<D>(ScoreFn<D, DIST, RP, FAST>::eval(A, B), rec[k].p);
+      if (v > best) {
+        best = v;
+        arg = k;
+      }
+    }
+  }
+  // largest value wins; among equal values the smallest k (arg = -1 means "nothing won" and never beats a k)
+  auto better = [](D v1, int k1, D v2, int k2) {
+    if (k1 < 0) return false;
+    if (k2 < 0) return true;
+    return v1 > v2 || (v1 == v2 && k1 < k2);
+  };
+  for (int o = 16; o > 0; o >>= 1) {
+    const D ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (better(ov, ok, best, arg)) {
+      best = ov;
+      arg = ok;
+    }
+  }
+  if ((tid & 31) == 0) {
+    red_v[tid >> 5] = best;
+    red_k[tid >> 5] = arg;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NT / 32; ++w)
+      if (better(red_v[w], red_k[w], best, arg)) {
+        best = red_v[w];
+        arg = red_k[w];
+      }
+    part_val[inst * pstride + (long long)c * g.n] = (arg < 0) ? Lim<D>::lowest() : best;
+    part_arg[inst * pstride + (long long)c * g.n] = arg;
+  }
+}
+
 // Fold the per-chunk partials of row i in ascending chunk order (= ascending k): strict > keeps the
 // first maximum, exactly like the reference's scan over k.  Writes maxScore_[j][i], nextStart_[j][i]
 // and the p field of the NEXT level's records.  Sharded runs also emit the value in block-cyclic

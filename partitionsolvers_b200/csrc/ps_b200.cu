@@ -152,6 +152,27 @@ struct LevelLaunch {
   }
 };
 
+template <typename D>
+struct LastLevelLaunch {
+  using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const D*, const D*, D*, int*);
+  static Fn pick(int dist, int rp, int running, int fast) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                                            \
+  return fast ? (running ? (Fn)last_level_kernel<D, DI, RPV, true, true, 128>                       \
+                         : (Fn)last_level_kernel<D, DI, RPV, false, true, 128>)                     \
+              : (running ? (Fn)last_level_kernel<D, DI, RPV, true, false, 128>                      \
+                         : (Fn)last_level_kernel<D, DI, RPV, false, false, 128>);
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: PS_PICK(DIST_GAUSSIAN, false)
+      case 1: PS_PICK(DIST_GAUSSIAN, true)
+      case 2: PS_PICK(DIST_POISSON, false)
+      case 3: PS_PICK(DIST_POISSON, true)
+      default: PS_PICK(DIST_RATIONAL, false)
+    }
+#undef PS_PICK
+  }
+};
+
 ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int rb_step, int tile_rows = BR) {
   ps::Geom g;
   g.n = n;
@@ -366,6 +387,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       fn = rp ? ps::level_tile_kernel_pois_f32x2<true> : ps::level_tile_kernel_pois_f32x2<false>;
     }
   }
+  auto fn_last = LastLevelLaunch<D>::pick(p.dist, rp, running, fast);
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lev_ev;
   for (int j = 2; j <= Tc; ++j) {
     ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, tile_rows);
@@ -374,7 +396,13 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     const bool timed = (j - 2) < PS_MAX_TIMED_LEVELS;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) PS_TRY(mark(ctx, &e0));
-    fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+    if (j == Tc && Tc >= 2) {
+      // last level: row 0 only -> k-parallel kernel, one CTA per chunk (128-row geometry)
+      g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, BR);
+      fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+    } else {
+      fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+    }
     if (timed) PS_TRY(mark(ctx, &e1));
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
         g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr);
