@@ -115,17 +115,16 @@ ps_status mark(ps_ctx* ctx, cudaEvent_t* out) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// k-chunk length: a multiple of BR giving enough equal tiles to balance 148 SMs (SURVEY.md hard part 5)
-// (always a multiple of 256 so that both the 128-row and the 256-row tile kernels can use it)
-int choose_chunk(int n, int batch, int user) {
-  const int Q = 2 * BR;
+// k-chunk length L: a multiple of the tile height Q (128, or 256 for the two-rows-per-thread kernel) giving enough
+// equal tiles to balance 148 SMs (SURVEY.md hard part 5).  Measured on C3: 1024..1280-wide chunks beat 4096 by
+// 5 % (finer tail); small instances get the smallest legal chunk so that a level still spreads over many SMs.
+int choose_chunk(int n, int batch, int user, int Q) {
   if (user > 0) return std::max(Q, (user / Q) * Q);
-  const long long want_tiles = 148LL * 256;  // measured on C3: 1024..1280-wide chunks beat 4096 by 5 % (finer tail)
-  const int nrb = cdiv(n, BR);
+  const long long want_tiles = 148LL * 256;
+  const int nrb = cdiv(n, Q);
   long long nch = (2 * want_tiles + (long long)batch * nrb - 1) / ((long long)batch * nrb);
   nch = std::max(1LL, std::min(128LL, nch));
   long long L = ((cdiv(n, nch) + Q - 1) / Q) * (long long)Q;
-  L = std::max<long long>(L, 2 * Q);
   L = std::min<long long>(L, 16384);
   L = std::min<long long>(L, ((n + Q - 1) / Q) * (long long)Q);
   return (int)std::max<long long>(L, Q);
@@ -346,11 +345,11 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     host_flags = *ctx->pinned_flags;
     fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
   }
-  // float Poisson on the fast path runs the two-rows-per-thread kernel (256-row tiles): halve the chunk so that
-  // its tiles hold as many cells as the 128-row ones and the launch balances as finely
-  const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2;
-  int L = choose_chunk(n, R, p.chunk_len);
-  if (use_x2 && p.chunk_len <= 0 && L >= 8 * BR) L = ((L / 2 + 2 * BR - 1) / (2 * BR)) * (2 * BR);
+  // float Poisson on the fast path runs the two-rows-per-thread packed kernel (256-row tiles) once there are enough
+  // rows to fill the machine with such tiles; smaller instances keep 128-row tiles (more, finer work items)
+  const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 &&
+                      (long long)n * R >= 16384;
+  const int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
   const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
   const long long pstride = (long long)nch_alloc * n;
   PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
@@ -587,7 +586,7 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   s->world = world;
   const int n = pp->n;
   const int Tc = std::min(pp->T, n);
-  s->L = choose_chunk(n, 1, pp->chunk_len);
+  s->L = choose_chunk(n, 1, pp->chunk_len, BR);
   s->nch_alloc = std::max(1, cdiv(std::max(1, n - 1), s->L));
   const int nrb_total = cdiv(n, BR);
   s->owned_blocks = nrb_total > rank ? (nrb_total - rank + world - 1) / world : 0;
