@@ -207,6 +207,17 @@ ps_status sort_stage(ps_ctx* ctx, const ps_problem& p, const D* d_a, const D* d_
     PS_CUDA(ctx, cudaMemcpyAsync(d_perm, p.perm, total * sizeof(int),
                                  p.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     if (!p.on_device) ctx->tm.h2d_bytes += total * sizeof(int);
+  } else if (n <= ps::SORT_SMALL_MAX) {
+    // small instances: keys + all digit passes + gather fused in one kernel, one CTA per instance
+    using U = typename ps::SortKey<D>::U;
+    const size_t smem = 2 * (size_t)n * (sizeof(U) + sizeof(int));
+    auto kfn = ps::sort_small_kernel<D>;
+    if (smem > 48 * 1024)
+      PS_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kfn<<<R, ps::SORT_THREADS, smem, st>>>(n, d_a, d_b, d_perm, (D*)ctx->a_s.p, (D*)ctx->b_s.p);
+    ctx->launches++;
+    PS_CUDA(ctx, cudaGetLastError());
+    return PS_OK;
   } else {
     // stable LSD radix sort of (a/b, index), all instances at once (radix_sort.cuh)
     using U = typename ps::SortKey<D>::U;
