@@ -152,11 +152,15 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
     // rows at the same k, so a warp is uniformly on one side of the A = B frontier except along the frontier itself.
     if constexpr (!RP && DIST != DIST_RATIONAL) {
       if (!gt_ab<FAST>(a_sum, b_sum)) return (D)0;
-    }
-    if constexpr (kLogTab)
+      if constexpr (kLogTab)
+        return ScoreFn<D, DIST, RP, FAST>::eval_gt(a_sum, b_sum, s_log);
+      else
+        return ScoreFn<D, DIST, RP, FAST>::eval_gt(a_sum, b_sum);
+    } else if constexpr (kLogTab) {
       return ScoreFn<D, DIST, RP, FAST>::eval(a_sum, b_sum, s_log);
-    else
+    } else {
       return ScoreFn<D, DIST, RP, FAST>::eval(a_sum, b_sum);
+    }
   };
 
   const int nk = k_hi - k_lo + 1;

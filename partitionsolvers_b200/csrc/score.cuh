@@ -45,11 +45,12 @@ template <bool FAST> __device__ __forceinline__ bool gt_ab(double a, double b) {
 // ------------------------------------------------------------------ float
 template <bool FAST>
 struct ScoreFn<float, DIST_POISSON, false, FAST> {
-  static __device__ __forceinline__ float eval(float A, float B) {
+  // the expression of the A > B branch alone (callers that have already tested A > B)
+  static __device__ __forceinline__ float eval_gt(float A, float B) {
     float q = div_f<FAST>(A, B);
-    float s = __fsub_rn(__fadd_rn(__fmul_rn(A, log_f<FAST>(q)), B), A);
-    return (A > B) ? s : 0.f;
+    return __fsub_rn(__fadd_rn(__fmul_rn(A, log_f<FAST>(q)), B), A);
   }
+  static __device__ __forceinline__ float eval(float A, float B) { return (A > B) ? eval_gt(A, B) : 0.f; }
 };
 template <bool FAST>
 struct ScoreFn<float, DIST_POISSON, true, FAST> {
@@ -59,11 +60,12 @@ struct ScoreFn<float, DIST_POISSON, true, FAST> {
 };
 template <bool FAST>
 struct ScoreFn<float, DIST_GAUSSIAN, false, FAST> {
-  static __device__ __forceinline__ float eval(float A, float B) {
+  static __device__ __forceinline__ float eval_gt(float A, float B) {
     double a = (double)A, b = (double)B;
     double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(div_d<FAST>(__dmul_rn(a, a), b), b)), a);
-    return (A > B) ? __double2float_rn(s) : 0.f;
+    return __double2float_rn(s);
   }
+  static __device__ __forceinline__ float eval(float A, float B) { return (A > B) ? eval_gt(A, B) : 0.f; }
 };
 template <bool FAST>
 struct ScoreFn<float, DIST_GAUSSIAN, true, FAST> {
@@ -83,10 +85,12 @@ struct ScoreFn<float, DIST_RATIONAL, RP, FAST> {
 // ------------------------------------------------------------------ double
 template <bool FAST>
 struct ScoreFn<double, DIST_POISSON, false, FAST> {
-  static __device__ __forceinline__ double eval(double A, double B, const GlogEntry* tab = g_glog_tab) {
+  static __device__ __forceinline__ double eval_gt(double A, double B, const GlogEntry* tab = g_glog_tab) {
     double q = div_d<FAST>(A, B);
-    double s = __dsub_rn(__dadd_rn(__dmul_rn(A, log_d<FAST>(q, tab)), B), A);
-    return gt_ab<FAST>(A, B) ? s : 0.;
+    return __dsub_rn(__dadd_rn(__dmul_rn(A, log_d<FAST>(q, tab)), B), A);
+  }
+  static __device__ __forceinline__ double eval(double A, double B, const GlogEntry* tab = g_glog_tab) {
+    return gt_ab<FAST>(A, B) ? eval_gt(A, B, tab) : 0.;
   }
 };
 template <bool FAST>
@@ -97,10 +101,10 @@ struct ScoreFn<double, DIST_POISSON, true, FAST> {
 };
 template <bool FAST>
 struct ScoreFn<double, DIST_GAUSSIAN, false, FAST> {
-  static __device__ __forceinline__ double eval(double A, double B) {
-    double s = __dsub_rn(__dmul_rn(.5, __dadd_rn(div_d<FAST>(__dmul_rn(A, A), B), B)), A);
-    return (A > B) ? s : 0.;
+  static __device__ __forceinline__ double eval_gt(double A, double B) {
+    return __dsub_rn(__dmul_rn(.5, __dadd_rn(div_d<FAST>(__dmul_rn(A, A), B), B)), A);
   }
+  static __device__ __forceinline__ double eval(double A, double B) { return (A > B) ? eval_gt(A, B) : 0.; }
 };
 template <bool FAST>
 struct ScoreFn<double, DIST_GAUSSIAN, true, FAST> {
