@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PS_B200_ABI_VERSION 1
+#define PS_B200_ABI_VERSION 2
 
 typedef enum ps_status {
   PS_OK = 0,
@@ -70,6 +70,12 @@ typedef struct ps_problem {
   int no_fast_math;/* debug: 1 = never take the range-prechecked branch-free math path (csrc/math_fast.cuh);  */
                    /*        2 = take it, but not the packed two-rows-per-thread float kernel               */
   int chunk_len;   /* tuning, 0 = default                                                             */
+  int screen;      /* levels 2..T-1: 0 = auto: the screened kernel (csrc/screen.cuh: a float upper bound per  */
+                   /* cell, the reference's arithmetic only for cells that can still be the row's maximum;    */
+                   /* same tables bit for bit) when the instance qualifies (PS_SUM_RUNNING, safe range, a > 0,*/
+                   /* exactly summable inputs such as counts), else the exhaustive kernel;                    */
+                   /* 1 = always the exhaustive kernel; 2 = screened + audit (every cell is ALSO evaluated    */
+                   /* exactly and ps_timings.screen_violations counts cells whose bound was too low)          */
 } ps_problem;
 
 /* Caller-allocated outputs; any pointer may be NULL (= not wanted).  D = float or double.
@@ -105,6 +111,9 @@ typedef struct ps_timings {
   long long level_cells[PS_MAX_TIMED_LEVELS]; /* (i,k) cells evaluated by that launch, all instances  */
   long long kernel_launches;              /* kernels launched by the call                            */
   long long h2d_bytes, d2h_bytes;
+  int screen_used;                  /* 1: levels ran the screened kernel                                      */
+  long long screen_exact_cells;     /* cells (32 per warp vote) evaluated with the reference's arithmetic      */
+  long long screen_violations;      /* audit mode only; must be 0                                              */
 } ps_timings;
 
 int ps_abi_version(void);
@@ -144,6 +153,10 @@ ps_status ps_ltss_f32(ps_ctx* ctx, int n, const float* a, const float* b, int di
  * 1 logf fast vs general entry, 2 double division vs div.rn, 3 log fast vs general entry. */
 ps_status ps_selftest_math(ps_ctx* ctx, int which, long long samples, unsigned long long seed,
                            long long* mismatches);
+/* The two hardware claims the screened kernel's error budget rests on, checked over EVERY float of the safe range:
+ * out[0] = max |x*rcp.approx(x) - 1| / 2^-24,  out[1] = max |lg2.approx(x) - log2 x| / (2^-24 max(1,|log2 x|)).
+ * csrc/screen.cuh assumes both <= 4. */
+ps_status ps_selftest_mufu(ps_ctx* ctx, double out[2]);
 /* Device log()/logf() (the restatement of glibc's routines the Poisson scores use) evaluated on n host
  * arguments; y_general takes the entry point that handles every input, y_fast the safe-range one. */
 ps_status ps_eval_log_f64(ps_ctx* ctx, long long n, const double* x, double* y_general, double* y_fast);

@@ -26,14 +26,15 @@ ABI_SYMBOLS = [
     "ps_range_score_f64", "ps_shard_create_f64", "ps_shard_create_f32", "ps_shard_chunk_rows",
     "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",
     "ps_shard_destroy", "ps_selftest_math", "ps_eval_log_f64", "ps_eval_log_f32",
-    "ps_ltss_f32",
+    "ps_ltss_f32", "ps_selftest_mufu",
 ]
 
 
 class PsProblem(C.Structure):
     _fields_ = [("n", C.c_int), ("T", C.c_int), ("dist", C.c_int), ("risk_part", C.c_int),
                 ("sum_mode", C.c_int), ("sort_mode", C.c_int), ("perm", C.c_void_p), ("sweep", C.c_int),
-                ("batch", C.c_int), ("on_device", C.c_int), ("no_fast_math", C.c_int), ("chunk_len", C.c_int)]
+                ("batch", C.c_int), ("on_device", C.c_int), ("no_fast_math", C.c_int), ("chunk_len", C.c_int),
+                ("screen", C.c_int)]
 
 
 class PsResult(C.Structure):
@@ -46,7 +47,8 @@ class PsTimings(C.Structure):
                 ("prepass_ms", C.c_float), ("levels_ms", C.c_float), ("backtrace_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("n_levels", C.c_int), ("level_ms", C.c_float * PS_MAX_TIMED_LEVELS),
                 ("level_cells", C.c_longlong * PS_MAX_TIMED_LEVELS), ("kernel_launches", C.c_longlong),
-                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("screen_used", C.c_int),
+                ("screen_exact_cells", C.c_longlong), ("screen_violations", C.c_longlong)]
 
 
 class PsError(RuntimeError):
@@ -101,6 +103,7 @@ def load():
         L.ps_selftest_math.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
         for nm in ("ps_eval_log_f64", "ps_eval_log_f32"):
             getattr(L, nm).argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ps_selftest_mufu.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.ps_ltss_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         _lib = L
@@ -153,10 +156,12 @@ class Context:
                     prepass_ms=t.prepass_ms, levels_ms=t.levels_ms, backtrace_ms=t.backtrace_ms,
                     d2h_ms=t.d2h_ms, level_ms=[t.level_ms[i] for i in range(nl)],
                     level_cells=[t.level_cells[i] for i in range(nl)],
-                    kernel_launches=t.kernel_launches, h2d_bytes=t.h2d_bytes, d2h_bytes=t.d2h_bytes)
+                    kernel_launches=t.kernel_launches, h2d_bytes=t.h2d_bytes, d2h_bytes=t.d2h_bytes,
+                    screen_used=t.screen_used, screen_exact_cells=t.screen_exact_cells,
+                    screen_violations=t.screen_violations)
 
     def solve_raw(self, a, b, T, dist, risk_part, dtype=np.float32, sum_mode=PS_SUM_RUNNING, perm=None,
-                  sweep=False, levels=False, chunk_len=0, want_perm=True, no_fast=False):
+                  sweep=False, levels=False, chunk_len=0, want_perm=True, no_fast=False, screen=0):
         """Host-buffer call.  a, b: [n] or [R, n].  Returns the raw ABI outputs as numpy arrays."""
         a = np.ascontiguousarray(a, dtype=dtype)
         b = np.ascontiguousarray(b, dtype=dtype)
@@ -168,7 +173,8 @@ class Context:
         nS = Tc + 1 if sweep else 1
         p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode,
                       sort_mode=PS_SORT_GIVEN if perm is not None else PS_SORT_DEVICE, perm=None,
-                      sweep=int(sweep), batch=R, on_device=0, no_fast_math=int(no_fast), chunk_len=chunk_len)
+                      sweep=int(sweep), batch=R, on_device=0, no_fast_math=int(no_fast), chunk_len=chunk_len,
+                      screen=int(screen))
         if perm is not None:
             perm = np.ascontiguousarray(perm, dtype=np.int32).reshape(R, n)
             p.perm = perm.ctypes.data
@@ -190,25 +196,27 @@ class Context:
         return out
 
     def solve_into(self, a, b, T, dist, risk_part, dtype, perm_out=None, bounds_out=None, scores_out=None,
-                   sum_mode=PS_SUM_RUNNING, sweep=False, chunk_len=0):
+                   sum_mode=PS_SUM_RUNNING, sweep=False, chunk_len=0, screen=0):
         """Host-buffer call that writes into caller-provided numpy arrays (e.g. views of pinned memory);
         nothing is allocated here, so the call is exactly the ABI call plus its copies."""
         batched = a.ndim == 2
         R = a.shape[0] if batched else 1
         n = a.shape[-1]
         p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode, sort_mode=PS_SORT_DEVICE,
-                      perm=None, sweep=int(sweep), batch=R, on_device=0, no_fast_math=0, chunk_len=chunk_len)
+                      perm=None, sweep=int(sweep), batch=R, on_device=0, no_fast_math=0, chunk_len=chunk_len,
+                      screen=int(screen))
         r = PsResult(perm=_vp(perm_out), bounds=_vp(bounds_out), subset_scores=_vp(scores_out), max_score=None,
                      next_start=None)
         fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
         self._check(fn(self._h, C.byref(p), _vp(a), _vp(b), C.byref(r)))
 
     def solve_device(self, d_a, d_b, n, T, dist, risk_part, dtype, R=1, sum_mode=PS_SUM_RUNNING, sweep=False,
-                     d_perm_out=0, d_bounds=0, d_scores=0, d_perm_in=0, chunk_len=0):
+                     d_perm_out=0, d_bounds=0, d_scores=0, d_perm_in=0, chunk_len=0, screen=0):
         """Device-pointer call (inputs resident in HBM; integers are raw device addresses)."""
         p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode,
                       sort_mode=PS_SORT_GIVEN if d_perm_in else PS_SORT_DEVICE, perm=d_perm_in or None,
-                      sweep=int(sweep), batch=R, on_device=1, no_fast_math=0, chunk_len=chunk_len)
+                      sweep=int(sweep), batch=R, on_device=1, no_fast_math=0, chunk_len=chunk_len,
+                      screen=int(screen))
         r = PsResult(perm=d_perm_out or None, bounds=d_bounds or None, subset_scores=d_scores or None,
                      max_score=None, next_start=None)
         fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
@@ -218,6 +226,12 @@ class Context:
         out = C.c_longlong(-1)
         self._check(self.lib.ps_selftest_math(self._h, which, samples, seed, C.byref(out)))
         return out.value
+
+    def selftest_mufu(self):
+        """(max |x rcp(x) - 1|, max lg2 error) in units of 2^-24 over every float of the safe range."""
+        out = (C.c_double * 2)()
+        self._check(self.lib.ps_selftest_mufu(self._h, out))
+        return float(out[0]), float(out[1])
 
     def ltss(self, a, b, dist):
         """LTSSSolver<float>: returns dict(perm, subset, score)."""

@@ -471,6 +471,18 @@ last_level_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
   }
 }
 
+// Screened levels (screen.cuh): pm = a float that dominates p (the level value the next level reads) together with
+// every rounding that involves it in the float bound, and the round-down conversion used for thresholds.
+template <typename D>
+__device__ __forceinline__ float screen_pm(D p) {
+  const float f = (sizeof(D) == 8) ? __double2float_ru((double)p) : (float)p;
+  return __fmaf_ru(fabsf(f), 9.5367431640625e-07f, f);  // + 2^-20 |p|
+}
+template <typename D>
+__device__ __forceinline__ float screen_rd(D v) {
+  return (sizeof(D) == 8) ? __double2float_rd((double)v) : (float)v;
+}
+
 // Fold the per-chunk partials of row i in ascending chunk order (= ascending k): strict > keeps the
 // first maximum, exactly like the reference's scan over k.  Writes maxScore_[j][i], nextStart_[j][i]
 // and the p field of the NEXT level's records.  Sharded runs also emit the value in block-cyclic
@@ -478,7 +490,8 @@ last_level_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
 template <typename D, int BR>
 __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int* __restrict__ part_arg,
                                D* __restrict__ ms_row, int* __restrict__ ns_row, long long table_stride,
-                               Rec4<D>* __restrict__ rec_next, D* __restrict__ shard_chunk) {
+                               Rec4<D>* __restrict__ rec_next, D* __restrict__ shard_chunk,
+                               float* __restrict__ pm_next) {
   const int inst = blockIdx.y;
   const long long pstride = (long long)g.nch_alloc * g.n;
   part_val += inst * pstride;
@@ -506,6 +519,7 @@ __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int
     if (ms_row) ms_row[inst * table_stride + i] = best;
     if (ns_row) ns_row[inst * table_stride + i] = arg;
     if (rec_next) rec_next[inst * g.rec_stride + i].p = best;
+    if (pm_next) pm_next[(inst * g.rec_stride + i) * 4 + 3] = screen_pm<D>(best);  // .w of the float record
   }
   if (shard_chunk) shard_chunk[m] = best;
 }
@@ -590,7 +604,7 @@ template <typename D>
 __global__ void level1_prefix_kernel(int n, long long rec_stride, int dist, int rp,
                                      const Rec4<D>* __restrict__ rec, D* __restrict__ ms1,
                                      int* __restrict__ ns1, long long table_stride,
-                                     Rec4<D>* __restrict__ rec_next) {
+                                     Rec4<D>* __restrict__ rec_next, float* __restrict__ pm_next) {
   const int inst = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -601,6 +615,7 @@ __global__ void level1_prefix_kernel(int n, long long rec_stride, int dist, int 
   ms1[inst * table_stride + i] = v;
   ns1[inst * table_stride + i] = n;
   rec_next[inst * rec_stride + i].p = v;
+  if (pm_next) pm_next[(inst * rec_stride + i) * 4 + 3] = screen_pm<D>(v);
 }
 
 // ---------------------------------------------------------------------------------------------

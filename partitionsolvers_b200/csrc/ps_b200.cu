@@ -18,6 +18,7 @@
 #include "../../include/ps_b200.h"
 #include "kernels.cuh"
 #include "radix_sort.cuh"
+#include "screen.cuh"
 
 namespace {
 
@@ -37,11 +38,11 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar;
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters;
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
   long long launches = 0;
-  int* pinned_flags = nullptr;
+  int* pinned_flags = nullptr;  // [0] range/exactness flags, [2..5] screen counters (as 2 x u64)
   int last_fast = 0;
 };
 
@@ -172,6 +173,36 @@ struct LastLevelLaunch {
   }
 };
 
+template <typename D>
+struct ScreenLaunch {
+  using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*);
+  using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, D*);
+  static Fn pick(int dist, int rp, int audit) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                             \
+  return audit ? (Fn)level_tile_screen_kernel<D, DI, RPV, true, BR>                  \
+               : (Fn)level_tile_screen_kernel<D, DI, RPV, false, BR>;
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: PS_PICK(DIST_GAUSSIAN, false)
+      case 1: PS_PICK(DIST_GAUSSIAN, true)
+      case 2: PS_PICK(DIST_POISSON, false)
+      case 3: PS_PICK(DIST_POISSON, true)
+      default: PS_PICK(DIST_RATIONAL, false)
+    }
+#undef PS_PICK
+  }
+  static LbFn pick_lb(int dist, int rp) {
+    using namespace ps;
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: return (LbFn)screen_lb_kernel<D, DIST_GAUSSIAN, false>;
+      case 1: return (LbFn)screen_lb_kernel<D, DIST_GAUSSIAN, true>;
+      case 2: return (LbFn)screen_lb_kernel<D, DIST_POISSON, false>;
+      case 3: return (LbFn)screen_lb_kernel<D, DIST_POISSON, true>;
+      default: return (LbFn)screen_lb_kernel<D, DIST_RATIONAL, false>;
+    }
+  }
+};
+
 ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int rb_step, int tile_rows = BR) {
   ps::Geom g;
   g.n = n;
@@ -279,8 +310,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   }
   const int n = p.n, R = p.batch;
   const int Tc = std::min(p.T, n);  // DP_impl.hpp:37-38
-  const int running = (p.sum_mode == PS_SUM_RUNNING);
+  int running = (p.sum_mode == PS_SUM_RUNNING);  // cleared below when the screened path takes over (exact sums)
   const int rp = p.risk_part ? 1 : 0;
+  if (p.screen < 0 || p.screen > 2) {
+    ctx->err = "bad screen option";
+    return PS_ERR_INVALID;
+  }
   PS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   memset(&ctx->tm, 0, sizeof(ctx->tm));
@@ -311,11 +346,23 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   int host_flags = 1;
   cudaEvent_t e_flags = nullptr;
   const bool want_fast = running && p.no_fast_math != 1;
+  // screened levels (screen.cuh): worth it once a level has enough cells to amortise the extra launch
+  const bool want_screen = want_fast && p.screen != 1 && p.no_fast_math == 0 && std::min(p.T, n) >= 3 && n >= 512 &&
+                           (long long)n * R >= 8192;
   if (want_fast) {
     PS_TRY(ensure(ctx, ctx->scalar, 64));
     PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, sizeof(int), st));
     ps::range_check_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, d_a, d_b, (int*)ctx->scalar.p);
     ctx->launches++;
+    if (want_screen) {  // exact summability of every instance -> flag bit 2
+      PS_TRY(ensure(ctx, ctx->scr_stats, (size_t)R * sizeof(ps::ScreenStats)));
+      ps::ScreenStats* d_st = (ps::ScreenStats*)ctx->scr_stats.p;
+      ps::screen_stats_init_kernel<<<cdiv(R, 256), 256, 0, st>>>(R, d_st);
+      const int bx = std::max(1, std::min(cdiv(n, 256 * 4), std::max(1, 2048 / R)));
+      ps::screen_stats_kernel<D><<<dim3(bx, R), 256, 0, st>>>(n, d_a, d_b, d_st);
+      ps::screen_decide_kernel<D><<<cdiv(R, 256), 256, 0, st>>>(R, d_st, (int*)ctx->scalar.p);
+      ctx->launches += 3;
+    }
     if (!ctx->pinned_flags) PS_CUDA(ctx, cudaMallocHost((void**)&ctx->pinned_flags, 64));
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags, ctx->scalar.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PS_TRY(mark(ctx, &e_flags));
@@ -330,6 +377,15 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   ps::Rec4<D>* recs[2] = {rec0, rec1};
   const D* d_as = (const D*)ctx->a_s.p;
   const D* d_bs = (const D*)ctx->b_s.p;
+  int fast = 0, screen = 0;
+  if (want_fast) {  // the precheck ran right after the inputs arrived; its flags are on the host by now
+    PS_CUDA(ctx, cudaEventSynchronize(e_flags));
+    host_flags = *ctx->pinned_flags;
+    fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
+    // screening needs positive sums for every score (relative error of the float range sums) and exact summability
+    screen = want_screen && fast && (host_flags & 2) == 0 && (host_flags & 4) == 0;
+  }
+  if (screen) running = 0;  // exactly summable: prefix differences ARE the reference's running sums, bit for bit
   if (running) {
     ps::build_rec_running_kernel<D><<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(n, rec_stride, d_as, d_bs,
                                                                               rec0, rec1);
@@ -350,12 +406,6 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(mark(ctx, &e_sort));
 
   // ---- level 1
-  int fast = 0;
-  if (want_fast) {  // the precheck ran right after the inputs arrived; its flag is on the host by now
-    PS_CUDA(ctx, cudaEventSynchronize(e_flags));
-    host_flags = *ctx->pinned_flags;
-    fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
-  }
   // float Poisson on the fast path runs the two-rows-per-thread packed kernel (256-row tiles) once there are enough
   // rows to fill the machine with such tiles; smaller instances keep 128-row tiles (more, finer work items)
   const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 &&
@@ -369,6 +419,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   int* d_pa = (int*)ctx->part_arg.p;
   D* d_SA = nullptr;
   D* d_SB = nullptr;
+  float4* recf[2] = {nullptr, nullptr};
   if (running) {
     if (nch_alloc > 1) {
       PS_TRY(ensure(ctx, ctx->SA, R * pstride * sizeof(D)));
@@ -380,8 +431,25 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         n, L, nch_alloc, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
         0, 1, nullptr);
   } else {
+    // screened levels read float records: double -> separate {lx, ly, -, pm} arrays, float -> the records themselves
+    if (screen) {
+      if constexpr (sizeof(D) == 8) {
+        PS_TRY(ensure(ctx, ctx->recf, 2 * R * rec_stride * sizeof(float4)));
+        recf[0] = (float4*)ctx->recf.p;
+        recf[1] = recf[0] + R * rec_stride;
+        ps::build_recf_kernel<<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(n, L, rec_stride, rec0, recf[0], recf[1]);
+        ctx->launches++;
+      } else {
+        recf[0] = (float4*)rec0;
+        recf[1] = (float4*)rec1;
+      }
+      PS_TRY(ensure(ctx, ctx->lb, (size_t)R * n * sizeof(D)));
+      PS_TRY(ensure(ctx, ctx->scr_counters, 2 * sizeof(unsigned long long)));
+      PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 2 * sizeof(unsigned long long), st));
+    }
     ps::level1_prefix_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, rec_stride, p.dist, rp, rec0,
-                                                                      d_ms + n, d_ns + n, table_stride, rec1);
+                                                                      d_ms + n, d_ns + n, table_stride, rec1,
+                                                                      screen ? (float*)recf[1] : nullptr);
   }
   ctx->launches++;
   PS_TRY(mark(ctx, &e_pre));
@@ -398,6 +466,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     }
   }
   auto fn_last = LastLevelLaunch<D>::pick(p.dist, rp, running, fast);
+  auto fn_scr = ScreenLaunch<D>::pick(p.dist, rp, p.screen == 2);
+  auto fn_lb = ScreenLaunch<D>::pick_lb(p.dist, rp);
+  D* d_lb = (D*)ctx->lb.p;
+  unsigned long long* d_cnt = (unsigned long long*)ctx->scr_counters.p;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lev_ev;
   for (int j = 2; j <= Tc; ++j) {
     ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, tile_rows);
@@ -410,12 +482,18 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       // last level: row 0 only -> k-parallel kernel, one CTA per chunk (128-row geometry)
       g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, BR);
       fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+    } else if (screen) {
+      // row lower bounds from a few exactly evaluated cells, then the screened tiles
+      fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, d_lb);
+      fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt);
+      ctx->launches++;
     } else {
       fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
     }
     if (timed) PS_TRY(mark(ctx, &e1));
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
-        g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr);
+        g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
+        screen ? (float*)recf[j & 1] : nullptr);
     ctx->launches += 2;
     if (timed) {
       lev_ev.push_back({e0, e1});
@@ -452,8 +530,17 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(copy_out(res->subset_scores, d_scores, (size_t)R * nS * Tc * sizeof(D)));
   PS_TRY(copy_out(res->max_score, d_ms, R * table_stride * sizeof(D)));
   PS_TRY(copy_out(res->next_start, d_ns, R * table_stride * sizeof(int)));
+  if (screen)
+    PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   PS_TRY(mark(ctx, &e_end));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->tm.screen_used = screen;
+  if (screen) {
+    unsigned long long cnt[2];
+    memcpy(cnt, ctx->pinned_flags + 2, sizeof(cnt));
+    ctx->tm.screen_exact_cells = (long long)cnt[0] * 32;
+    ctx->tm.screen_violations = (long long)cnt[1];
+  }
 
   auto ms_between = [&](cudaEvent_t x, cudaEvent_t y) {
     float v = 0.f;
@@ -698,7 +785,7 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
                                          s->part_arg);
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
         g, (const D*)s->part_val, s->part_arg, (D*)nullptr, s->ns + (long long)j * n, 0,
-        (ps::Rec4<D>*)nullptr, my_chunk);
+        (ps::Rec4<D>*)nullptr, my_chunk, nullptr);
   }
   PS_CUDA(ctx, cudaGetLastError());
   PS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -809,6 +896,18 @@ ps_status ps_selftest_math(ps_ctx* ctx, int which, long long samples, unsigned l
   PS_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->scalar.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
   *mismatches = (long long)bad;
+  return PS_OK;
+}
+
+ps_status ps_selftest_mufu(ps_ctx* ctx, double out[2]) {
+  if (!ctx || !out) return PS_ERR_INVALID;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  PS_TRY(ensure(ctx, ctx->scalar, 64));
+  PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, 2 * sizeof(double), ctx->stream));
+  ps::selftest_mufu_kernel<<<148 * 8, 256, 0, ctx->stream>>>((double*)ctx->scalar.p);
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaMemcpyAsync(out, ctx->scalar.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PS_OK;
 }
 

@@ -1,0 +1,432 @@
+// screen.cuh -- the SCREENED level kernel: every (i,k) cell is bounded in float, only cells that can still
+// win are evaluated with the reference's arithmetic.
+//
+// One DP level (DP_impl.hpp:101-118) is  out[i] = max_k S(i,k) + prev[k], first maximum wins.  The exhaustive
+// kernel (kernels.cuh) spends 60-100 issue cycles per cell on IEEE division and a bit-exact glibc log although
+// all but a few cells of a row lose by a wide margin.  This kernel visits the same cells, but per cell it forms a
+// cheap float UPPER BOUND  ub >= S_ref(i,k) + prev[k]  (MUFU.RCP / MUFU.LG2, ~14 instructions) and compares it with a
+// LOWER BOUND on the row's maximum (an exactly evaluated cell of the same row); a cell whose upper bound is below
+// that cannot be the row's maximum and is dropped.  Surviving cells (a few per cent: the neighbourhood of the
+// maximum) are evaluated by the same ScoreFn functors as the exhaustive kernel, in ascending k with a strict >,
+// so value AND first-argmax are the reference's, bit for bit:
+//   * the first maximiser k* has v(k*) = max >= LB, hence ub(k*) >= LB: it is always evaluated exactly;
+//   * every evaluated cell before k* is strictly smaller (k* is the FIRST maximiser), cells after it never replace it;
+//   * a NaN bound compares false with "ub < thr" and is evaluated exactly; a NaN value never wins, as in the reference.
+//
+// Preconditions (checked per call on the device; otherwise the exhaustive kernel runs):
+//   (P1) safe range (range_check_kernel) and a[i] > 0, b[i] > 0: all range sums are positive normal numbers;
+//   (P2) exact summability (exact_check_kernel): every a[i] (b[i]) is a multiple of one power of two 2^e and
+//        sum|a| <= 2^(e+p) (p = 24/53), e.g. counts.  Then EVERY partial sum is representable, every addition the
+//        reference performs is exact, and range sums formed as differences of a prefix scan are bit-identical to
+//        the reference's running sums (score_impl.hpp:248-256) -- cells can be evaluated in any order.
+//
+// Error budget of the bound (u = 2^-24; hardware claims R1, R2 are verified exhaustively by ps_selftest_mufu):
+//   (R1) |x * rcp.approx(x) - 1| <= 4u;   (R2) |lg2.approx(x) - log2 x| <= 4u * max(1, |log2 x|).
+//   inputs   double: At = fl(lx[k] + bx), lx = fl32(P[k] - P[cL]), bx = fl32(P[cL] - P[i]), all terms >= 0
+//                    => |At - A| <= 3u A.   float: At = P[k] - P[i] exactly (P2).
+//            diagonal tiles (cL <= i) convert the exact double difference instead (|At - A| <= u A).
+//   value    for g(A,B) = A ln(A/B) + B - A:  |g(At,Bt) - g(A,B)| <= 3u (A |ln q| + |A - B|)   (mean value theorem)
+//   MUFU     ln(q) from rcp, one multiply and lg2: absolute error <= (5u + 4u ln2) + 4u |ln q|
+//   chain    every float operation of the bound rounds by <= u relative to an intermediate bounded by
+//            A |ln q| + A + B + |p|
+//   ref      the reference's own rounding: |S_ref - g| <= 6 u_D (A |ln q| + A + B), final add u_D (|S| + |p|)
+//   => ub = t ln2 (1 + 32u) + (B - A) + 48u A + pm,  pm = ru(p) + 16u |p|   dominates S_ref + p  (needed: 16u, 30u, 3u).
+//   The other scores follow the same scheme; their budgets are next to their functors.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "kernels.cuh"
+
+namespace ps {
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+constexpr float SCR_LN2_UP = 0.693147182464599609375f * (1.0f + 1.9073486328125e-06f);  // ln2 (1 + 2^-19)
+constexpr float SCR_REL_UP = 1.0f + 1.9073486328125e-06f;                               // 1 + 2^-19
+constexpr float SCR_CA = 2.86102294921875e-06f;                                         // 48 u
+constexpr float SCR_TINY = 9.31322574615478515625e-10f;                                 // 2^-30
+
+// Upper bound of S(A,B) + p from float sums At, Bt (> 0) and pm = screen_pm(p).
+template <int DIST, bool RP>
+struct ScreenUB;
+
+template <>
+struct ScreenUB<DIST_POISSON, false> {  // (A > B) ? A ln(A/B) + B - A : 0      score_impl.hpp:385-388
+  static __device__ __forceinline__ float eval(float A, float B, float pm) {
+    if (A > B) {
+      const float q = A * rcp_approx(B);
+      const float t = A * lg2_approx(q);
+      const float dm = fmaf(A, -(1.0f - SCR_CA), B);  // B - A + 48u A
+      return fmaf(t, SCR_LN2_UP, dm + pm);
+    }
+    // At <= Bt although A > B is only possible within the input error: then S <= (6uA)^2 / B << 2^-30 B
+    return fmaf(B, SCR_TINY, pm);
+  }
+};
+template <>
+struct ScreenUB<DIST_POISSON, true> {  // A ln(A/B), either sign       score_impl.hpp:377-378
+  // d/dA = ln q + 1, d/dB = -q: input error 3u (A |ln q| + 2A); the remaining terms as for the mult-clust score
+  static __device__ __forceinline__ float eval(float A, float B, float pm) {
+    const float q = A * rcp_approx(B);
+    const float t = A * lg2_approx(q);
+    const float e = fmaf(fabsf(t), 0.693147182464599609375f * 1.9073486328125e-06f, fmaf(A, SCR_CA, pm));
+    return fmaf(t, 0.693147182464599609375f, e);
+  }
+};
+template <>
+struct ScreenUB<DIST_GAUSSIAN, false> {  // (A > B) ? .5 (A^2/B + B) - A : 0 = (A-B)^2 / (2B)   score_impl.hpp:429-431
+  // g(At,Bt) is evaluated in its cancellation-free form, relative error 2^-21; input error
+  // |dg| <= (q-1) 3uA + .5 (q^2-1) 3uB <= 6u A (q-1); reference rounding <= 9 u_D A q (+ u g when D = float).
+  static __device__ __forceinline__ float eval(float A, float B, float pm) {
+    if (A > B) {
+      const float dif = A - B;
+      const float h = dif * rcp_approx(B);  // q - 1
+      const float gt = (0.5f * dif) * h;
+      const float ah = A * h;
+      float e = fmaf(ah, 8.0f * 5.9604644775390625e-08f, pm);
+      e = fmaf(A, SCR_TINY, e);
+      return fmaf(gt, SCR_REL_UP, e);
+    }
+    return fmaf(B, SCR_TINY, pm);
+  }
+};
+template <>
+struct ScreenUB<DIST_GAUSSIAN, true> {  // A^2 / (2B)       score_impl.hpp:438-439
+  // everything is relative to g: inputs 9u, rcp 4u, roundings 3u, reference 3u  < 32u
+  static __device__ __forceinline__ float eval(float A, float B, float pm) {
+    const float gt = (0.5f * A) * (A * rcp_approx(B));
+    return fmaf(gt, SCR_REL_UP, pm);
+  }
+};
+template <bool RP>
+struct ScreenUB<DIST_RATIONAL, RP> {  // A^2 / B          score_impl.hpp:464-465,471-472
+  static __device__ __forceinline__ float eval(float A, float B, float pm) {
+    const float gt = A * (A * rcp_approx(B));
+    return fmaf(gt, SCR_REL_UP, pm);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// (P2) exact summability.  stats[inst] = {min over elements of the exponent of the lowest set bit, sum |.|}
+// for a and for b; screen_decide_kernel raises flag bit 2 (value 4) if some instance fails.
+// ---------------------------------------------------------------------------------------------
+struct ScreenStats {
+  int ea, eb;
+  double sa, sb;
+};
+__device__ __forceinline__ int lowbit_exp(double v) {
+  const long long bits = __double_as_longlong(v);
+  const int e = (int)((bits >> 52) & 0x7ff) - 1075;
+  const long long m = (bits & 0xfffffffffffffLL) | (1LL << 52);
+  return e + __ffsll(m) - 1;
+}
+__device__ __forceinline__ int lowbit_exp(float v) {
+  const int bits = __float_as_int(v);
+  const int e = ((bits >> 23) & 0xff) - 150;
+  const int m = (bits & 0x7fffff) | 0x800000;
+  return e + __ffs(m) - 1;
+}
+__global__ void screen_stats_init_kernel(int R, ScreenStats* __restrict__ st) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) {
+    st[r].ea = st[r].eb = 0x7fffffff;
+    st[r].sa = st[r].sb = 0.0;
+  }
+}
+template <typename D>
+__global__ void __launch_bounds__(256)
+screen_stats_kernel(int n, const D* __restrict__ a, const D* __restrict__ b, ScreenStats* __restrict__ st) {
+  const int inst = blockIdx.y;
+  a += (long long)inst * n;
+  b += (long long)inst * n;
+  int ea = 0x7fffffff, eb = 0x7fffffff;
+  double sa = 0.0, sb = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const D av = a[k], bv = b[k];
+    if (av != (D)0) ea = min(ea, lowbit_exp(av));
+    if (bv != (D)0) eb = min(eb, lowbit_exp(bv));
+    sa += fabs((double)av);
+    sb += fabs((double)bv);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ea = min(ea, __shfl_xor_sync(0xffffffffu, ea, o));
+    eb = min(eb, __shfl_xor_sync(0xffffffffu, eb, o));
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&st[inst].ea, ea);
+    atomicMin(&st[inst].eb, eb);
+    atomicAdd(&st[inst].sa, sa);
+    atomicAdd(&st[inst].sb, sb);
+  }
+}
+template <typename D>
+__global__ void screen_decide_kernel(int R, const ScreenStats* __restrict__ st, int* __restrict__ flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  constexpr int P = (sizeof(D) == 8) ? 53 : 24;
+  // the double sums are exact whenever the instance qualifies; the 2^-20 slack covers their rounding when it does not
+  const double slack = 1.0 - 9.5367431640625e-07;
+  bool ok = true;
+  if (st[r].ea != 0x7fffffff) ok = ok && (st[r].sa <= ldexp(slack, st[r].ea + P));
+  if (st[r].eb != 0x7fffffff) ok = ok && (st[r].sb <= ldexp(slack, st[r].eb + P));
+  if (!ok) atomicOr(flags, 4);
+}
+
+// double only: float screening records {lx, ly, -, pm}: prefix sums relative to the start of the k-chunk they fall
+// in (chunk of k = (k-1)/L, origin cL), so that float range sums carry a RELATIVE error (header).  pm is written by
+// the level kernels (level1_prefix_kernel / combine_kernel).
+__global__ void build_recf_kernel(int n, int L, long long rec_stride, const Rec4<double>* __restrict__ rec,
+                                  float4* __restrict__ recf0, float4* __restrict__ recf1) {
+  const int inst = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n) return;
+  rec += inst * rec_stride;
+  const int kc = (k > 0) ? ((k - 1) / L) * L : 0;
+  const Rec4<double> r = rec[k], o = rec[kc];
+  const float4 f = make_float4(__double2float_rn(r.x - o.x), __double2float_rn(r.y - o.y), 0.f, 0.f);
+  recf0[inst * rec_stride + k] = f;
+  recf1[inst * rec_stride + k] = f;
+}
+
+template <typename D, int DIST, bool RP, bool LOGTAB>
+__device__ __forceinline__ D screen_exact_score(D A, D B, const GlogEntry* s_log) {
+  if constexpr (!RP && DIST != DIST_RATIONAL) {
+    if (!gt_ab<true>(A, B)) return (D)0;
+    if constexpr (LOGTAB)
+      return ScoreFn<D, DIST, RP, true>::eval_gt(A, B, s_log);
+    else
+      return ScoreFn<D, DIST, RP, true>::eval_gt(A, B);
+  } else if constexpr (LOGTAB) {
+    return ScoreFn<D, DIST, RP, true>::eval(A, B, s_log);
+  } else {
+    return ScoreFn<D, DIST, RP, true>::eval(A, B);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lower bound of every row's maximum: the best of <= 2*64 EXACTLY evaluated cells of the row (a coarse sweep over
+// the row's k range, then a finer one around the best coarse sample).  Any evaluated cell is a valid bound; the
+// sampling only decides how tight it is (on C3 the best sample is within 1 of the maximum).
+// ---------------------------------------------------------------------------------------------
+template <typename D, int DIST, bool RP>
+__global__ void __launch_bounds__(128)
+screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, D* __restrict__ LB) {
+  const int inst = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nrows) return;
+  rec += (long long)inst * g.rec_stride;
+  const D Xi = rec[i].x, Yi = rec[i].y;
+  const int k0 = i + 1, k1 = g.kmax;
+  const int len = k1 - k0 + 1;
+  D best = Lim<D>::lowest();
+  int kb = k1;
+  auto probe = [&](int k) {
+    const Rec4<D> r = rec[k];
+    const D v = add_rn<D>(screen_exact_score<D, DIST, RP, false>(sub_rn<D>(r.x, Xi), sub_rn<D>(r.y, Yi), nullptr), r.p);
+    if (v > best) {
+      best = v;
+      kb = k;
+    }
+  };
+  const int ns = max(4, min(64, len >> 7));
+  const int sc = max(1, len / ns);
+  for (int k = k0; k <= k1; k += sc) probe(k);
+  probe(k1);
+  if (sc > 1) {
+    const int lo = max(k0, kb - sc), hi = min(k1, kb + sc);
+    const int sf = max(1, (hi - lo) / ns);
+    for (int k = lo; k <= hi; k += sf) probe(k);
+  }
+  LB[(long long)inst * g.n + i] = best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One (row block, k-chunk) tile of one level, screened.  Same tiling, launch order and partial/combine protocol as
+// level_tile_kernel.  counters[0] += warp-cells evaluated exactly, counters[1] += audit violations (ub < exact value).
+// ---------------------------------------------------------------------------------------------
+template <typename D, int DIST, bool RP, bool AUDIT, int BR>
+__global__ void __launch_bounds__(BR)
+level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* __restrict__ recf,
+                         const D* __restrict__ LB, D* __restrict__ part_val, int* __restrict__ part_arg,
+                         unsigned long long* __restrict__ counters) {
+  constexpr int BK = BR;
+  constexpr bool DBL = (sizeof(D) == 8);
+  __shared__ float4 sbuf[2][BK];
+  constexpr bool kLogTab = DBL && (DIST == DIST_POISSON);
+  __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
+  if (kLogTab) {
+    static_assert(BR >= 128, "one table entry per thread");
+    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
+  }
+
+  const int inst = blockIdx.y;
+  rec += (long long)inst * g.rec_stride;
+  recf += (long long)inst * g.rec_stride;
+  LB += (long long)inst * g.n;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  part_val += inst * pstride;
+  part_arg += inst * pstride;
+
+  int rb, c;
+  decode_tile(g, blockIdx.x, rb, c);
+  const int tid = threadIdx.x;
+  const int i0 = rb * BR;
+  const int i = i0 + tid;
+  const int k_lo = max(c * g.L + 1, i0 + 1);
+  const int k_hi = min((c + 1) * g.L, g.kmax);
+  const bool diag = (c == rb / g.G);
+
+  const int il = min(i, g.n - 1);
+  const D Xi = rec[il].x, Yi = rec[il].y;
+  float bx, by;  // At = recf[k].x + bx
+  if (DBL) {
+    const Rec4<D> o = rec[c * g.L];
+    bx = __double2float_rn((double)o.x - (double)Xi);
+    by = __double2float_rn((double)o.y - (double)Yi);
+  } else {
+    bx = -(float)Xi;
+    by = -(float)Yi;
+  }
+  D best = Lim<D>::lowest();
+  int arg = -1;
+  float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
+  unsigned int nexact = 0, nviol = 0;
+
+  // one cell: bound, vote, exact evaluation of the whole warp if any lane survives
+  auto cell = [&](const int k, const float4 r, const bool valid, auto from_double) {
+    float A, B;
+    if constexpr (decltype(from_double)::value) {
+      const Rec4<D> R = rec[k];
+      A = __double2float_rn((double)R.x - (double)Xi);
+      B = __double2float_rn((double)R.y - (double)Yi);
+    } else {
+      A = __fadd_rn(r.x, bx);
+      B = __fadd_rn(r.y, by);
+    }
+    const float ub = ScreenUB<DIST, RP>::eval(A, B, r.w);
+    const bool pass = valid && !(ub < thr);
+    if (AUDIT || __any_sync(0xffffffffu, pass)) {
+      const Rec4<D> R = rec[k];
+      const D v = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
+      if (AUDIT) {
+        if (valid && (double)ub < (double)v) ++nviol;
+        if (!__any_sync(0xffffffffu, pass)) return;  // audit only: keep the screened kernel's own decisions
+      }
+      ++nexact;
+      if (valid && v > best) {
+        best = v;
+        arg = k;
+        thr = fmaxf(thr, screen_rd<D>(best));
+      }
+    }
+  };
+  using T_ = std::integral_constant<bool, true>;
+  using F_ = std::integral_constant<bool, false>;
+
+  const int nk = k_hi - k_lo + 1;
+  const int nstages = (nk + BK - 1) / BK;
+  {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
+    sbuf[0][tid] = r;
+  }
+  for (int s = 0; s < nstages; ++s) {
+    __syncthreads();
+    const int kb = k_lo + s * BK;
+    const int kn = kb + BK + tid;
+    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_next = (s + 1 < nstages);
+    if (has_next && kn <= k_hi) nx = recf[kn];
+    const int cnt = min(BK, k_hi - kb + 1);
+    const float4* __restrict__ sb = sbuf[s & 1];
+    if (DBL && diag) {
+      // diagonal tile of the double kernel: chunk-relative float sums would cancel, convert the exact differences
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
+    } else if (kb > i0 + BR - 1) {
+      if (cnt == BK) {
+        // Interior stage.  Cells are bounded in groups of U: the U chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA
+        // pipe operations) are independent, so their latencies overlap, and one vote decides for the whole group;
+        // only a group with a surviving cell (near the row maximum) goes through the per-cell path.
+        constexpr int U = 8;
+        constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
+#pragma unroll 1
+        for (int kk = 0; kk < BK; kk += U) {
+          float A[U], B[U], W[U];
+          bool gt = false;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float4 r = sb[kk + u];
+            A[u] = __fadd_rn(r.x, bx);
+            B[u] = __fadd_rn(r.y, by);
+            W[u] = r.w;
+            if (FRONTIER) gt |= A[u] > B[u];
+          }
+          bool alive = false;
+          if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
+            // the whole 32 x U patch is on the S = 0 side of the A = B frontier (mult-clust scores)
+#pragma unroll
+            for (int u = 0; u < U; ++u) alive |= !(fmaf(B[u], SCR_TINY, W[u]) < thr);
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) alive |= !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
+          }
+          if (AUDIT || __any_sync(0xffffffffu, alive)) {
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) cell(kb + kk + u, sb[kk + u], true, F_{});
+          }
+        }
+      } else {
+        for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
+      }
+    } else {
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, F_{});
+    }
+    if (has_next) sbuf[(s + 1) & 1][tid] = nx;
+  }
+  if (i < g.nrows) {
+    part_val[(long long)c * g.n + i] = best;
+    part_arg[(long long)c * g.n + i] = arg;
+  }
+  if (counters) {
+    if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
+    if (AUDIT) {
+      for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+      if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+    }
+  }
+}
+
+// Exhaustive check of the two hardware claims the error budget rests on, over every float in the safe range:
+// out[0] = max |x rcp(x) - 1| / u  over x in [2^-62, 2^62];  out[1] = max |lg2(x) - log2 x| / (u max(1, |log2 x|))
+// over x in [2^-92, 2^92]  (u = 2^-24; references computed in double).
+__global__ void selftest_mufu_kernel(double* __restrict__ out) {
+  const unsigned int stride = gridDim.x * blockDim.x;
+  double e_rcp = 0.0, e_lg2 = 0.0;
+  const unsigned int lo = (127u - 92u) << 23, hi = (127u + 92u) << 23;
+  for (unsigned int bits = lo + blockIdx.x * blockDim.x + threadIdx.x; bits < hi; bits += stride) {
+    const float x = __uint_as_float(bits);
+    const int ex = (int)(bits >> 23) - 127;
+    if (ex >= -62 && ex < 62) e_rcp = fmax(e_rcp, fabs((double)x * (double)rcp_approx(x) - 1.0));
+    const double l = log2((double)x);
+    e_lg2 = fmax(e_lg2, fabs((double)lg2_approx(x) - l) / fmax(1.0, fabs(l)));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    e_rcp = fmax(e_rcp, __shfl_xor_sync(0xffffffffu, e_rcp, o));
+    e_lg2 = fmax(e_lg2, __shfl_xor_sync(0xffffffffu, e_lg2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // non-negative doubles order like their bit patterns
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(e_rcp * 16777216.0));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(e_lg2 * 16777216.0));
+  }
+}
+
+}  // namespace ps

@@ -76,7 +76,7 @@ class CudaShardEngine:
 
     def create(self, a_s, b_s, n, T, dist_id, risk_part, dtype, rank, world, sum_mode=capi.PS_SUM_RUNNING):
         p = capi.PsProblem(n=n, T=T, dist=dist_id, risk_part=int(risk_part), sum_mode=sum_mode, sort_mode=0,
-                           perm=None, sweep=0, batch=1, on_device=1, no_fast_math=0, chunk_len=0)
+                           perm=None, sweep=0, batch=1, on_device=1, no_fast_math=0, chunk_len=0, screen=0)
         fn = self.lib.ps_shard_create_f64 if dtype == np.float64 else self.lib.ps_shard_create_f32
         self.ctx._check(fn(self.ctx._h, C.byref(p), C.c_void_p(a_s.data_ptr()), C.c_void_p(b_s.data_ptr()), rank,
                            world, C.byref(self._h)))
