@@ -51,6 +51,7 @@ struct Geom {
   // row sharding (single huge instance over several GPUs): this rank owns row blocks
   // rb_first + rb_step * m, m = 0..NRB-1 (NRB counts OWNED blocks).  Unsharded: 0, 1.
   int rb_first, rb_step;
+  const int2* tile_map;   // optional table tile -> (rb, c) in launch order; nullptr = decode arithmetically
 };
 
 __host__ __device__ inline int geom_count_tiles(int NCH, int G, int NRB, int rb_first, int rb_step) {
@@ -67,6 +68,12 @@ __host__ __device__ inline int geom_count_tiles(int NCH, int G, int NRB, int rb_
 // tail keeps the SMs level (first-fit in decreasing cost); with uniform cost (risk partitioning) the order is
 // harmless.  Tile t -> (row block rb, chunk c), c from the row block's diagonal chunk rb/G up to NCH-1.
 __device__ __forceinline__ void decode_tile(const Geom& g, int t, int& rb, int& c) {
+  if (g.tile_map) {  // unsharded runs: the (rb, c) of every tile, tabulated once per geometry (build_tile_map_kernel)
+    const int2 m = g.tile_map[t];
+    rb = m.x;
+    c = m.y;
+    return;
+  }
   if (g.rb_step == 1 && g.rb_first == 0) {
     int s = (g.NRB - 1) / g.G;  // super-block = G row blocks sharing a diagonal chunk
     for (;;) {
@@ -90,6 +97,17 @@ __device__ __forceinline__ void decode_tile(const Geom& g, int t, int& rb, int& 
     }
     t -= cnt;
   }
+}
+
+// The decode loop walks up to NRB/G super-blocks; with 30k short tiles per level that is a few per cent of a level,
+// so unsharded runs tabulate it once per geometry.
+__global__ void build_tile_map_kernel(Geom g, int2* __restrict__ map) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.ntiles) return;
+  g.tile_map = nullptr;
+  int rb, c;
+  decode_tile(g, t, rb, c);
+  map[t] = make_int2(rb, c);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -38,7 +38,8 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters;
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map;
+  int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
   long long launches = 0;
@@ -218,6 +219,7 @@ ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int
   g.rb_first = rb_first;
   g.rb_step = rb_step;
   g.ntiles = ps::geom_count_tiles(g.NCH, g.G, g.NRB, rb_first, rb_step);
+  g.tile_map = nullptr;
   return g;
 }
 
@@ -482,13 +484,26 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       // last level: row 0 only -> k-parallel kernel, one CTA per chunk (128-row geometry)
       g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, BR);
       fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
-    } else if (screen) {
-      // row lower bounds from a few exactly evaluated cells, then the screened tiles
-      fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, d_lb);
-      fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt);
-      ctx->launches++;
     } else {
-      fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+      if (g.ntiles >= 2048) {
+        // tile -> (row block, chunk) table, rebuilt only when the geometry changes (kmax shrinks by one per level)
+        if (ctx->map_key[0] != g.NCH || ctx->map_key[1] != g.G || ctx->map_key[2] != g.NRB ||
+            ctx->map_key[3] != g.ntiles) {
+          PS_TRY(ensure(ctx, ctx->tile_map, (size_t)g.ntiles * sizeof(int2)));
+          ps::build_tile_map_kernel<<<cdiv(g.ntiles, 128), 128, 0, st>>>(g, (int2*)ctx->tile_map.p);
+          ctx->launches++;
+          ctx->map_key[0] = g.NCH, ctx->map_key[1] = g.G, ctx->map_key[2] = g.NRB, ctx->map_key[3] = g.ntiles;
+        }
+        g.tile_map = (const int2*)ctx->tile_map.p;
+      }
+      if (screen) {
+        // row lower bounds from a few exactly evaluated cells, then the screened tiles
+        fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, d_lb);
+        fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt);
+        ctx->launches++;
+      } else {
+        fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+      }
     }
     if (timed) PS_TRY(mark(ctx, &e1));
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(

@@ -378,9 +378,26 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
 #pragma unroll
             for (int u = 0; u < U; ++u) alive |= !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
           }
-          if (AUDIT || __any_sync(0xffffffffu, alive)) {
+          if (AUDIT) {
 #pragma unroll 1
             for (int u = 0; u < U; ++u) cell(kb + kk + u, sb[kk + u], true, F_{});
+          } else if (__any_sync(0xffffffffu, alive)) {
+            // a survivor: the group lies in the neighbourhood of the row maximum, where most cells survive --
+            // evaluate all U exactly (independent chains, loads issued together), then take them in ascending k
+            D v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const Rec4<D> R = rec[kb + kk + u];
+              v[u] = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (v[u] > best) {
+                best = v[u];
+                arg = kb + kk + u;
+              }
+            thr = fmaxf(thr, screen_rd<D>(best));
+            nexact += U;
           }
         }
       } else {
