@@ -176,7 +176,7 @@ struct LastLevelLaunch {
 
 template <typename D>
 struct ScreenLaunch {
-  using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*);
+  using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*, const int*);
   using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, D*);
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
@@ -353,7 +353,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
                            (long long)n * R >= 8192;
   if (want_fast) {
     PS_TRY(ensure(ctx, ctx->scalar, 64));
-    PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, sizeof(int), st));
+    PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, 2 * sizeof(int), st));  // [0] range/exactness, [1] sortedness
     ps::range_check_kernel<D><<<cdiv(total, 256), 256, 0, st>>>(total, d_a, d_b, (int*)ctx->scalar.p);
     ctx->launches++;
     if (want_screen) {  // exact summability of every instance -> flag bit 2
@@ -445,6 +445,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         recf[0] = (float4*)rec0;
         recf[1] = (float4*)rec1;
       }
+      ps::screen_sorted_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, d_as, d_bs, (int*)ctx->scalar.p + 1);
+      ctx->launches++;
       PS_TRY(ensure(ctx, ctx->lb, (size_t)R * n * sizeof(D)));
       PS_TRY(ensure(ctx, ctx->scr_counters, 2 * sizeof(unsigned long long)));
       PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 2 * sizeof(unsigned long long), st));
@@ -499,7 +501,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       if (screen) {
         // row lower bounds from a few exactly evaluated cells, then the screened tiles
         fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, d_lb);
-        fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt);
+        fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt,
+                                                 (const int*)ctx->scalar.p);
         ctx->launches++;
       } else {
         fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
@@ -728,7 +731,7 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   if (running && pp->no_fast_math != 1) {
     PS_TRY(ensure(ctx, ctx->scalar, 64));
     int flags = 1;
-    PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, sizeof(int), st));
+    PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, 2 * sizeof(int), st));  // [0] range/exactness, [1] sortedness
     ps::range_check_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, a_s, b_s, (int*)ctx->scalar.p);
     PS_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->scalar.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PS_CUDA(ctx, cudaStreamSynchronize(st));

@@ -180,6 +180,19 @@ __global__ void screen_decide_kernel(int R, const ScreenStats* __restrict__ st, 
   if (!ok) atomicOr(flags, 4);
 }
 
+// Priorities ascending?  (always true after the device sort; a caller-supplied permutation is only trusted after this
+// check.)  flag[0] |= 1 if some a[k]/b[k] > a[k+1]/b[k+1] or a key is NaN.
+template <typename D>
+__global__ void screen_sorted_kernel(int n, const D* __restrict__ as, const D* __restrict__ bs, int* __restrict__ flag) {
+  const int inst = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k + 1 >= n) return;
+  as += (long long)inst * n;
+  bs += (long long)inst * n;
+  const D k0 = as[k] / bs[k], k1 = as[k + 1] / bs[k + 1];
+  if (!(k0 <= k1)) atomicOr(flag, 1);
+}
+
 // double only: float screening records {lx, ly, -, pm}: prefix sums relative to the start of the k-chunk they fall
 // in (chunk of k = (k-1)/L, origin cL), so that float range sums carry a RELATIVE error (header).  pm is written by
 // the level kernels (level1_prefix_kernel / combine_kernel).
@@ -256,10 +269,12 @@ template <typename D, int DIST, bool RP, bool AUDIT, int BR>
 __global__ void __launch_bounds__(BR)
 level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* __restrict__ recf,
                          const D* __restrict__ LB, D* __restrict__ part_val, int* __restrict__ part_arg,
-                         unsigned long long* __restrict__ counters) {
+                         unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags) {
   constexpr int BK = BR;
   constexpr bool DBL = (sizeof(D) == 8);
+  constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;  // scores that are 0 unless A > B
   __shared__ float4 sbuf[2][BK];
+  __shared__ float s_pmax[2][BR / 32];  // per stage and warp: max of pm over the records that warp staged
   constexpr bool kLogTab = DBL && (DIST == DIST_POISSON);
   __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
   if (kLogTab) {
@@ -333,10 +348,20 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
 
   const int nk = k_hi - k_lo + 1;
   const int nstages = (nk + BK - 1) / BK;
+  // mult-clust scores, priorities verified ascending (dev_flags[1] == 0): A/B of a row grows with k, so a stage whose
+  // LAST cell has A <= B (1 - 2^-18) for every row of the warp lies entirely on the S = 0 side of the frontier; there
+  // v = prev[k] exactly, and if the largest pm of the stage is below every lane's threshold the warp skips the stage.
+  // (Margin: the float sums are within 3u, the sorted keys fl(a/b) within 2 u_D of the true ratios.)
+  const bool mono = FRONTIER && dev_flags && (dev_flags[1] == 0);
+  auto stage_max = [&](float w, int buf) {
+    for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((tid & 31) == 0) s_pmax[buf][tid >> 5] = w;
+  };
   {
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
     sbuf[0][tid] = r;
+    if (FRONTIER) stage_max(r.w, 0);
   }
   for (int s = 0; s < nstages; ++s) {
     __syncthreads();
@@ -351,12 +376,28 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
       // diagonal tile of the double kernel: chunk-relative float sums would cancel, convert the exact differences
       for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
     } else if (kb > i0 + BR - 1) {
-      if (cnt == BK) {
+      bool skip = false;
+      if (FRONTIER && cnt == BK && mono) {
+        float pmx = s_pmax[s & 1][0];
+#pragma unroll
+        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
+        const float4 re = sb[BK - 1];
+        const float Ae = __fadd_rn(re.x, bx), Be = __fadd_rn(re.y, by);
+        skip = __all_sync(0xffffffffu, (Ae <= Be * 0.999996185302734375f) && (pmx < thr));
+      }
+      if (skip) {
+        if (AUDIT) {  // audit: every cell of a skipped stage must indeed lose (exact value below the threshold)
+          for (int kk = 0; kk < BK; ++kk) {
+            const Rec4<D> R = rec[kb + kk];
+            const D v = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
+            if (!((double)v < (double)thr)) ++nviol;
+          }
+        }
+      } else if (cnt == BK) {
         // Interior stage.  Cells are bounded in groups of U: the U chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA
         // pipe operations) are independent, so their latencies overlap, and one vote decides for the whole group;
         // only a group with a surviving cell (near the row maximum) goes through the per-cell path.
         constexpr int U = 8;
-        constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
 #pragma unroll 1
         for (int kk = 0; kk < BK; kk += U) {
           float A[U], B[U], W[U];
@@ -406,7 +447,10 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     } else {
       for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, F_{});
     }
-    if (has_next) sbuf[(s + 1) & 1][tid] = nx;
+    if (has_next) {
+      sbuf[(s + 1) & 1][tid] = nx;
+      if (FRONTIER) stage_max(nx.w, (s + 1) & 1);
+    }
   }
   if (i < g.nrows) {
     part_val[(long long)c * g.n + i] = best;
