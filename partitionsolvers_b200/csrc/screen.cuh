@@ -275,6 +275,14 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
   constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;  // scores that are 0 unless A > B
   __shared__ float4 sbuf[2][BK];
   __shared__ float s_pmax[2][BR / 32];  // per stage and warp: max of pm over the records that warp staged
+  constexpr int U = 8;                  // cells per group
+  __shared__ float s_gmax[2][BK / U];   // per stage and group of U consecutive k: max of pm
+  // Scores that never decrease when a row's range is extended to the right (priorities ascending, a > 0): with
+  // r = a_k/b_k >= q = A/B,  dS/db = r ln q + 1 - q >= q ln q + 1 - q >= 0 (Poisson mult-clust, q > 1; S = 0 below),
+  // (q-1) r - (q^2-1)/2 >= (q-1)^2/2 (Gaussian mult-clust), 2 q r - q^2 >= q^2 (A^2/B, A^2/2B).  Poisson risk-part
+  // (A ln(A/B), decreasing while q < 1/e) is not.  For these, ONE bound at the last cell of a group with the group's
+  // largest pm covers every cell of the group.
+  constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
   constexpr bool kLogTab = DBL && (DIST == DIST_POISSON);
   __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
   if (kLogTab) {
@@ -352,16 +360,19 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
   // LAST cell has A <= B (1 - 2^-18) for every row of the warp lies entirely on the S = 0 side of the frontier; there
   // v = prev[k] exactly, and if the largest pm of the stage is below every lane's threshold the warp skips the stage.
   // (Margin: the float sums are within 3u, the sorted keys fl(a/b) within 2 u_D of the true ratios.)
-  const bool mono = FRONTIER && dev_flags && (dev_flags[1] == 0);
+  const bool mono = (FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0);
   auto stage_max = [&](float w, int buf) {
-    for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+    static_assert(U == 8, "group maxima are formed over 8 adjacent lanes");
+    for (int o = 1; o < 8; o <<= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((tid & 7) == 0) s_gmax[buf][tid >> 3] = w;
+    for (int o = 8; o < 32; o <<= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
     if ((tid & 31) == 0) s_pmax[buf][tid >> 5] = w;
   };
   {
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
     sbuf[0][tid] = r;
-    if (FRONTIER) stage_max(r.w, 0);
+    if (FRONTIER || GROUPB) stage_max(r.w, 0);
   }
   for (int s = 0; s < nstages; ++s) {
     __syncthreads();
@@ -397,9 +408,24 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
         // Interior stage.  Cells are bounded in groups of U: the U chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA
         // pipe operations) are independent, so their latencies overlap, and one vote decides for the whole group;
         // only a group with a surviving cell (near the row maximum) goes through the per-cell path.
-        constexpr int U = 8;
 #pragma unroll 1
         for (int kk = 0; kk < BK; kk += U) {
+          if (GROUPB && mono) {
+            // tier 1: one bound for the whole group (monotone scores): S(i,k) <= S(i,k_last), pm[k] <= group max
+            const float4 re = sb[kk + U - 1];
+            const float ubg = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), s_gmax[s & 1][kk / U]);
+            if (!__any_sync(0xffffffffu, !(ubg < thr))) {
+              if (AUDIT) {  // every cell of a dropped group must lose
+                for (int u = 0; u < U; ++u) {
+                  const Rec4<D> R = rec[kb + kk + u];
+                  const D v = add_rn<D>(
+                      screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
+                  if (!((double)v < (double)thr)) ++nviol;
+                }
+              }
+              continue;
+            }
+          }
           float A[U], B[U], W[U];
           bool gt = false;
 #pragma unroll
@@ -449,7 +475,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     }
     if (has_next) {
       sbuf[(s + 1) & 1][tid] = nx;
-      if (FRONTIER) stage_max(nx.w, (s + 1) & 1);
+      if (FRONTIER || GROUPB) stage_max(nx.w, (s + 1) & 1);
     }
   }
   if (i < g.nrows) {
