@@ -177,7 +177,7 @@ struct LastLevelLaunch {
 template <typename D>
 struct ScreenLaunch {
   using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*, const int*);
-  using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, D*);
+  using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, float4*, D*);
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
 #define PS_PICK(DI, RPV)                                                             \
@@ -439,7 +439,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         PS_TRY(ensure(ctx, ctx->recf, 2 * R * rec_stride * sizeof(float4)));
         recf[0] = (float4*)ctx->recf.p;
         recf[1] = recf[0] + R * rec_stride;
-        ps::build_recf_kernel<<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(n, L, rec_stride, rec0, recf[0], recf[1]);
+        ps::build_recf_kernel<<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(n, rec_stride, rec0, recf[0], recf[1]);
         ctx->launches++;
       } else {
         recf[0] = (float4*)rec0;
@@ -453,7 +453,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     }
     ps::level1_prefix_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, rec_stride, p.dist, rp, rec0,
                                                                       d_ms + n, d_ns + n, table_stride, rec1,
-                                                                      screen ? (float*)recf[1] : nullptr);
+                                                                      (screen && sizeof(D) == 8) ? (float*)recf[1] : nullptr);
   }
   ctx->launches++;
   PS_TRY(mark(ctx, &e_pre));
@@ -500,7 +500,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       }
       if (screen) {
         // row lower bounds from a few exactly evaluated cells, then the screened tiles
-        fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, d_lb);
+        fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb);
         fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt,
                                                  (const int*)ctx->scalar.p);
         ctx->launches++;
@@ -511,7 +511,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (timed) PS_TRY(mark(ctx, &e1));
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
         g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
-        screen ? (float*)recf[j & 1] : nullptr);
+        (screen && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr);
     ctx->launches += 2;
     if (timed) {
       lev_ev.push_back({e0, e1});

@@ -193,20 +193,36 @@ __global__ void screen_sorted_kernel(int n, const D* __restrict__ as, const D* _
   if (!(k0 <= k1)) atomicOr(flag, 1);
 }
 
-// double only: float screening records {lx, ly, -, pm}: prefix sums relative to the start of the k-chunk they fall
-// in (chunk of k = (k-1)/L, origin cL), so that float range sums carry a RELATIVE error (header).  pm is written by
-// the level kernels (level1_prefix_kernel / combine_kernel).
-__global__ void build_recf_kernel(int n, int L, long long rec_stride, const Rec4<double>* __restrict__ rec,
+// Float screening records, one float4 per k, staged by the level kernel:
+//   double: a separate array {lx, ly, gmax, pm}: prefix sums RELATIVE to the start of the 128-block k falls in
+//           (origin o(k) = 128 floor((k-1)/128); a stage of the level kernel is exactly one block), so that float range
+//           sums carry a relative error (header); pm = screen_pm(prev[k]) is written by level1_prefix_kernel /
+//           combine_kernel.
+//   float : the level records themselves {Px, Py, p, gmax}; pm = p + 2^-20 |p| is formed on the fly.
+// gmax (screen_lb_kernel, once per level) is kept in the LAST record of every aligned group of 8 (k = 8m+8): the
+// largest pm of k = 8m+1 .. 8m+8.
+constexpr int SCR_BLOCK = 128;
+__global__ void build_recf_kernel(int n, long long rec_stride, const Rec4<double>* __restrict__ rec,
                                   float4* __restrict__ recf0, float4* __restrict__ recf1) {
   const int inst = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > n) return;
   rec += inst * rec_stride;
-  const int kc = (k > 0) ? ((k - 1) / L) * L : 0;
-  const Rec4<double> r = rec[k], o = rec[kc];
-  const float4 f = make_float4(__double2float_rn(r.x - o.x), __double2float_rn(r.y - o.y), 0.f, 0.f);
+  const int o = (k > 0) ? ((k - 1) / SCR_BLOCK) * SCR_BLOCK : 0;
+  const Rec4<double> r = rec[k], q = rec[o];
+  const float4 f = make_float4(__double2float_rn(r.x - q.x), __double2float_rn(r.y - q.y), 0.f, 0.f);
   recf0[inst * rec_stride + k] = f;
   recf1[inst * rec_stride + k] = f;
+}
+
+template <typename D>
+__device__ __forceinline__ float screen_pm_of(const float4 r) {
+  if (sizeof(D) == 8) return r.w;
+  return fmaf(fabsf(r.z), 9.5367431640625e-07f, r.z);
+}
+template <typename D>
+__device__ __forceinline__ float screen_gmax_of(const float4 r) {
+  return (sizeof(D) == 8) ? r.z : r.w;
 }
 
 template <typename D, int DIST, bool RP, bool LOGTAB>
@@ -225,17 +241,28 @@ __device__ __forceinline__ D screen_exact_score(D A, D B, const GlogEntry* s_log
 }
 
 // ---------------------------------------------------------------------------------------------
-// Lower bound of every row's maximum: the best of <= 2*64 EXACTLY evaluated cells of the row (a coarse sweep over
-// the row's k range, then a finer one around the best coarse sample).  Any evaluated cell is a valid bound; the
-// sampling only decides how tight it is (on C3 the best sample is within 1 of the maximum).
+// Per level, before the tiles: (1) a lower bound of every row's maximum = the best of <= 2*64 EXACTLY evaluated cells
+// of the row (a coarse sweep over the row's k range, then a finer one around the best coarse sample).  Any evaluated
+// cell is a valid bound; the sampling only decides how tight it is (on C3 the best sample is within 1 of the maximum).
+// (2) the group maxima of pm (one thread per aligned group of 8 records).
 // ---------------------------------------------------------------------------------------------
 template <typename D, int DIST, bool RP>
 __global__ void __launch_bounds__(128)
-screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, D* __restrict__ LB) {
+screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ recf, D* __restrict__ LB) {
   const int inst = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nrows) return;
   rec += (long long)inst * g.rec_stride;
+  recf += (long long)inst * g.rec_stride;
+  if ((i & 7) == 0 && i + 8 <= g.n) {
+    float m = screen_pm_of<D>(recf[i + 1]);
+#pragma unroll
+    for (int q = 2; q <= 8; ++q) m = fmaxf(m, screen_pm_of<D>(recf[i + q]));
+    if (sizeof(D) == 8)
+      recf[i + 8].z = m;
+    else
+      recf[i + 8].w = m;
+  }
   const D Xi = rec[i].x, Yi = rec[i].y;
   const int k0 = i + 1, k1 = g.kmax;
   const int len = k1 - k0 + 1;
@@ -263,30 +290,34 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, D* __restrict__ LB) {
 
 // ---------------------------------------------------------------------------------------------
 // One (row block, k-chunk) tile of one level, screened.  Same tiling, launch order and partial/combine protocol as
-// level_tile_kernel.  counters[0] += warp-cells evaluated exactly, counters[1] += audit violations (ub < exact value).
+// level_tile_kernel; a stage = one 128-block of k.  Three tiers, cheapest first:
+//   stage  (mult-clust scores) the stage's last cell has A <= B for every row of the warp: S = 0 on the whole stage,
+//          v = prev[k]; dropped if the largest pm of the stage is below every lane's threshold;
+//   group  (scores monotone in k) ONE bound per 8 cells: S(i,k) <= S(i,k_last), pm[k] <= gmax;
+//   cell   one bound per cell, 8 independent chains, one vote; a group with a survivor is evaluated exactly.
+// Monotonicity needs ascending priorities (dev_flags[1] == 0, screen_sorted_kernel).
+// counters[0] += warp-cells evaluated exactly, counters[1] += audit violations (a dropped cell that does not lose).
 // ---------------------------------------------------------------------------------------------
 template <typename D, int DIST, bool RP, bool AUDIT, int BR>
 __global__ void __launch_bounds__(BR)
 level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* __restrict__ recf,
                          const D* __restrict__ LB, D* __restrict__ part_val, int* __restrict__ part_arg,
                          unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags) {
+  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
   constexpr int BK = BR;
+  constexpr int U = 8;  // cells per group
   constexpr bool DBL = (sizeof(D) == 8);
   constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;  // scores that are 0 unless A > B
-  __shared__ float4 sbuf[2][BK];
-  __shared__ float s_pmax[2][BR / 32];  // per stage and warp: max of pm over the records that warp staged
-  constexpr int U = 8;                  // cells per group
-  __shared__ float s_gmax[2][BK / U];   // per stage and group of U consecutive k: max of pm
   // Scores that never decrease when a row's range is extended to the right (priorities ascending, a > 0): with
   // r = a_k/b_k >= q = A/B,  dS/db = r ln q + 1 - q >= q ln q + 1 - q >= 0 (Poisson mult-clust, q > 1; S = 0 below),
   // (q-1) r - (q^2-1)/2 >= (q-1)^2/2 (Gaussian mult-clust), 2 q r - q^2 >= q^2 (A^2/B, A^2/2B).  Poisson risk-part
-  // (A ln(A/B), decreasing while q < 1/e) is not.  For these, ONE bound at the last cell of a group with the group's
-  // largest pm covers every cell of the group.
+  // (A ln(A/B), decreasing while q < 1/e) is not.
   constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
+  __shared__ float4 sbuf[2][BK];
+  __shared__ float s_pmax[2][BR / 32];  // per stage and warp: largest pm among the records that warp staged
   constexpr bool kLogTab = DBL && (DIST == DIST_POISSON);
   __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
   if (kLogTab) {
-    static_assert(BR >= 128, "one table entry per thread");
     if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
   }
 
@@ -305,25 +336,25 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
   const int i = i0 + tid;
   const int k_lo = max(c * g.L + 1, i0 + 1);
   const int k_hi = min((c + 1) * g.L, g.kmax);
-  const bool diag = (c == rb / g.G);
 
   const int il = min(i, g.n - 1);
   const D Xi = rec[il].x, Yi = rec[il].y;
-  float bx, by;  // At = recf[k].x + bx
-  if (DBL) {
-    const Rec4<D> o = rec[c * g.L];
-    bx = __double2float_rn((double)o.x - (double)Xi);
-    by = __double2float_rn((double)o.y - (double)Yi);
-  } else {
-    bx = -(float)Xi;
-    by = -(float)Yi;
-  }
+  float bx = -(float)Xi, by = -(float)Yi;  // float: At = Px[k] - Px[i], exact.  double: set per stage
   D best = Lim<D>::lowest();
   int arg = -1;
   float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
   unsigned int nexact = 0, nviol = 0;
+  const bool mono = (FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0);
 
-  // one cell: bound, vote, exact evaluation of the whole warp if any lane survives
+  auto exact_at = [&](const int k) -> D {
+    const Rec4<D> R = rec[k];
+    return add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
+  };
+  // audit: a dropped cell must lose against the threshold it was dropped with
+  auto audit_dropped = [&](const int k, const bool valid) {
+    if (valid && !((double)exact_at(k) < (double)thr)) ++nviol;
+  };
+  // one cell on its own: bound, vote, exact evaluation of the warp if any lane survives (diagonal and ragged stages)
   auto cell = [&](const int k, const float4 r, const bool valid, auto from_double) {
     float A, B;
     if constexpr (decltype(from_double)::value) {
@@ -334,45 +365,40 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
       A = __fadd_rn(r.x, bx);
       B = __fadd_rn(r.y, by);
     }
-    const float ub = ScreenUB<DIST, RP>::eval(A, B, r.w);
+    const float ub = ScreenUB<DIST, RP>::eval(A, B, screen_pm_of<D>(r));
     const bool pass = valid && !(ub < thr);
-    if (AUDIT || __any_sync(0xffffffffu, pass)) {
-      const Rec4<D> R = rec[k];
-      const D v = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
-      if (AUDIT) {
-        if (valid && (double)ub < (double)v) ++nviol;
-        if (!__any_sync(0xffffffffu, pass)) return;  // audit only: keep the screened kernel's own decisions
-      }
+    if (__any_sync(0xffffffffu, pass)) {
+      const D v = exact_at(k);
+      if (AUDIT && valid && (double)ub < (double)v) ++nviol;
       ++nexact;
       if (valid && v > best) {
         best = v;
         arg = k;
         thr = fmaxf(thr, screen_rd<D>(best));
       }
+    } else if (AUDIT) {
+      audit_dropped(k, valid);
     }
   };
   using T_ = std::integral_constant<bool, true>;
   using F_ = std::integral_constant<bool, false>;
+  // the largest pm of a stage from the group maxima held by the records with (k-1) % 8 == 7, i.e. lanes 7, 15, 23, 31
+  auto stage_max = [&](const float4 r, const int buf) {
+    float w = ((tid & 7) == 7) ? screen_gmax_of<D>(r) : -3.402823466e+38f;
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 8));
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 16));
+    if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
+  };
 
   const int nk = k_hi - k_lo + 1;
   const int nstages = (nk + BK - 1) / BK;
-  // mult-clust scores, priorities verified ascending (dev_flags[1] == 0): A/B of a row grows with k, so a stage whose
-  // LAST cell has A <= B (1 - 2^-18) for every row of the warp lies entirely on the S = 0 side of the frontier; there
-  // v = prev[k] exactly, and if the largest pm of the stage is below every lane's threshold the warp skips the stage.
-  // (Margin: the float sums are within 3u, the sorted keys fl(a/b) within 2 u_D of the true ratios.)
-  const bool mono = (FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0);
-  auto stage_max = [&](float w, int buf) {
-    static_assert(U == 8, "group maxima are formed over 8 adjacent lanes");
-    for (int o = 1; o < 8; o <<= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
-    if ((tid & 7) == 0) s_gmax[buf][tid >> 3] = w;
-    for (int o = 8; o < 32; o <<= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
-    if ((tid & 31) == 0) s_pmax[buf][tid >> 5] = w;
-  };
+  Rec4<D> onx;  // double: record at the origin of the next stage (k = kb - 1)
   {
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
     sbuf[0][tid] = r;
-    if (FRONTIER || GROUPB) stage_max(r.w, 0);
+    if (FRONTIER) stage_max(r, 0);
+    if (DBL) onx = rec[k_lo - 1];
   }
   for (int s = 0; s < nstages; ++s) {
     __syncthreads();
@@ -381,51 +407,51 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool has_next = (s + 1 < nstages);
     if (has_next && kn <= k_hi) nx = recf[kn];
+    if (DBL) {
+      // At = lx[k] + bx with bx = fl32(P[kb-1] - P[i]) >= 0 on every stage right of the diagonal
+      bx = __double2float_rn((double)onx.x - (double)Xi);
+      by = __double2float_rn((double)onx.y - (double)Yi);
+      if (has_next) onx = rec[kb + BK - 1];
+    }
     const int cnt = min(BK, k_hi - kb + 1);
     const float4* __restrict__ sb = sbuf[s & 1];
-    if (DBL && diag) {
-      // diagonal tile of the double kernel: chunk-relative float sums would cancel, convert the exact differences
-      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
-    } else if (kb > i0 + BR - 1) {
+    if (kb <= i0 + BR - 1) {
+      // diagonal stage: row i only sees k > i; the double kernel converts exact differences (kb - 1 = i0 <= i)
+      if (DBL)
+        for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
+      else
+        for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, F_{});
+    } else if (cnt < BK) {
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
+    } else {
       bool skip = false;
-      if (FRONTIER && cnt == BK && mono) {
+      if (FRONTIER && mono) {
         float pmx = s_pmax[s & 1][0];
 #pragma unroll
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
         const float4 re = sb[BK - 1];
         const float Ae = __fadd_rn(re.x, bx), Be = __fadd_rn(re.y, by);
+        // margin 2^-18: the float sums are within 3u, the sorted keys fl(a/b) within 2 u_D of the true ratios
         skip = __all_sync(0xffffffffu, (Ae <= Be * 0.999996185302734375f) && (pmx < thr));
       }
       if (skip) {
-        if (AUDIT) {  // audit: every cell of a skipped stage must indeed lose (exact value below the threshold)
-          for (int kk = 0; kk < BK; ++kk) {
-            const Rec4<D> R = rec[kb + kk];
-            const D v = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
-            if (!((double)v < (double)thr)) ++nviol;
-          }
-        }
-      } else if (cnt == BK) {
-        // Interior stage.  Cells are bounded in groups of U: the U chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA
-        // pipe operations) are independent, so their latencies overlap, and one vote decides for the whole group;
-        // only a group with a surviving cell (near the row maximum) goes through the per-cell path.
+        if (AUDIT)
+          for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true);
+      } else {
 #pragma unroll 1
         for (int kk = 0; kk < BK; kk += U) {
           if (GROUPB && mono) {
-            // tier 1: one bound for the whole group (monotone scores): S(i,k) <= S(i,k_last), pm[k] <= group max
             const float4 re = sb[kk + U - 1];
-            const float ubg = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), s_gmax[s & 1][kk / U]);
+            const float ubg =
+                ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), screen_gmax_of<D>(re));
             if (!__any_sync(0xffffffffu, !(ubg < thr))) {
-              if (AUDIT) {  // every cell of a dropped group must lose
-                for (int u = 0; u < U; ++u) {
-                  const Rec4<D> R = rec[kb + kk + u];
-                  const D v = add_rn<D>(
-                      screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
-                  if (!((double)v < (double)thr)) ++nviol;
-                }
-              }
+              if (AUDIT)
+                for (int u = 0; u < U; ++u) audit_dropped(kb + kk + u, true);
               continue;
             }
           }
+          // U independent chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA-pipe operations): their latencies overlap,
+          // one vote decides for the group
           float A[U], B[U], W[U];
           bool gt = false;
 #pragma unroll
@@ -433,12 +459,12 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
             const float4 r = sb[kk + u];
             A[u] = __fadd_rn(r.x, bx);
             B[u] = __fadd_rn(r.y, by);
-            W[u] = r.w;
+            W[u] = screen_pm_of<D>(r);
             if (FRONTIER) gt |= A[u] > B[u];
           }
           bool alive = false;
           if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
-            // the whole 32 x U patch is on the S = 0 side of the A = B frontier (mult-clust scores)
+            // the whole 32 x U patch is on the S = 0 side of the A = B frontier
 #pragma unroll
             for (int u = 0; u < U; ++u) alive |= !(fmaf(B[u], SCR_TINY, W[u]) < thr);
           } else {
@@ -453,10 +479,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
             // evaluate all U exactly (independent chains, loads issued together), then take them in ascending k
             D v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const Rec4<D> R = rec[kb + kk + u];
-              v[u] = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
-            }
+            for (int u = 0; u < U; ++u) v[u] = exact_at(kb + kk + u);
 #pragma unroll
             for (int u = 0; u < U; ++u)
               if (v[u] > best) {
@@ -467,15 +490,11 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
             nexact += U;
           }
         }
-      } else {
-        for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
       }
-    } else {
-      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, F_{});
     }
     if (has_next) {
       sbuf[(s + 1) & 1][tid] = nx;
-      if (FRONTIER || GROUPB) stage_max(nx.w, (s + 1) & 1);
+      if (FRONTIER) stage_max(nx, (s + 1) & 1);
     }
   }
   if (i < g.nrows) {
