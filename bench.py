@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--sum-mode", default="running", choices=["running", "prefix"])
     ap.add_argument("--no-extras", action="store_true", help="skip variants, replicas and the CPU baseline")
     ap.add_argument("--skip-peaks", action="store_true", help="do not run the pipe-peak microbenchmark (ncu runs)")
+    ap.add_argument("--exhaustive", action="store_true",
+                    help="headline on the exhaustive level kernel (every cell evaluated with the reference's arithmetic) "
+                         "instead of the default screened kernel; both produce identical tables")
     ap.add_argument("--chunk-len", type=int, default=0, help="tuning: k-chunk length of the level tiles (0 = library default)")
     ap.add_argument("--sharded-n", type=int, default=200000, help="N>1 only: size of the row-sharded instance")
     ap.add_argument("--sharded-T", type=int, default=8)
@@ -241,7 +244,7 @@ def main():
         flush.add_(1)
         torch.cuda.synchronize()
 
-    def run_variant(dtype_name, steps, warmup, with_e2e=True, sm=sum_mode):
+    def run_variant(dtype_name, steps, warmup, with_e2e=True, sm=sum_mode, screen=0):
         npdt = np.float64 if dtype_name == "f64" else np.float32
         tdt = torch.float64 if dtype_name == "f64" else torch.float32
         # every rank solves its own instance of the workload (rank-dependent seed)
@@ -259,17 +262,17 @@ def main():
         def step_resident():
             ctx.solve_device(a_d.data_ptr(), b_d.data_ptr(), n, T, dist_id, rp, npdt, sum_mode=sm,
                              d_perm_out=perm_d.data_ptr(), d_bounds=bounds_d.data_ptr(),
-                             d_scores=scores_d.data_ptr(), chunk_len=args.chunk_len)
+                             d_scores=scores_d.data_ptr(), chunk_len=args.chunk_len, screen=screen)
 
         def step_e2e():
             ctx.solve_into(a_pin.numpy(), b_pin.numpy(), T, dist_id, rp, npdt, perm_out=perm_pin.numpy(),
                            bounds_out=bounds_pin.numpy(), scores_out=scores_pin.numpy(), sum_mode=sm,
-                           chunk_len=args.chunk_len)
+                           chunk_len=args.chunk_len, screen=screen)
 
         for _ in range(warmup):
             step_resident()
         # ---- resident, device-timed
-        dev_ms, lev_ms, lev_cells, launches = [], [], [], 0
+        dev_ms, lev_ms, lev_cells, launches, exact_cells, screened = [], [], [], 0, 0, 0
         stage = {"sort_scan_ms": 0.0, "prepass_ms": 0.0, "levels_ms": 0.0, "backtrace_ms": 0.0}
         barrier()
         w0 = time.perf_counter()
@@ -281,6 +284,8 @@ def main():
             lev_ms += tm["level_ms"]
             lev_cells += tm["level_cells"]
             launches += tm["kernel_launches"]
+            exact_cells += tm["screen_exact_cells"]
+            screened = tm["screen_used"]
             for k in stage:
                 stage[k] += tm[k] / steps
         barrier()
@@ -290,7 +295,8 @@ def main():
                "value": world * synth.nominal_cells(n, T) / (ms * 1e-3),
                "actual_cells_per_s": world * synth.actual_cells(n, T) / (ms * 1e-3),
                "level_ms_sum": float(np.sum(lev_ms)), "level_cells_sum": float(np.sum(lev_cells)),
-               "level_launches": len(lev_ms), "stage_ms": stage,
+               "level_launches": len(lev_ms), "stage_ms": stage, "screen_used": int(screened),
+               "exact_cells": float(exact_cells),
                "bounds": bounds_d.cpu().numpy().tolist()}
         # fraction of (i,k) cells past the A = B frontier (only those evaluate division + log in the mult-clust
         # scores, exactly like the reference's ternary): Monte-Carlo estimate on the sorted inputs
@@ -320,7 +326,7 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    main_res = run_variant(args.dtype, args.steps, args.warmup)
+    main_res = run_variant(args.dtype, args.steps, args.warmup, screen=1 if args.exhaustive else 0)
     clocks = sampler.stop()
 
     line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -338,49 +344,83 @@ def main():
     peaks = measured_peaks() if (rank == 0 and not args.skip_peaks) else None
     w = 8 if args.dtype == "f64" else 4
     flops_full = ALG_FLOPS_PER_CELL[(dist_id, rp)]
-    # mult-clust Poisson/Gaussian: a cell with A <= B scores 0 by definition (score_impl.hpp:385-388) and needs only
-    # the two sums, the compare, the add of prev and the max compare = 5 flops; weight by the measured fraction
-    p_gt = main_res["frac_cells_A_gt_B"] if (not rp and dist_id != 2) else 1.0
-    flops_cell = 5.0 + (flops_full - 5.0) * p_gt
-    lev_s = main_res["level_ms_sum"] * 1e-3
-    achieved = main_res["level_cells_sum"] * flops_cell / lev_s / 1e12
-    if peaks:
-        peak = (peaks["dadd_ops"] if args.dtype == "f64" else peaks["fadd_ops"]) / 1e12
-        peak_src = "measured by tools/peaks.cu on this device: non-fused FP add/mul issue rate (parity forbids FMA contraction of the score)"
-    else:
-        peak = (148 * 64 if args.dtype == "f64" else 148 * 128) * 1.965e9 / 1e12
-        peak_src = "fallback: lanes x 1.965 GHz (ps_peaks binary missing)"
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "level_kernel_summary.json")
-    if os.path.exists(prof):
-        try:
-            traffic = json.load(open(prof)).get(args.dtype, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    avg_launch_ms = main_res["level_ms_sum"] / max(1, main_res["level_launches"])
     hbm_peak = 6554.6
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    alg_bytes_per_launch = ALG_HBM_BYTES_PER_ROW(w) * n
-    line["roofline"] = {
-        "kernel": "level_tile_kernel", "bound": "fp64_pipe" if args.dtype == "f64" else "fp32_issue",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-        "alg_flops_per_cell": flops_cell, "alg_flops_per_evaluated_cell": flops_full,
-        "frac_cells_A_gt_B": p_gt, "cells_per_launch_avg": main_res["level_cells_sum"] / max(
-            1, main_res["level_launches"]), "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
-        "share_of_step": main_res["level_ms_sum"] / (args.steps * main_res["ms_per_step"]),
-        "sfu": {"ops_per_cell": 1, "what": "one MUFU reciprocal per cell (division seed); log is table-driven, no MUFU",
-                "achieved_tops": main_res["level_cells_sum"] / lev_s / 1e12,
-                "peak_tops": (peaks["mufu_lg2_ops"] / 1e12) if peaks else 148 * 16 * 1.965e9 / 1e12,
-                "frac": (main_res["level_cells_sum"] / lev_s) / (peaks["mufu_lg2_ops"] if peaks else 148 * 16 * 1.965e9)},
-        "hbm": {"alg_bytes_per_launch": alg_bytes_per_launch,
-                "achieved_gbs": alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                "note": "not HBM-bound: algorithmic traffic is (4w+4)n bytes per level"},
-        "measured_pipe_peaks": peaks}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "level_kernel_summary.json")))
+    except Exception:
+        prof = {}
+
+    def roofline_of(res, dtype_name):
+        """Roofline object of the level kernel a run used (the dominant kernel: > 90 % of a step).
+        achieved = ALGORITHMIC flops of the level launches / their CUDA-event time.  The algorithmic count charges
+        every (i,k) cell: 10 flops for a Poisson mult-clust cell with A > B, 5 for a cell with A <= B whose score is
+        0 by definition (score_impl.hpp:385-388) -- SURVEY.md 8d."""
+        screened = bool(res["screen_used"])
+        p_gt = res["frac_cells_A_gt_B"] if (not rp and dist_id != 2) else 1.0
+        flops_cell = 5.0 + (flops_full - 5.0) * p_gt
+        lev_s = res["level_ms_sum"] * 1e-3
+        achieved = res["level_cells_sum"] * flops_cell / lev_s / 1e12
+        # exhaustive kernel: arithmetic in the data type; screened kernel: float bounds for all cells, data type only
+        # for the ~1 % of cells that survive
+        pipe64 = (dtype_name == "f64") and not screened
+        if peaks:
+            peak = (peaks["dadd_ops"] if pipe64 else peaks["fadd_ops"]) / 1e12
+            peak_src = ("measured by tools/peaks.cu on this device: non-fused FP add/mul issue rate "
+                        "(parity forbids FMA contraction of the score)")
+        else:
+            peak = (148 * 64 if pipe64 else 148 * 128) * 1.965e9 / 1e12
+            peak_src = "fallback: lanes x 1.965 GHz (ps_peaks binary missing)"
+        kname = "level_tile_screen_kernel" if screened else "level_tile_kernel"
+        pk = prof.get(("screen_" if screened else "") + dtype_name, {})
+        launches = max(1, res["level_launches"])
+        avg_launch_ms = res["level_ms_sum"] / launches
+        alg_bytes_per_launch = ALG_HBM_BYTES_PER_ROW(8 if dtype_name == "f64" else 4) * n
+        mufu_peak = peaks["mufu_lg2_ops"] if peaks else 148 * 16 * 1.965e9
+        r = {"kernel": kname, "bound": "fp64_pipe" if pipe64 else "fp32_issue",
+             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+             "traffic": pk.get("dram_bytes_per_launch"),
+             "alg_flops_per_cell": flops_cell, "alg_flops_per_evaluated_cell": flops_full,
+             "frac_cells_A_gt_B": p_gt, "cells_per_launch_avg": res["level_cells_sum"] / launches,
+             "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
+             "share_of_step": res["level_ms_sum"] / (res["steps"] * res["ms_per_step"]),
+             "hbm": {"alg_bytes_per_launch": alg_bytes_per_launch,
+                     "achieved_gbs": alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                     "note": "not HBM-bound: algorithmic traffic is (4w+4)n bytes per level"}}
+        if screened:
+            r["screen"] = {
+                "exact_cell_fraction": res["exact_cells"] / max(1.0, res["level_cells_sum"]),
+                "executed_warp_instructions_per_cell": pk.get("warp_instructions_per_cell"),
+                "issue_slot_utilisation": pk.get("issue_active_pct"),
+                "note": "cells are bounded in float, singly or 8 / 128 at a time where the score is monotone in k; "
+                        "only cells that can still be the row maximum are evaluated with the reference's arithmetic. "
+                        "The algorithmic count still charges every cell, so frac may exceed 1: the kernel's own "
+                        "ceiling is instruction issue (see issue_slot_utilisation from ncu, profiles/)"}
+        else:
+            r["sfu"] = {"ops_per_cell": 1,
+                        "what": "one MUFU reciprocal per evaluated cell (division seed); log is table-driven, no MUFU",
+                        "achieved_tops": res["level_cells_sum"] / lev_s / 1e12, "peak_tops": mufu_peak / 1e12,
+                        "frac": (res["level_cells_sum"] / lev_s) / mufu_peak}
+        return r
+
+    main_res["steps"] = args.steps
+    line["roofline"] = roofline_of(main_res, args.dtype)
+    line["roofline"]["measured_pipe_peaks"] = peaks
+    line["config"]["level_kernel"] = ("screened (float bounds, exact arithmetic for surviving cells; identical tables)"
+                                      if main_res["screen_used"] else "exhaustive")
 
     if not args.no_extras:
+        # the same workload on the other level kernel (identical tables): exhaustive = every cell evaluated with the
+        # reference's arithmetic, the kernel whose pipe roofline is the classical one
+        ex_steps = max(2, args.steps // 2)
+        vx = run_variant(args.dtype, ex_steps, 3, with_e2e=True, screen=0 if args.exhaustive else 1)
+        vx["steps"] = ex_steps
+        line["other_level_kernel"] = {"value": vx["value"], "ms_per_step": vx["ms_per_step"], "e2e": vx["e2e"],
+                                      "same_partition": vx["bounds"] == main_res["bounds"],
+                                      "roofline": roofline_of(vx, args.dtype)}
         other = "f32" if args.dtype == "f64" else "f64"
         v = run_variant(other, max(2, args.steps // 2), 3, with_e2e=True)
         line["variants"] = {other: {"value": v["value"], "ms_per_step": v["ms_per_step"], "e2e": v["e2e"],

@@ -350,7 +350,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   const bool want_fast = running && p.no_fast_math != 1;
   // screened levels (screen.cuh): worth it once a level has enough cells to amortise the extra launch
   const bool want_screen = want_fast && p.screen != 1 && p.no_fast_math == 0 && std::min(p.T, n) >= 3 && n >= 512 &&
-                           (long long)n * R >= 8192;
+                           (long long)n * R >= 6000;  // measured crossover (tools/screen_threshold.py)
   if (want_fast) {
     PS_TRY(ensure(ctx, ctx->scalar, 64));
     PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, 2 * sizeof(int), st));  // [0] range/exactness, [1] sortedness
