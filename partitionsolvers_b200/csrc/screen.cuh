@@ -291,9 +291,8 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ r
 // ---------------------------------------------------------------------------------------------
 // One (row block, k-chunk) tile of one level, screened.  Same tiling, launch order and partial/combine protocol as
 // level_tile_kernel; a stage = one 128-block of k.  Three tiers, cheapest first:
-//   stage  (mult-clust scores) the stage's last cell has A <= B for every row of the warp: S = 0 on the whole stage,
-//          v = prev[k]; dropped if the largest pm of the stage is below every lane's threshold;
-//   group  (scores monotone in k) ONE bound per 8 cells: S(i,k) <= S(i,k_last), pm[k] <= gmax;
+//   stage  (scores monotone in k) ONE bound per 128 cells: S(i,k) <= S(i,k_last), pm[k] <= largest pm of the stage;
+//   group  (same) one bound per 8 cells, with the group's largest pm;
 //   cell   one bound per cell, 8 independent chains, one vote; a group with a survivor is evaluated exactly.
 // Monotonicity needs ascending priorities (dev_flags[1] == 0, screen_sorted_kernel).
 // counters[0] += warp-cells evaluated exactly, counters[1] += audit violations (a dropped cell that does not lose).
@@ -397,7 +396,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
     sbuf[0][tid] = r;
-    if (FRONTIER) stage_max(r, 0);
+    if (GROUPB) stage_max(r, 0);
     if (DBL) onx = rec[k_lo - 1];
   }
   for (int s = 0; s < nstages; ++s) {
@@ -425,14 +424,14 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
       for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
     } else {
       bool skip = false;
-      if (FRONTIER && mono) {
+      if (GROUPB && mono) {
+        // stage tier: the bound at the stage's LAST cell with the stage's largest pm covers all 128 cells
         float pmx = s_pmax[s & 1][0];
 #pragma unroll
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
         const float4 re = sb[BK - 1];
-        const float Ae = __fadd_rn(re.x, bx), Be = __fadd_rn(re.y, by);
-        // margin 2^-18: the float sums are within 3u, the sorted keys fl(a/b) within 2 u_D of the true ratios
-        skip = __all_sync(0xffffffffu, (Ae <= Be * 0.999996185302734375f) && (pmx < thr));
+        const float ubs = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), pmx);
+        skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
       if (skip) {
         if (AUDIT)
@@ -494,7 +493,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     }
     if (has_next) {
       sbuf[(s + 1) & 1][tid] = nx;
-      if (FRONTIER) stage_max(nx, (s + 1) & 1);
+      if (GROUPB) stage_max(nx, (s + 1) & 1);
     }
   }
   if (i < g.nrows) {
