@@ -38,7 +38,7 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map;
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax;
   int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
@@ -176,8 +176,9 @@ struct LastLevelLaunch {
 
 template <typename D>
 struct ScreenLaunch {
-  using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*, const int*);
-  using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, float4*, D*);
+  using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*, const int*,
+                      const float*, int);
+  using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, float4*, D*, float*, int);
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
 #define PS_PICK(DI, RPV)                                                             \
@@ -412,7 +413,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // rows to fill the machine with such tiles; smaller instances keep 128-row tiles (more, finer work items)
   const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 &&
                       (long long)n * R >= 16384;
-  const int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
+  int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
+  // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);
+  // at most ~200 chunks so that the per-chunk partials stay small
+  if (screen && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
   const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
   const long long pstride = (long long)nch_alloc * n;
   PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
@@ -448,6 +452,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       ps::screen_sorted_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, d_as, d_bs, (int*)ctx->scalar.p + 1);
       ctx->launches++;
       PS_TRY(ensure(ctx, ctx->lb, (size_t)R * n * sizeof(D)));
+      PS_TRY(ensure(ctx, ctx->scr_bmax, (size_t)R * (n / ps::SCR_BLOCK + 2) * sizeof(float)));
       PS_TRY(ensure(ctx, ctx->scr_counters, 2 * sizeof(unsigned long long)));
       PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 2 * sizeof(unsigned long long), st));
     }
@@ -500,9 +505,11 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       }
       if (screen) {
         // row lower bounds from a few exactly evaluated cells, then the screened tiles
-        fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb);
+        fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, (float*)ctx->scr_bmax.p,
+                                                           n / ps::SCR_BLOCK + 2);
         fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt,
-                                                 (const int*)ctx->scalar.p);
+                                                 (const int*)ctx->scalar.p, (const float*)ctx->scr_bmax.p,
+                                                 n / ps::SCR_BLOCK + 2);
         ctx->launches++;
       } else {
         fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);

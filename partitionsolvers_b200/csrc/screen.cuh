@@ -248,12 +248,19 @@ __device__ __forceinline__ D screen_exact_score(D A, D B, const GlogEntry* s_log
 // ---------------------------------------------------------------------------------------------
 template <typename D, int DIST, bool RP>
 __global__ void __launch_bounds__(128)
-screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ recf, D* __restrict__ LB) {
+screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ recf, D* __restrict__ LB,
+                 float* __restrict__ bmax, int nblk) {
   const int inst = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nrows) return;
   rec += (long long)inst * g.rec_stride;
   recf += (long long)inst * g.rec_stride;
+  if ((i & (SCR_BLOCK - 1)) == 0) {  // largest pm of the 128-block k = i+1 .. i+128 (tile tier)
+    float m = -3.402823466e+38f;
+    const int ke = min(i + SCR_BLOCK, g.n);
+    for (int k = i + 1; k <= ke; ++k) m = fmaxf(m, screen_pm_of<D>(recf[k]));
+    bmax[(long long)inst * nblk + i / SCR_BLOCK] = m;
+  }
   if ((i & 7) == 0 && i + 8 <= g.n) {
     float m = screen_pm_of<D>(recf[i + 1]);
 #pragma unroll
@@ -290,7 +297,8 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ r
 
 // ---------------------------------------------------------------------------------------------
 // One (row block, k-chunk) tile of one level, screened.  Same tiling, launch order and partial/combine protocol as
-// level_tile_kernel; a stage = one 128-block of k.  Three tiers, cheapest first:
+// level_tile_kernel; a stage = one 128-block of k.  Four tiers, cheapest first:
+//   tile   (scores monotone in k) ONE bound for the whole tile, before anything is staged;
 //   stage  (scores monotone in k) ONE bound per 128 cells: S(i,k) <= S(i,k_last), pm[k] <= largest pm of the stage;
 //   group  (same) one bound per 8 cells, with the group's largest pm;
 //   cell   one bound per cell, 8 independent chains, one vote; a group with a survivor is evaluated exactly.
@@ -301,7 +309,8 @@ template <typename D, int DIST, bool RP, bool AUDIT, int BR>
 __global__ void __launch_bounds__(BR)
 level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* __restrict__ recf,
                          const D* __restrict__ LB, D* __restrict__ part_val, int* __restrict__ part_arg,
-                         unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags) {
+                         unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
+                         const float* __restrict__ bmax, int nblk) {
   static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
   constexpr int BK = BR;
   constexpr int U = 8;  // cells per group
@@ -389,6 +398,29 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
   };
 
+  if (GROUPB && mono) {
+    // tile tier: the bound at the tile's last cell with the largest pm of the tile's 128-blocks covers the whole tile
+    bmax += (long long)inst * nblk;
+    float tmax = -3.402823466e+38f;
+    for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
+    const Rec4<D> R = rec[k_hi];
+    const float At = DBL ? __double2float_rn((double)R.x - (double)Xi) : __fadd_rn((float)R.x, bx);
+    const float Bt = DBL ? __double2float_rn((double)R.y - (double)Yi) : __fadd_rn((float)R.y, by);
+    const bool lose = (i >= g.nrows) || (ScreenUB<DIST, RP>::eval(At, Bt, tmax) < thr);
+    if (__syncthreads_and(lose)) {
+      if (AUDIT)
+        for (int k = max(k_lo, i + 1); k <= k_hi; ++k) audit_dropped(k, i < g.nrows);
+      if (i < g.nrows) {
+        part_val[(long long)c * g.n + i] = best;
+        part_arg[(long long)c * g.n + i] = arg;
+      }
+      if (AUDIT && counters) {
+        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+      }
+      return;
+    }
+  }
   const int nk = k_hi - k_lo + 1;
   const int nstages = (nk + BK - 1) / BK;
   Rec4<D> onx;  // double: record at the origin of the next stage (k = kb - 1)
