@@ -192,8 +192,8 @@ def main():
                     help="headline on the exhaustive level kernel (every cell evaluated with the reference's arithmetic) "
                          "instead of the default screened kernel; both produce identical tables")
     ap.add_argument("--chunk-len", type=int, default=0, help="tuning: k-chunk length of the level tiles (0 = library default)")
-    ap.add_argument("--sharded-n", type=int, default=200000, help="N>1 only: size of the row-sharded instance")
-    ap.add_argument("--sharded-T", type=int, default=8)
+    ap.add_argument("--sharded-n", type=int, default=1000000, help="N>1 only: size of the row-sharded instance")
+    ap.add_argument("--sharded-T", type=int, default=32)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -182,6 +182,8 @@ ps_status ps_shard_level(ps_shard* s, int j, void* my_chunk_dev);
 /* split index next_start[j][i] (host lookup of one element; valid on the owning rank, else -2) */
 ps_status ps_shard_next_start(ps_shard* s, int j, int i, int* out);
 int ps_shard_owner(const ps_shard* s, int i);
+/* 1 if this shard's levels run the screened kernel (ps_problem.screen, csrc/screen.cuh) */
+int ps_shard_screened(const ps_shard* s);
 void ps_shard_destroy(ps_shard* s);
 
 #ifdef __cplusplus

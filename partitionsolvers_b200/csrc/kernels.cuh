@@ -618,6 +618,21 @@ level1_running_kernel(int n, int L, int nch_alloc, long long rec_stride, int dis
   if (shard_chunk) shard_chunk[blockIdx.x * BR + tid] = v;
 }
 
+// Sharded runs, prefix records: level 1 of the owned rows, in block-cyclic chunk order.
+template <typename D, int BR>
+__global__ void level1_prefix_shard_kernel(int n, int dist, int rp, const Rec4<D>* __restrict__ rec,
+                                           int* __restrict__ ns1, int rb_first, int rb_step,
+                                           D* __restrict__ shard_chunk) {
+  const int rb = rb_first + rb_step * blockIdx.x;
+  const int i = rb * BR + threadIdx.x;
+  D v = Lim<D>::lowest();
+  if (i < n) {
+    v = score_dyn<D>(dist, rp, sub_rn<D>(rec[n].x, rec[i].x), sub_rn<D>(rec[n].y, rec[i].y));
+    ns1[i] = n;
+  }
+  shard_chunk[blockIdx.x * BR + threadIdx.x] = v;
+}
+
 template <typename D>
 __global__ void level1_prefix_kernel(int n, long long rec_stride, int dist, int rp,
                                      const Rec4<D>* __restrict__ rec, D* __restrict__ ms1,
@@ -964,7 +979,8 @@ __global__ void eval_log_kernel(long long n, const D* __restrict__ x, D* __restr
 // and into the p field of the next level's records.
 template <typename D, int BR>
 __global__ void shard_unpermute_kernel(int n, int world, int chunk, const D* __restrict__ gathered,
-                                       Rec4<D>* __restrict__ rec_next, D* __restrict__ level_nat) {
+                                       Rec4<D>* __restrict__ rec_next, D* __restrict__ level_nat,
+                                       float* __restrict__ pm_next) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)world * chunk) return;
   const int r = (int)(g / chunk);
@@ -974,6 +990,7 @@ __global__ void shard_unpermute_kernel(int n, int world, int chunk, const D* __r
   if (i < n) {
     const D v = gathered[g];
     rec_next[i].p = v;
+    if (pm_next) pm_next[(long long)i * 4 + 3] = screen_pm<D>(v);
     if (level_nat) level_nat[i] = v;
   }
 }

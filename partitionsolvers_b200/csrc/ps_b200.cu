@@ -61,6 +61,14 @@ struct ps_shard {
   int* ns = nullptr;     // [T+1][n] (owned rows filled)
   int cur = 0;           // record buffer holding the previous level in its p field
   int fast = 0;          // inputs passed the safe-range precheck (math_fast.cuh)
+  int screen = 0;        // levels run the screened kernel (screen.cuh): prefix records, float screening records
+  float4* recf = nullptr;   // double only: [2][n+1] screening records
+  void* lb = nullptr;       // [n] row lower bounds of the level in flight
+  float* bmax = nullptr;    // [n/128 + 2] block maxima of pm
+  int* dflags = nullptr;    // [2] device flags: range/exactness, sortedness
+  int2* tile_map = nullptr;
+  int map_key[4] = {-1, -1, -1, -1};
+  unsigned long long* counters = nullptr;
 };
 
 namespace {
@@ -715,35 +723,63 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   s->owned_blocks = nrb_total > rank ? (nrb_total - rank + world - 1) / world : 0;
   s->chunk_rows = cdiv(nrb_total, world) * BR;  // same on every rank
   const long long rec_stride = (long long)n + 1;
-  const long long pstride = (long long)s->nch_alloc * n;
   cudaStream_t st = ctx->stream;
   PS_CUDA(ctx, cudaMalloc(&s->rec, 2 * rec_stride * sizeof(ps::Rec4<D>)));
-  PS_CUDA(ctx, cudaMalloc(&s->part_val, pstride * sizeof(D)));
-  PS_CUDA(ctx, cudaMalloc((void**)&s->part_arg, pstride * sizeof(int)));
   PS_CUDA(ctx, cudaMalloc((void**)&s->ns, (size_t)(Tc + 1) * n * sizeof(int)));
   PS_CUDA(ctx, cudaMemsetAsync(s->ns, 0xff, (size_t)(Tc + 1) * n * sizeof(int), st));
-  const int running = (pp->sum_mode == PS_SUM_RUNNING);
+  int running = (pp->sum_mode == PS_SUM_RUNNING);
+  if (running && pp->no_fast_math != 1) {
+    // safe range, exact summability and sortedness of the (already sorted) inputs -> fast math / screened levels
+    PS_CUDA(ctx, cudaMalloc((void**)&s->dflags, 2 * sizeof(int)));
+    PS_CUDA(ctx, cudaMemsetAsync(s->dflags, 0, 2 * sizeof(int), st));
+    ps::range_check_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, a_s, b_s, s->dflags);
+    const bool want_screen = pp->screen != 1 && pp->screen != 2 && pp->no_fast_math == 0 && Tc >= 3 && n >= 6000;
+    if (want_screen) {
+      PS_TRY(ensure(ctx, ctx->scr_stats, sizeof(ps::ScreenStats)));
+      ps::ScreenStats* d_st = (ps::ScreenStats*)ctx->scr_stats.p;
+      ps::screen_stats_init_kernel<<<1, 32, 0, st>>>(1, d_st);
+      ps::screen_stats_kernel<D><<<dim3(std::max(1, std::min(cdiv(n, 1024), 2048)), 1), 256, 0, st>>>(n, a_s, b_s, d_st);
+      ps::screen_decide_kernel<D><<<1, 32, 0, st>>>(1, d_st, s->dflags);
+      ps::screen_sorted_kernel<D><<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(n, a_s, b_s, s->dflags + 1);
+    }
+    int flags[2] = {1, 1};
+    PS_CUDA(ctx, cudaMemcpyAsync(flags, s->dflags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PS_CUDA(ctx, cudaStreamSynchronize(st));
+    s->fast = ((flags[0] & 1) == 0) && (pp->dist != PS_DIST_POISSON || (flags[0] & 2) == 0);
+    s->screen = want_screen && s->fast && (flags[0] & 6) == 0;
+  }
+  if (s->screen) {
+    running = 0;  // exactly summable inputs: prefix differences are the reference's running sums, bit for bit
+    s->L = std::min(s->L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
+    s->nch_alloc = std::max(1, cdiv(std::max(1, n - 1), s->L));
+  }
+  const long long pstride = (long long)s->nch_alloc * n;
+  PS_CUDA(ctx, cudaMalloc(&s->part_val, pstride * sizeof(D)));
+  PS_CUDA(ctx, cudaMalloc((void**)&s->part_arg, pstride * sizeof(int)));
   if (running && s->nch_alloc > 1) {
     PS_CUDA(ctx, cudaMalloc(&s->SA, pstride * sizeof(D)));
     PS_CUDA(ctx, cudaMalloc(&s->SB, pstride * sizeof(D)));
   }
   ps::Rec4<D>* rec0 = (ps::Rec4<D>*)s->rec;
   ps::Rec4<D>* rec1 = rec0 + rec_stride;
+  if (s->screen) {
+    PS_CUDA(ctx, cudaMalloc(&s->lb, (size_t)n * sizeof(D)));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->bmax, (size_t)(n / ps::SCR_BLOCK + 2) * sizeof(float)));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->counters, 2 * sizeof(unsigned long long)));
+    PS_CUDA(ctx, cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned long long), st));
+  }
   if (running)
     ps::build_rec_running_kernel<D><<<dim3(cdiv(n + 1, 256), 1), 256, 0, st>>>(n, rec_stride, a_s, b_s, rec0,
                                                                               rec1);
   else
     ps::build_rec_prefix_kernel<D, 1024><<<1, 1024, 0, st>>>(n, rec_stride, a_s, b_s, rec0, rec1);
-  PS_CUDA(ctx, cudaGetLastError());
-  if (running && pp->no_fast_math != 1) {
-    PS_TRY(ensure(ctx, ctx->scalar, 64));
-    int flags = 1;
-    PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, 2 * sizeof(int), st));  // [0] range/exactness, [1] sortedness
-    ps::range_check_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, a_s, b_s, (int*)ctx->scalar.p);
-    PS_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->scalar.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PS_CUDA(ctx, cudaStreamSynchronize(st));
-    s->fast = ((flags & 1) == 0) && (pp->dist != PS_DIST_POISSON || (flags & 2) == 0);
+  if (s->screen) {
+    if constexpr (sizeof(D) == 8) {
+      PS_CUDA(ctx, cudaMalloc((void**)&s->recf, 2 * rec_stride * sizeof(float4)));
+      ps::build_recf_kernel<<<dim3(cdiv(n + 1, 256), 1), 256, 0, st>>>(n, rec_stride, rec0, s->recf, s->recf + rec_stride);
+    }
   }
+  PS_CUDA(ctx, cudaGetLastError());
   PS_CUDA(ctx, cudaStreamSynchronize(st));
   s->cur = 0;
   *out = s;
@@ -761,7 +797,11 @@ ps_status shard_level1_impl(ps_shard* s, D* my_chunk) {
   PS_CUDA(ctx, cudaMemsetAsync(my_chunk, 0, (size_t)s->chunk_rows * sizeof(D), st));
   // level 1 always walks the row (RUNNING) so that SA/SB get filled; in PREFIX mode the same kernel is
   // run on the prefix records' increments?  No: PREFIX shards use the closed form below.
-  if (s->p.sum_mode == PS_SUM_RUNNING) {
+  if (s->screen) {
+    if (s->owned_blocks > 0)
+      ps::level1_prefix_shard_kernel<D, BR><<<s->owned_blocks, BR, 0, st>>>(
+          n, s->p.dist, s->p.risk_part ? 1 : 0, rec0, s->ns + n, s->rank, s->world, my_chunk);
+  } else if (s->p.sum_mode == PS_SUM_RUNNING) {
     if (s->owned_blocks > 0)
       ps::level1_running_kernel<D, BR><<<dim3(s->owned_blocks, 1), BR, 0, st>>>(
           n, s->L, s->nch_alloc, rec_stride, s->p.dist, s->p.risk_part ? 1 : 0, rec0, (D*)s->SA, (D*)s->SB,
@@ -784,8 +824,9 @@ ps_status shard_set_prev_impl(ps_shard* s, const D* gathered) {
   s->cur ^= 1;
   ps::Rec4<D>* dst = rec0 + (long long)s->cur * rec_stride;
   const long long tot = (long long)s->world * s->chunk_rows;
+  float* pm_next = (s->screen && sizeof(D) == 8) ? (float*)(s->recf + (long long)s->cur * rec_stride) : nullptr;
   ps::shard_unpermute_kernel<D, BR><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(n, s->world, s->chunk_rows,
-                                                                            gathered, dst, (D*)nullptr);
+                                                                            gathered, dst, (D*)nullptr, pm_next);
   PS_CUDA(ctx, cudaGetLastError());
   PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PS_OK;
@@ -804,8 +845,30 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
   ps::Geom g = make_geom(n, j, Tc, s->L, s->nch_alloc, s->rank, s->world);
   cudaStream_t st = ctx->stream;
   PS_CUDA(ctx, cudaMemsetAsync(my_chunk, 0, (size_t)s->chunk_rows * sizeof(D), st));
-  if (g.ntiles > 0) {
-    auto fn = LevelLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, s->p.sum_mode == PS_SUM_RUNNING, s->fast);
+  if (g.ntiles > 0 && s->screen && j < Tc) {
+    if (g.ntiles >= 2048) {
+      if (s->map_key[0] != g.NCH || s->map_key[1] != g.G || s->map_key[2] != g.NRB || s->map_key[3] != g.ntiles) {
+        if (s->tile_map) PS_CUDA(ctx, cudaFree(s->tile_map));
+        s->tile_map = nullptr;
+        PS_CUDA(ctx, cudaMalloc((void**)&s->tile_map, (size_t)g.ntiles * sizeof(int2)));
+        ps::build_tile_map_kernel<<<cdiv(g.ntiles, 128), 128, 0, st>>>(g, s->tile_map);
+        s->map_key[0] = g.NCH, s->map_key[1] = g.G, s->map_key[2] = g.NRB, s->map_key[3] = g.ntiles;
+      }
+      g.tile_map = s->tile_map;
+    }
+    // lower bounds and pm maxima for every row / record (cheap; each rank needs them for all k), owned tiles only
+    float4* rf = (sizeof(D) == 8) ? s->recf + (long long)s->cur * rec_stride : (float4*)rin;
+    auto fn_lb = ScreenLaunch<D>::pick_lb(s->p.dist, s->p.risk_part ? 1 : 0);
+    auto fn_scr = ScreenLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, 0);
+    fn_lb<<<dim3(cdiv(g.nrows, 128), 1), 128, 0, st>>>(g, rin, rf, (D*)s->lb, s->bmax, n / ps::SCR_BLOCK + 2);
+    fn_scr<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, rf, (const D*)s->lb, (D*)s->part_val, s->part_arg, s->counters,
+                                             s->dflags, s->bmax, n / ps::SCR_BLOCK + 2);
+    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
+        g, (const D*)s->part_val, s->part_arg, (D*)nullptr, s->ns + (long long)j * n, 0,
+        (ps::Rec4<D>*)nullptr, my_chunk, nullptr);
+  } else if (g.ntiles > 0) {
+    const int running = (s->p.sum_mode == PS_SUM_RUNNING) && !s->screen;
+    auto fn = LevelLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, running, s->fast);
     fn<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, (const D*)s->SA, (const D*)s->SB, (D*)s->part_val,
                                          s->part_arg);
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
@@ -992,6 +1055,7 @@ ps_status ps_shard_next_start(ps_shard* s, int j, int i, int* out) {
   return PS_OK;
 }
 
+int ps_shard_screened(const ps_shard* s) { return s ? s->screen : 0; }
 void ps_shard_destroy(ps_shard* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
@@ -1001,6 +1065,12 @@ void ps_shard_destroy(ps_shard* s) {
   cudaFree(s->part_val);
   cudaFree(s->part_arg);
   cudaFree(s->ns);
+  cudaFree(s->recf);
+  cudaFree(s->lb);
+  cudaFree(s->bmax);
+  cudaFree(s->dflags);
+  cudaFree(s->tile_map);
+  cudaFree(s->counters);
   delete s;
 }
 

@@ -85,6 +85,11 @@ class CudaShardEngine:
         self.tdt = self.torch.float64 if dtype == np.float64 else self.torch.float32
         return self
 
+    @property
+    def screened(self):
+        """True when this shard's levels run the screened kernel (csrc/screen.cuh)."""
+        return bool(self.lib.ps_shard_screened(self._h))
+
     def new_chunk(self):
         return self.torch.zeros(self.chunk_rows, dtype=self.tdt, device=self.device)
 

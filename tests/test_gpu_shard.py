@@ -9,12 +9,13 @@ from partitionsolvers_b200 import capi, multigpu, synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("n", [3000, 7000])  # 7000: the shards run the screened level kernel (csrc/screen.cuh)
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-def test_sharded_levels_equal_unsharded(ctx, world, dt):
+def test_sharded_levels_equal_unsharded(ctx, world, dt, n):
     import torch
     dev = torch.device("cuda", ctx.device)
-    n, T, dist_id, rp = 3000, 6, 1, False
+    T, dist_id, rp = 6, 1, False
     a, b = synth.poisson_planted(n, 6, seed=41, dtype=dt)
     full = ctx.solve_raw(a, b, T, dist_id, rp, dtype=dt, levels=True)
     engines = [multigpu.CudaShardEngine(ctx, dev) for _ in range(world)]
@@ -22,6 +23,7 @@ def test_sharded_levels_equal_unsharded(ctx, world, dt):
     assert np.array_equal(perm, full["perm"])
     for r, e in enumerate(engines):
         e.create(a_s, b_s, n, T, dist_id, rp, dt, r, world)
+    assert all(e.screened == (n >= 6000) for e in engines)
     chunks = [e.new_chunk() for e in engines]
 
     def exchange():
