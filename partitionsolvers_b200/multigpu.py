@@ -69,8 +69,10 @@ class CudaShardEngine:
         b_d = torch.as_tensor(np.ascontiguousarray(b, dtype), device=self.device)
         n = a_d.shape[0]
         perm_d = torch.empty(n, dtype=torch.int32, device=self.device)
-        # T=1: sort + level 1 only (no O(n^2 T) work); we only want the sort index
-        self.ctx.solve_device(a_d.data_ptr(), b_d.data_ptr(), n, 1, 2, True, dtype, d_perm_out=perm_d.data_ptr())
+        # T=1: sort + level 1 only; we only want the sort index, so level 1 takes the closed prefix form instead of
+        # walking every row (O(n^2) additions in RUNNING mode: 0.2 s at n = 1e6)
+        self.ctx.solve_device(a_d.data_ptr(), b_d.data_ptr(), n, 1, 2, True, dtype, d_perm_out=perm_d.data_ptr(),
+                              sum_mode=capi.PS_SUM_PREFIX)
         idx = perm_d.long()
         return perm_d.cpu().numpy(), a_d[idx].contiguous().to(tdt), b_d[idx].contiguous().to(tdt)
 
