@@ -509,7 +509,8 @@ template <typename D, int BR>
 __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int* __restrict__ part_arg,
                                D* __restrict__ ms_row, int* __restrict__ ns_row, long long table_stride,
                                Rec4<D>* __restrict__ rec_next, D* __restrict__ shard_chunk,
-                               float* __restrict__ pm_next) {
+                               float* __restrict__ pm_next, const int* __restrict__ tile_stamp = nullptr,
+                               int stamp = 0, int stamp_stride = 0) {
   const int inst = blockIdx.y;
   const long long pstride = (long long)g.nch_alloc * g.n;
   part_val += inst * pstride;
@@ -528,6 +529,8 @@ __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int
   int arg = -1;
   if (i < g.nrows) {
     for (int c = i / g.L; c < g.NCH; ++c) {
+      // screened levels: a tile that was dropped whole wrote nothing and left its stamp alone
+      if (tile_stamp && tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + i / BR] != stamp) continue;
       const D v = part_val[(long long)c * g.n + i];
       if (v > best) {
         best = v;
@@ -719,6 +722,7 @@ build_rec_prefix_kernel(int n, long long rec_stride, const D* __restrict__ as, c
   const int per = (n + NT - 1) / NT;
   const int lo = min(n, tid * per), hi = min(n, lo + per);
   D ta = 0, tb = 0;
+#pragma unroll 8
   for (int k = lo; k < hi; ++k) {
     ta = add_rn<D>(ta, as[k]);
     tb = add_rn<D>(tb, bs[k]);
@@ -744,6 +748,7 @@ build_rec_prefix_kernel(int n, long long rec_stride, const D* __restrict__ as, c
     rec0[0] = z;
     rec1[0] = z;
   }
+#pragma unroll 4
   for (int k = lo; k < hi; ++k) {
     ra = add_rn<D>(ra, as[k]);
     rb = add_rn<D>(rb, bs[k]);

@@ -38,7 +38,8 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax;
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp;
+  int stamp = 0;  // last stamp handed to a screened level (tile_stamp holds the stamp of the level that wrote a tile)
   int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
@@ -185,7 +186,7 @@ struct LastLevelLaunch {
 template <typename D>
 struct ScreenLaunch {
   using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*, const int*,
-                      const float*, int);
+                      const float*, int, int*, int, int);
   using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, float4*, D*, float*, int);
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
@@ -461,6 +462,15 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       ctx->launches++;
       PS_TRY(ensure(ctx, ctx->lb, (size_t)R * n * sizeof(D)));
       PS_TRY(ensure(ctx, ctx->scr_bmax, (size_t)R * (n / ps::SCR_BLOCK + 2) * sizeof(float)));
+      {
+        const size_t need = (size_t)R * nch_alloc * cdiv(n, BR) * sizeof(int);
+        const bool fresh = need > ctx->tile_stamp.cap;
+        PS_TRY(ensure(ctx, ctx->tile_stamp, need));
+        if (fresh || ctx->stamp > 0x7ff00000) {
+          PS_CUDA(ctx, cudaMemsetAsync(ctx->tile_stamp.p, 0, ctx->tile_stamp.cap, st));
+          ctx->stamp = 0;
+        }
+      }
       PS_TRY(ensure(ctx, ctx->scr_counters, 2 * sizeof(unsigned long long)));
       PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 2 * sizeof(unsigned long long), st));
     }
@@ -517,7 +527,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
                                                            n / ps::SCR_BLOCK + 2);
         fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt,
                                                  (const int*)ctx->scalar.p, (const float*)ctx->scr_bmax.p,
-                                                 n / ps::SCR_BLOCK + 2);
+                                                 n / ps::SCR_BLOCK + 2, (int*)ctx->tile_stamp.p, ++ctx->stamp,
+                                                 cdiv(n, BR));
         ctx->launches++;
       } else {
         fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
@@ -526,7 +537,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (timed) PS_TRY(mark(ctx, &e1));
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
         g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
-        (screen && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr);
+        (screen && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
+        (screen && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp, cdiv(n, BR));
     ctx->launches += 2;
     if (timed) {
       lev_ev.push_back({e0, e1});
@@ -862,7 +874,7 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
     auto fn_scr = ScreenLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, 0);
     fn_lb<<<dim3(cdiv(g.nrows, 128), 1), 128, 0, st>>>(g, rin, rf, (D*)s->lb, s->bmax, n / ps::SCR_BLOCK + 2);
     fn_scr<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, rf, (const D*)s->lb, (D*)s->part_val, s->part_arg, s->counters,
-                                             s->dflags, s->bmax, n / ps::SCR_BLOCK + 2);
+                                             s->dflags, s->bmax, n / ps::SCR_BLOCK + 2, nullptr, 0, 0);
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
         g, (const D*)s->part_val, s->part_arg, (D*)nullptr, s->ns + (long long)j * n, 0,
         (ps::Rec4<D>*)nullptr, my_chunk, nullptr);

@@ -241,7 +241,7 @@ __device__ __forceinline__ D screen_exact_score(D A, D B, const GlogEntry* s_log
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per level, before the tiles: (1) a lower bound of every row's maximum = the best of <= 2*64 EXACTLY evaluated cells
+// Per level, before the tiles: (1) a lower bound of every row's maximum = the best of <= 2*32 EXACTLY evaluated cells
 // of the row (a coarse sweep over the row's k range, then a finer one around the best coarse sample).  Any evaluated
 // cell is a valid bound; the sampling only decides how tight it is (on C3 the best sample is within 1 of the maximum).
 // (2) the group maxima of pm (one thread per aligned group of 8 records).
@@ -283,7 +283,7 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ r
       kb = k;
     }
   };
-  const int ns = max(4, min(64, len >> 7));
+  const int ns = max(4, min(32, len >> 7));
   const int sc = max(1, len / ns);
   for (int k = k0; k <= k1; k += sc) probe(k);
   probe(k1);
@@ -310,7 +310,8 @@ __global__ void __launch_bounds__(BR)
 level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* __restrict__ recf,
                          const D* __restrict__ LB, D* __restrict__ part_val, int* __restrict__ part_arg,
                          unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
-                         const float* __restrict__ bmax, int nblk) {
+                         const float* __restrict__ bmax, int nblk, int* __restrict__ tile_stamp, int stamp,
+                         int stamp_stride) {
   static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
   constexpr int BK = BR;
   constexpr int U = 8;  // cells per group
@@ -410,7 +411,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     if (__syncthreads_and(lose)) {
       if (AUDIT)
         for (int k = max(k_lo, i + 1); k <= k_hi; ++k) audit_dropped(k, i < g.nrows);
-      if (i < g.nrows) {
+      if (!tile_stamp && i < g.nrows) {  // with stamps a dropped tile writes nothing: combine_kernel skips it
         part_val[(long long)c * g.n + i] = best;
         part_arg[(long long)c * g.n + i] = arg;
       }
@@ -532,6 +533,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     part_val[(long long)c * g.n + i] = best;
     part_arg[(long long)c * g.n + i] = arg;
   }
+  if (tile_stamp && tid == 0) tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + rb] = stamp;
   if (counters) {
     if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
     if (AUDIT) {
