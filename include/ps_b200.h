@@ -114,6 +114,8 @@ typedef struct ps_timings {
   int screen_used;                  /* 1: levels ran the screened kernel                                      */
   long long screen_exact_cells;     /* cells (32 per warp vote) evaluated with the reference's arithmetic      */
   long long screen_violations;      /* audit mode only; must be 0                                              */
+  long long screen_tiers[6];        /* audit mode only: tiles kept, dropped; warp-stages kept, dropped;        */
+                                    /* warp-groups kept, dropped (a stage = 128 k, a group = 8 k, x 32 rows)   */
 } ps_timings;
 
 int ps_abi_version(void);

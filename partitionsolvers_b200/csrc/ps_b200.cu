@@ -375,7 +375,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       ps::screen_decide_kernel<D><<<cdiv(R, 256), 256, 0, st>>>(R, d_st, (int*)ctx->scalar.p);
       ctx->launches += 3;
     }
-    if (!ctx->pinned_flags) PS_CUDA(ctx, cudaMallocHost((void**)&ctx->pinned_flags, 64));
+    if (!ctx->pinned_flags) PS_CUDA(ctx, cudaMallocHost((void**)&ctx->pinned_flags, 128));
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags, ctx->scalar.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PS_TRY(mark(ctx, &e_flags));
   }
@@ -471,8 +471,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
           ctx->stamp = 0;
         }
       }
-      PS_TRY(ensure(ctx, ctx->scr_counters, 2 * sizeof(unsigned long long)));
-      PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 2 * sizeof(unsigned long long), st));
+      PS_TRY(ensure(ctx, ctx->scr_counters, 8 * sizeof(unsigned long long)));
+      PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 8 * sizeof(unsigned long long), st));
     }
     ps::level1_prefix_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, rec_stride, p.dist, rp, rec0,
                                                                       d_ms + n, d_ns + n, table_stride, rec1,
@@ -576,15 +576,16 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(copy_out(res->max_score, d_ms, R * table_stride * sizeof(D)));
   PS_TRY(copy_out(res->next_start, d_ns, R * table_stride * sizeof(int)));
   if (screen)
-    PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   PS_TRY(mark(ctx, &e_end));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->tm.screen_used = screen;
   if (screen) {
-    unsigned long long cnt[2];
+    unsigned long long cnt[8];
     memcpy(cnt, ctx->pinned_flags + 2, sizeof(cnt));
     ctx->tm.screen_exact_cells = (long long)cnt[0] * 32;
     ctx->tm.screen_violations = (long long)cnt[1];
+    for (int q = 0; q < 6; ++q) ctx->tm.screen_tiers[q] = (long long)cnt[2 + q];
   }
 
   auto ms_between = [&](cudaEvent_t x, cudaEvent_t y) {

@@ -20,18 +20,23 @@
 //        reference performs is exact, and range sums formed as differences of a prefix scan are bit-identical to
 //        the reference's running sums (score_impl.hpp:248-256) -- cells can be evaluated in any order.
 //
-// Error budget of the bound (u = 2^-24; hardware claims R1, R2 are verified exhaustively by ps_selftest_mufu):
+// Error budget of the bound (u = 2^-24).  Hardware claims, verified over EVERY float of the safe range by
+// ps_selftest_mufu (measured on B200: 1.65u and 3.85u):
 //   (R1) |x * rcp.approx(x) - 1| <= 4u;   (R2) |lg2.approx(x) - log2 x| <= 4u * max(1, |log2 x|).
-//   inputs   double: At = fl(lx[k] + bx), lx = fl32(P[k] - P[cL]), bx = fl32(P[cL] - P[i]), all terms >= 0
-//                    => |At - A| <= 3u A.   float: At = P[k] - P[i] exactly (P2).
-//            diagonal tiles (cL <= i) convert the exact double difference instead (|At - A| <= u A).
-//   value    for g(A,B) = A ln(A/B) + B - A:  |g(At,Bt) - g(A,B)| <= 3u (A |ln q| + |A - B|)   (mean value theorem)
-//   MUFU     ln(q) from rcp, one multiply and lg2: absolute error <= (5u + 4u ln2) + 4u |ln q|
-//   chain    every float operation of the bound rounds by <= u relative to an intermediate bounded by
-//            A |ln q| + A + B + |p|
-//   ref      the reference's own rounding: |S_ref - g| <= 6 u_D (A |ln q| + A + B), final add u_D (|S| + |p|)
-//   => ub = t ln2 (1 + 32u) + (B - A) + 48u A + pm,  pm = ru(p) + 16u |p|   dominates S_ref + p  (needed: 16u, 30u, 3u).
-//   The other scores follow the same scheme; their budgets are next to their functors.
+// Poisson mult-clust, g(A,B) = A ln(A/B) + B - A, q = A/B > 1, t = fl(At * lg2(fl(At * rcp(Bt)))):
+//                                                                        relative to  t ln2 |  A  | |p|
+//   inputs  double: At = fl(lx[k] + bx), lx = fl32(P[k] - P[o]), bx = fl32(P[o] - P[i]) >= 0,
+//           |At - A| <= 2u A; float: At = P[k] - P[i] exactly (P2).
+//           |g(At,Bt) - g(A,B)| <= 2u (A |ln q| + |A - B|)                      2u    | 2u  |
+//   MUFU    ln(q) from rcp, one multiply, lg2: |error| <= 5u + 4u ln2 + 4u |ln q|   4u+1u | 7.8u|
+//   chain   dm, dm + pm, the final fma: each rounds by u relative to its result        1u    | 3u  | 2u
+//   ref     the reference's own rounding, D = float (negligible for double):
+//           fl(A/B), logf (< 1 ulp), the product, + B, - A, + p                         6u    | 2u  | 1u
+//                                                                             total    14u    |14.8u| 3u
+//   => ub = t ln2 (1 + 16u) + (B - A) + 20u A + pm,  pm = ru(p) + 16u |p|   dominates S_ref(A,B) + p.
+//   Poisson risk-part (A ln q, d/dA = ln q + 1, d/dB = -q) needs 15.8u on A.  The A^2/B family is bounded
+//   relative to g itself: inputs 6u, rcp 4u, roundings 4u < 32u.  Every dropped cell is re-checked in audit mode
+//   (ps_problem.screen = 2); the GPU tests require 0 violations on ~10^10 cells.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -47,9 +52,10 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return r;
 }
 
-constexpr float SCR_LN2_UP = 0.693147182464599609375f * (1.0f + 1.9073486328125e-06f);  // ln2 (1 + 2^-19)
-constexpr float SCR_REL_UP = 1.0f + 1.9073486328125e-06f;                               // 1 + 2^-19
-constexpr float SCR_CA = 2.86102294921875e-06f;                                         // 48 u
+constexpr float SCR_U = 5.9604644775390625e-08f;                                        // u = 2^-24
+constexpr float SCR_LN2_UP = 0.693147182464599609375f * (1.0f + 16.0f * SCR_U);         // ln2 (1 + 16u)
+constexpr float SCR_REL_UP = 1.0f + 32.0f * SCR_U;                                      // 1 + 32u
+constexpr float SCR_CA = 20.0f * SCR_U;                                                 // 20 u
 constexpr float SCR_TINY = 9.31322574615478515625e-10f;                                 // 2^-30
 
 // Upper bound of S(A,B) + p from float sums At, Bt (> 0) and pm = screen_pm(p).
@@ -75,7 +81,7 @@ struct ScreenUB<DIST_POISSON, true> {  // A ln(A/B), either sign       score_imp
   static __device__ __forceinline__ float eval(float A, float B, float pm) {
     const float q = A * rcp_approx(B);
     const float t = A * lg2_approx(q);
-    const float e = fmaf(fabsf(t), 0.693147182464599609375f * 1.9073486328125e-06f, fmaf(A, SCR_CA, pm));
+    const float e = fmaf(fabsf(t), 0.693147182464599609375f * 16.0f * SCR_U, fmaf(A, SCR_CA, pm));
     return fmaf(t, 0.693147182464599609375f, e);
   }
 };
@@ -303,7 +309,8 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ r
 //   group  (same) one bound per 8 cells, with the group's largest pm;
 //   cell   one bound per cell, 8 independent chains, one vote; a group with a survivor is evaluated exactly.
 // Monotonicity needs ascending priorities (dev_flags[1] == 0, screen_sorted_kernel).
-// counters[0] += warp-cells evaluated exactly, counters[1] += audit violations (a dropped cell that does not lose).
+// counters[0] += warp-cells evaluated exactly, counters[1] += audit violations (a dropped cell that does not lose);
+// audit runs also count tiles kept/dropped [2,3], warp-stages kept/dropped [4,5], warp-groups kept/dropped [6,7].
 // ---------------------------------------------------------------------------------------------
 template <typename D, int DIST, bool RP, bool AUDIT, int BR>
 __global__ void __launch_bounds__(BR)
@@ -408,7 +415,9 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     const float At = DBL ? __double2float_rn((double)R.x - (double)Xi) : __fadd_rn((float)R.x, bx);
     const float Bt = DBL ? __double2float_rn((double)R.y - (double)Yi) : __fadd_rn((float)R.y, by);
     const bool lose = (i >= g.nrows) || (ScreenUB<DIST, RP>::eval(At, Bt, tmax) < thr);
-    if (__syncthreads_and(lose)) {
+    const bool tile_dropped = __syncthreads_and(lose);
+    if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
+    if (tile_dropped) {
       if (AUDIT)
         for (int k = max(k_lo, i + 1); k <= k_hi; ++k) audit_dropped(k, i < g.nrows);
       if (!tile_stamp && i < g.nrows) {  // with stamps a dropped tile writes nothing: combine_kernel skips it
@@ -466,6 +475,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
         const float ubs = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), pmx);
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
+      if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
       if (skip) {
         if (AUDIT)
           for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true);
@@ -476,7 +486,9 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
             const float4 re = sb[kk + U - 1];
             const float ubg =
                 ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), screen_gmax_of<D>(re));
-            if (!__any_sync(0xffffffffu, !(ubg < thr))) {
+            const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
+            if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
+            if (gdrop) {
               if (AUDIT)
                 for (int u = 0; u < U; ++u) audit_dropped(kb + kk + u, true);
               continue;
