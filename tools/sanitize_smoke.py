@@ -22,6 +22,17 @@ for dt in (np.float32, np.float64):
     ctx.solve_raw(a[:129], b[:129], 129, 2, False, dtype=dt, levels=True)
     ctx.range_score(a, b, 1, False, dtype=dt)
     ctx.eval_log(np.abs(a) + 0.1, dtype=dt)
+    # screened levels (csrc/screen.cuh): every score, plain and audit mode, a replica batch, an unsorted permutation
+    a6, b6 = synth.poisson_planted(6143, 4, seed=6, dtype=dt)
+    for dist, rp in ((1, False), (1, True), (0, False), (0, True), (2, False)):
+        ctx.solve_raw(a6, b6, 4, dist, rp, dtype=dt, levels=True)
+        assert ctx.timings()["screen_used"] == 1
+    ctx.solve_raw(a6, b6, 4, 1, False, dtype=dt, screen=2)
+    ctx.solve_raw(a6, b6, 4, 1, False, dtype=dt, perm=np.random.RandomState(1).permutation(6143).astype(np.int32))
+    ab, bb = synth.poisson_null(1531, seed=4, dtype=dt, replicas=5)
+    ctx.solve_raw(ab, bb, 4, 1, False, dtype=dt, sweep=True)
+    assert ctx.timings()["screen_used"] == 1
+ctx.selftest_mufu()
 ctx.ltss(a.astype(np.float32), b.astype(np.float32), 1)
 ctx.selftest_math(0, 1 << 16)
 ctx.selftest_math(3, 1 << 16)
@@ -29,11 +40,11 @@ try:
     import torch
     from partitionsolvers_b200 import multigpu
     dev = torch.device("cuda", ctx.device)
-    a, b = synth.poisson_planted(1000, 4, seed=5, dtype=np.float64)
+    a, b = synth.poisson_planted(6200, 4, seed=5, dtype=np.float64)
     engines = [multigpu.CudaShardEngine(ctx, dev) for _ in range(2)]
     perm, a_s, b_s = engines[0].sort(a, b, np.float64)
     for r, e in enumerate(engines):
-        e.create(a_s, b_s, 1000, 4, 1, False, np.float64, r, 2)
+        e.create(a_s, b_s, 6200, 4, 1, False, np.float64, r, 2)
     chunks = [e.new_chunk() for e in engines]
     for e, c in zip(engines, chunks):
         e.level1(c)
