@@ -111,7 +111,7 @@ typedef struct ps_timings {
   long long level_cells[PS_MAX_TIMED_LEVELS]; /* (i,k) cells evaluated by that launch, all instances  */
   long long kernel_launches;              /* kernels launched by the call                            */
   long long h2d_bytes, d2h_bytes;
-  int screen_used;                  /* 1: levels ran the screened kernel                                      */
+  int screen_used;                  /* 1: screened levels (exact sums); 2: screened levels, running sums; 0: exhaustive */
   long long screen_exact_cells;     /* cells (32 per warp vote) evaluated with the reference's arithmetic      */
   long long screen_violations;      /* audit mode only; must be 0                                              */
   long long screen_tiers[6];        /* audit mode only: tiles kept, dropped; warp-stages kept, dropped;        */

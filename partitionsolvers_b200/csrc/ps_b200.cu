@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "radix_sort.cuh"
 #include "screen.cuh"
+#include "screen_run.cuh"
 
 namespace {
 
@@ -38,7 +39,7 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp;
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp, fxinfo, pfx;
   int stamp = 0;  // last stamp handed to a screened level (tile_stamp holds the stamp of the level that wrote a tile)
   int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
@@ -214,6 +215,37 @@ struct ScreenLaunch {
   }
 };
 
+struct ScreenRunLaunch {
+  using Fn = void (*)(ps::Geom, const ps::Rec4<double>*, const float4*, const longlong2*, const ps::FxInfo*,
+                      const double*, const double*, const double*, double*, int*, unsigned long long*, const int*,
+                      const float*, int, int*, int, int);
+  using LbFn = void (*)(ps::Geom, const ps::Rec4<double>*, float4*, const double*, const double*, double*, float*, int);
+  static Fn pick(int dist, int rp, int audit) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                          \
+  return audit ? (Fn)level_tile_screen_run_kernel<DI, RPV, true, BR>              \
+               : (Fn)level_tile_screen_run_kernel<DI, RPV, false, BR>;
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: PS_PICK(DIST_GAUSSIAN, false)
+      case 1: PS_PICK(DIST_GAUSSIAN, true)
+      case 2: PS_PICK(DIST_POISSON, false)
+      case 3: PS_PICK(DIST_POISSON, true)
+      default: PS_PICK(DIST_RATIONAL, false)
+    }
+#undef PS_PICK
+  }
+  static LbFn pick_lb(int dist, int rp) {
+    using namespace ps;
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: return (LbFn)screen_lb_run_kernel<DIST_GAUSSIAN, false>;
+      case 1: return (LbFn)screen_lb_run_kernel<DIST_GAUSSIAN, true>;
+      case 2: return (LbFn)screen_lb_run_kernel<DIST_POISSON, false>;
+      case 3: return (LbFn)screen_lb_run_kernel<DIST_POISSON, true>;
+      default: return (LbFn)screen_lb_run_kernel<DIST_RATIONAL, false>;
+    }
+  }
+};
+
 ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int rb_step, int tile_rows = BR) {
   ps::Geom g;
   g.n = n;
@@ -374,6 +406,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       ps::screen_stats_kernel<D><<<dim3(bx, R), 256, 0, st>>>(n, d_a, d_b, d_st);
       ps::screen_decide_kernel<D><<<cdiv(R, 256), 256, 0, st>>>(R, d_st, (int*)ctx->scalar.p);
       ctx->launches += 3;
+      if (sizeof(D) == 8) {  // fixed-point shifts and conditions of the running-sum screen (screen_run.cuh) -> flag bit 3
+        PS_TRY(ensure(ctx, ctx->fxinfo, (size_t)R * sizeof(ps::FxInfo)));
+        ps::fx_setup_kernel<<<cdiv(R, 256), 256, 0, st>>>(R, n, (p.dist == PS_DIST_POISSON && rp) ? 1 : 0, d_st,
+                                                          (ps::FxInfo*)ctx->fxinfo.p, (int*)ctx->scalar.p);
+        ctx->launches++;
+      }
     }
     if (!ctx->pinned_flags) PS_CUDA(ctx, cudaMallocHost((void**)&ctx->pinned_flags, 128));
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags, ctx->scalar.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -389,13 +427,17 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   ps::Rec4<D>* recs[2] = {rec0, rec1};
   const D* d_as = (const D*)ctx->a_s.p;
   const D* d_bs = (const D*)ctx->b_s.p;
-  int fast = 0, screen = 0;
+  int fast = 0, screen = 0, screen_run = 0;
   if (want_fast) {  // the precheck ran right after the inputs arrived; its flags are on the host by now
     PS_CUDA(ctx, cudaEventSynchronize(e_flags));
     host_flags = *ctx->pinned_flags;
     fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
     // screening needs positive sums for every score (relative error of the float range sums) and exact summability
     screen = want_screen && fast && (host_flags & 2) == 0 && (host_flags & 4) == 0;
+    // double inputs whose sums round: float bounds from fixed-point prefix sums, survivors from the reference's running sums
+    // (measured crossover against the exhaustive kernel: n ~ 16000, tools/run_c3r.py; audit runs take it at any size)
+    screen_run = want_screen && fast && !screen && sizeof(D) == 8 && (host_flags & 8) == 0 &&
+                 (n >= 16384 || p.screen == 2);
   }
   if (screen) running = 0;  // exactly summable: prefix differences ARE the reference's running sums, bit for bit
   if (running) {
@@ -425,7 +467,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
   // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);
   // at most ~200 chunks so that the per-chunk partials stay small
-  if (screen && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
+  if ((screen || screen_run) && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
   const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
   const long long pstride = (long long)nch_alloc * n;
   PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
@@ -435,6 +477,23 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   D* d_SA = nullptr;
   D* d_SB = nullptr;
   float4* recf[2] = {nullptr, nullptr};
+  // sortedness flag, row lower bounds, block maxima, tile stamps and counters of the screened level kernels
+  auto screen_buffers = [&]() -> ps_status {
+    ps::screen_sorted_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, d_as, d_bs, (int*)ctx->scalar.p + 1);
+    ctx->launches++;
+    PS_TRY(ensure(ctx, ctx->lb, (size_t)R * n * sizeof(D)));
+    PS_TRY(ensure(ctx, ctx->scr_bmax, (size_t)R * (n / ps::SCR_BLOCK + 2) * sizeof(float)));
+    const size_t need = (size_t)R * nch_alloc * cdiv(n, BR) * sizeof(int);
+    const bool fresh = need > ctx->tile_stamp.cap;
+    PS_TRY(ensure(ctx, ctx->tile_stamp, need));
+    if (fresh || ctx->stamp > 0x7ff00000) {
+      PS_CUDA(ctx, cudaMemsetAsync(ctx->tile_stamp.p, 0, ctx->tile_stamp.cap, st));
+      ctx->stamp = 0;
+    }
+    PS_TRY(ensure(ctx, ctx->scr_counters, 8 * sizeof(unsigned long long)));
+    PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 8 * sizeof(unsigned long long), st));
+    return PS_OK;
+  };
   if (running) {
     if (nch_alloc > 1) {
       PS_TRY(ensure(ctx, ctx->SA, R * pstride * sizeof(D)));
@@ -445,6 +504,21 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     ps::level1_running_kernel<D, BR><<<dim3(cdiv(n, BR), R), BR, 0, st>>>(
         n, L, nch_alloc, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
         0, 1, nullptr);
+    if constexpr (sizeof(D) == 8) {
+      if (screen_run) {
+        PS_TRY(ensure(ctx, ctx->recf, 2 * R * rec_stride * sizeof(float4)));
+        PS_TRY(ensure(ctx, ctx->pfx, R * rec_stride * sizeof(longlong2)));
+        recf[0] = (float4*)ctx->recf.p;
+        recf[1] = recf[0] + R * rec_stride;
+        ps::fx_prefix_kernel<1024><<<R, 1024, 0, st>>>(n, rec_stride, d_as, d_bs, (ps::FxInfo*)ctx->fxinfo.p,
+                                                      (longlong2*)ctx->pfx.p);
+        ps::build_recf_fx_kernel<<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(
+            n, rec_stride, (const longlong2*)ctx->pfx.p, (const ps::FxInfo*)ctx->fxinfo.p, recf[0], recf[1]);
+        ps::pm_from_rec_kernel<<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(n, rec_stride, rec1, recf[1]);
+        ctx->launches += 3;
+        PS_TRY(screen_buffers());
+      }
+    }
   } else {
     // screened levels read float records: double -> separate {lx, ly, -, pm} arrays, float -> the records themselves
     if (screen) {
@@ -458,21 +532,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         recf[0] = (float4*)rec0;
         recf[1] = (float4*)rec1;
       }
-      ps::screen_sorted_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, d_as, d_bs, (int*)ctx->scalar.p + 1);
-      ctx->launches++;
-      PS_TRY(ensure(ctx, ctx->lb, (size_t)R * n * sizeof(D)));
-      PS_TRY(ensure(ctx, ctx->scr_bmax, (size_t)R * (n / ps::SCR_BLOCK + 2) * sizeof(float)));
-      {
-        const size_t need = (size_t)R * nch_alloc * cdiv(n, BR) * sizeof(int);
-        const bool fresh = need > ctx->tile_stamp.cap;
-        PS_TRY(ensure(ctx, ctx->tile_stamp, need));
-        if (fresh || ctx->stamp > 0x7ff00000) {
-          PS_CUDA(ctx, cudaMemsetAsync(ctx->tile_stamp.p, 0, ctx->tile_stamp.cap, st));
-          ctx->stamp = 0;
-        }
-      }
-      PS_TRY(ensure(ctx, ctx->scr_counters, 8 * sizeof(unsigned long long)));
-      PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 8 * sizeof(unsigned long long), st));
+      PS_TRY(screen_buffers());
     }
     ps::level1_prefix_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, rec_stride, p.dist, rp, rec0,
                                                                       d_ms + n, d_ns + n, table_stride, rec1,
@@ -521,7 +581,20 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         }
         g.tile_map = (const int2*)ctx->tile_map.p;
       }
-      if (screen) {
+      if (screen_run) {
+        if constexpr (sizeof(D) == 8) {
+          auto fn_lbr = ScreenRunLaunch::pick_lb(p.dist, rp);
+          auto fn_run = ScreenRunLaunch::pick(p.dist, rp, p.screen == 2);
+          fn_lbr<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_SA, d_SB, d_lb,
+                                                              (float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2);
+          fn_run<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], (const longlong2*)ctx->pfx.p,
+                                                   (const ps::FxInfo*)ctx->fxinfo.p, d_SA, d_SB, d_lb, d_pv, d_pa, d_cnt,
+                                                   (const int*)ctx->scalar.p, (const float*)ctx->scr_bmax.p,
+                                                   n / ps::SCR_BLOCK + 2, (int*)ctx->tile_stamp.p, ++ctx->stamp,
+                                                   cdiv(n, BR));
+          ctx->launches++;
+        }
+      } else if (screen) {
         // row lower bounds from a few exactly evaluated cells, then the screened tiles
         fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, (float*)ctx->scr_bmax.p,
                                                            n / ps::SCR_BLOCK + 2);
@@ -537,8 +610,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (timed) PS_TRY(mark(ctx, &e1));
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
         g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
-        (screen && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
-        (screen && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp, cdiv(n, BR));
+        ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
+        ((screen || screen_run) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp, cdiv(n, BR));
     ctx->launches += 2;
     if (timed) {
       lev_ev.push_back({e0, e1});
@@ -575,12 +648,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(copy_out(res->subset_scores, d_scores, (size_t)R * nS * Tc * sizeof(D)));
   PS_TRY(copy_out(res->max_score, d_ms, R * table_stride * sizeof(D)));
   PS_TRY(copy_out(res->next_start, d_ns, R * table_stride * sizeof(int)));
-  if (screen)
+  if (screen || screen_run)
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   PS_TRY(mark(ctx, &e_end));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
-  ctx->tm.screen_used = screen;
-  if (screen) {
+  ctx->tm.screen_used = screen ? 1 : (screen_run ? 2 : 0);
+  if (screen || screen_run) {
     unsigned long long cnt[8];
     memcpy(cnt, ctx->pinned_flags + 2, sizeof(cnt));
     ctx->tm.screen_exact_cells = (long long)cnt[0] * 32;
@@ -947,7 +1020,8 @@ void ps_destroy(ps_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->a_in,  &ctx->b_in,     &ctx->key_in,   &ctx->key_out, &ctx->idx_in, &ctx->perm,
                     &ctx->a_s,   &ctx->b_s,      &ctx->rec,      &ctx->SA,      &ctx->SB,     &ctx->part_val,
                     &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->sort_hist,
-                    &ctx->scalar};
+                    &ctx->scalar, &ctx->recf,    &ctx->lb,       &ctx->scr_stats, &ctx->scr_counters, &ctx->tile_map,
+                    &ctx->scr_bmax, &ctx->tile_stamp, &ctx->fxinfo, &ctx->pfx};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);

@@ -125,6 +125,10 @@ struct ScreenUB<DIST_RATIONAL, RP> {  // A^2 / B          score_impl.hpp:464-465
 struct ScreenStats {
   int ea, eb;
   double sa, sb;
+  // for the fixed-point bounds of screen_run.cuh: bit patterns of the smallest positive a and the smallest b
+  // (positive doubles order like their bit patterns), number of elements with a <= 0
+  unsigned long long min_a_pos, min_b;
+  int n_nonpos, pad;
 };
 __device__ __forceinline__ int lowbit_exp(double v) {
   const long long bits = __double_as_longlong(v);
@@ -143,6 +147,8 @@ __global__ void screen_stats_init_kernel(int R, ScreenStats* __restrict__ st) {
   if (r < R) {
     st[r].ea = st[r].eb = 0x7fffffff;
     st[r].sa = st[r].sb = 0.0;
+    st[r].min_a_pos = st[r].min_b = 0x7ff0000000000000ULL;
+    st[r].n_nonpos = st[r].pad = 0;
   }
 }
 template <typename D>
@@ -153,24 +159,37 @@ screen_stats_kernel(int n, const D* __restrict__ a, const D* __restrict__ b, Scr
   b += (long long)inst * n;
   int ea = 0x7fffffff, eb = 0x7fffffff;
   double sa = 0.0, sb = 0.0;
+  unsigned long long ma = 0x7ff0000000000000ULL, mb = 0x7ff0000000000000ULL;
+  int np = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const D av = a[k], bv = b[k];
     if (av != (D)0) ea = min(ea, lowbit_exp(av));
     if (bv != (D)0) eb = min(eb, lowbit_exp(bv));
     sa += fabs((double)av);
     sb += fabs((double)bv);
+    if (av > (D)0)
+      ma = min(ma, (unsigned long long)__double_as_longlong((double)av));
+    else
+      ++np;
+    if (bv > (D)0) mb = min(mb, (unsigned long long)__double_as_longlong((double)bv));
   }
   for (int o = 16; o > 0; o >>= 1) {
     ea = min(ea, __shfl_xor_sync(0xffffffffu, ea, o));
     eb = min(eb, __shfl_xor_sync(0xffffffffu, eb, o));
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
     sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    ma = min(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    mb = min(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    np += __shfl_xor_sync(0xffffffffu, np, o);
   }
   if ((threadIdx.x & 31) == 0) {
     atomicMin(&st[inst].ea, ea);
     atomicMin(&st[inst].eb, eb);
     atomicAdd(&st[inst].sa, sa);
     atomicAdd(&st[inst].sb, sb);
+    atomicMin(&st[inst].min_a_pos, ma);
+    atomicMin(&st[inst].min_b, mb);
+    if (np) atomicAdd(&st[inst].n_nonpos, np);
   }
 }
 template <typename D>

@@ -1,0 +1,481 @@
+// screen_run.cuh -- screened levels for double inputs whose partial sums are NOT exactly representable
+// (real-valued a, b: the Gaussian / Rational workloads, tract-like expected counts).
+//
+// screen.cuh needs exact summability because it forms a cell's range sums as prefix differences, which equal the
+// reference's left-to-right running sums (score_impl.hpp:248-256) only when no addition rounds.  Here the two jobs
+// are separated:
+//   * the BOUND of a cell still comes from float range sums, now derived from 64-bit FIXED-POINT prefix sums
+//     (integer differences are exact, so there is no cancellation however long the prefix is);
+//   * a cell that survives is evaluated from the reference's own RUNNING sums, re-created by walking the records from
+//     the nearest checkpoint: the level-1 pass (level1_running_kernel) leaves every row's running sums at every
+//     k-chunk boundary (SA/SB, the same arrays the exhaustive RUNNING kernel starts its tiles from).  The walk is
+//     lazy and warp-uniform (lanes = adjacent rows at the same k): a warp only walks the tiles in which it has a
+//     survivor, so the 2 DADD per walked cell are paid on a few per cent of the cells.
+// Values and first-argmax are therefore the reference's, bit for bit, exactly as argued in screen.cuh: the first
+// maximiser's bound survives, every evaluated cell uses reference arithmetic on reference sums, ascending k, strict >.
+//
+// Fixed point.  Per instance and array: shift s with sum|x| * 2^s < 2^61 (fx_setup_kernel);
+//   a_fx = ceil(a 2^s)  (range sums of a are bounded from ABOVE),  b_fx = floor(b 2^s)  (from BELOW).
+// Every bound of screen.cuh is non-decreasing in A and non-increasing in B on the region where it is used, except
+// Poisson risk-part (A ln(A/B) decreases in A while A/B < 1/e), which therefore also needs the two-sided condition below.
+// Conditions checked on the device (else the exhaustive kernel runs):
+//   (F1) min b * 2^sb >= 2^28: |B_fx 2^-sb - B| <= 2^-28 B for every range  (0.06 u, u = 2^-24);
+//   (F2) Poisson risk-part only: the same for the positive a;
+//   (F3) n <= 2^22: the reference's running sum of m <= n positive terms differs from the true sum by at most
+//        (m-1) 2^-53 <= 2^-31 relatively  (0.01 u);
+//   (F4) at most n/8 elements with a <= 0.  Rows i < ipos = 1 + (last index with a <= 0) own range sums that need not be
+//        positive: the float bounds do not apply and their tiles are evaluated exhaustively inside this kernel.
+// Float range sums: At = fl(lx[k] + bx), lx = fl(2^-s (P[k] - P[o])), bx = fl(2^-s (P[o] - P[i])), o = origin of k's
+// 128-block: three roundings on non-negative terms, |At - A_fx| <= 2u A_fx as in screen.cuh; with (F1)-(F3) the input
+// line of the error budget becomes 2.07u (of the 2u + 2u/5u spare the margins carry).  The monotone tiers (tile, stage,
+// group) are argued on the TRUE sums; the reference's values differ from the true-sum values by the (F3) term.
+// Audit mode (ps_problem.screen = 2) re-evaluates every dropped cell with the reference's arithmetic, as in screen.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "screen.cuh"
+
+namespace ps {
+
+struct FxInfo {
+  int sa, sb;      // shifts
+  float sca, scb;  // 2^-sa, 2^-sb
+  int ipos;        // rows >= ipos have only positive a to their right (written by fx_prefix_kernel)
+  int ok;          // instance qualifies
+  int pad[2];
+};
+
+// Per instance: shifts and the conditions (F1)-(F4).  flags[0] |= 8 if some instance does not qualify.
+__global__ void fx_setup_kernel(int R, int n, int need_tight_a, const ScreenStats* __restrict__ st,
+                                FxInfo* __restrict__ fx, int* __restrict__ flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const ScreenStats s = st[r];
+  int ea = 0, eb = 0;
+  frexp(fmax(s.sa, 1e-300), &ea);  // sa < 2^ea
+  frexp(fmax(s.sb, 1e-300), &eb);
+  FxInfo f;
+  f.sa = 60 - ea;
+  f.sb = 60 - eb;
+  f.sca = (float)ldexp(1.0, -f.sa);
+  f.scb = (float)ldexp(1.0, -f.sb);
+  f.ipos = 0;
+  const double min_a = __longlong_as_double((long long)s.min_a_pos);
+  const double min_b = __longlong_as_double((long long)s.min_b);
+  const double tight = 268435456.0;  // 2^28
+  bool ok = (n <= (1 << 22)) && (f.sa >= -90 && f.sa <= 90) && (f.sb >= -90 && f.sb <= 90);
+  ok = ok && s.min_b != 0x7ff0000000000000ULL && ldexp(min_b, f.sb) >= tight;
+  if (need_tight_a) ok = ok && s.min_a_pos != 0x7ff0000000000000ULL && ldexp(min_a, f.sa) >= tight;
+  ok = ok && (s.n_nonpos <= n / 8);
+  f.ok = ok ? 1 : 0;
+  f.pad[0] = f.pad[1] = 0;
+  fx[r] = f;
+  if (!ok) atomicOr(flags, 8);
+}
+
+// Fixed-point prefix sums of the SORTED arrays: pfx[k] = {sum_{j<k} ceil(a_j 2^sa), sum_{j<k} floor(b_j 2^sb)}.
+// Integer addition is associative: any scan order gives the same (exact) result.  One CTA per instance, every thread owns
+// a contiguous slice.  Also ipos.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+fx_prefix_kernel(int n, long long rec_stride, const double* __restrict__ as, const double* __restrict__ bs,
+                 FxInfo* __restrict__ fx, longlong2* __restrict__ pfx) {
+  __shared__ long long sa[NT], sb[NT];
+  __shared__ int s_ipos;
+  const int inst = blockIdx.x;
+  as += (long long)inst * n;
+  bs += (long long)inst * n;
+  pfx += inst * rec_stride;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_ipos = 0;
+  const int sha = fx[inst].sa, shb = fx[inst].sb;
+  const int per = (n + NT - 1) / NT;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  long long ta = 0, tb = 0;
+  int ip = 0;
+  for (int k = lo; k < hi; ++k) {
+    const double av = as[k];
+    ta += __double2ll_ru(scalbn(av, sha));
+    tb += __double2ll_rd(scalbn(bs[k], shb));
+    if (!(av > 0.0)) ip = k + 1;
+  }
+  sa[tid] = ta;
+  sb[tid] = tb;
+  __syncthreads();
+  if (ip) atomicMax(&s_ipos, ip);
+  if (tid == 0) {
+    long long ra = 0, rb = 0;
+    for (int q = 0; q < NT; ++q) {
+      const long long xa = sa[q], xb = sb[q];
+      sa[q] = ra;
+      sb[q] = rb;
+      ra += xa;
+      rb += xb;
+    }
+  }
+  __syncthreads();
+  long long ra = sa[tid], rb = sb[tid];
+  if (tid == 0) {
+    pfx[0] = make_longlong2(0, 0);
+    fx[inst].ipos = s_ipos;
+  }
+  for (int k = lo; k < hi; ++k) {
+    ra += __double2ll_ru(scalbn(as[k], sha));
+    rb += __double2ll_rd(scalbn(bs[k], shb));
+    pfx[k + 1] = make_longlong2(ra, rb);
+  }
+}
+
+// Float screening records {lx, ly, gmax, pm} from the fixed-point prefix sums (both level buffers); lx, ly relative to the
+// origin of k's 128-block as in build_recf_kernel.
+__global__ void build_recf_fx_kernel(int n, long long rec_stride, const longlong2* __restrict__ pfx,
+                                     const FxInfo* __restrict__ fx, float4* __restrict__ recf0,
+                                     float4* __restrict__ recf1) {
+  const int inst = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n) return;
+  pfx += inst * rec_stride;
+  const FxInfo F = fx[inst];
+  const int o = (k > 0) ? ((k - 1) / SCR_BLOCK) * SCR_BLOCK : 0;
+  const longlong2 r = pfx[k], q = pfx[o];
+  const float4 f = make_float4(__ll2float_rn(r.x - q.x) * F.sca, __ll2float_rn(r.y - q.y) * F.scb, 0.f, 0.f);
+  recf0[inst * rec_stride + k] = f;
+  recf1[inst * rec_stride + k] = f;
+}
+
+// pm of level 1 (level1_running_kernel wrote the level values into the p field of the records)
+__global__ void pm_from_rec_kernel(int n, long long rec_stride, const Rec4<double>* __restrict__ rec,
+                                   float4* __restrict__ recf) {
+  const int inst = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n) return;
+  recf[inst * rec_stride + k].w = screen_pm<double>(rec[inst * rec_stride + k].p);
+}
+
+// Row lower bounds for the running-sum path: the cells whose running sums are at hand are the chunk boundaries
+// (i, c L), c L > i -- all of them are evaluated (at most ~200 per row).  Also the group / block maxima of pm, as in
+// screen_lb_kernel.
+template <int DIST, bool RP>
+__global__ void __launch_bounds__(128)
+screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __restrict__ recf,
+                     const double* __restrict__ SA, const double* __restrict__ SB, double* __restrict__ LB,
+                     float* __restrict__ bmax, int nblk) {
+  using D = double;
+  const int inst = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nrows) return;
+  rec += (long long)inst * g.rec_stride;
+  recf += (long long)inst * g.rec_stride;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  if ((i & (SCR_BLOCK - 1)) == 0) {
+    float m = -3.402823466e+38f;
+    const int ke = min(i + SCR_BLOCK, g.n);
+    for (int k = i + 1; k <= ke; ++k) m = fmaxf(m, recf[k].w);
+    bmax[(long long)inst * nblk + i / SCR_BLOCK] = m;
+  }
+  if ((i & 7) == 0 && i + 8 <= g.n) {
+    float m = recf[i + 1].w;
+#pragma unroll
+    for (int q = 2; q <= 8; ++q) m = fmaxf(m, recf[i + q].w);
+    recf[i + 8].z = m;
+  }
+  D best = Lim<D>::lowest();
+  if (SA) {
+    const int c1 = min(g.kmax / g.L, g.nch_alloc - 1);
+    for (int c = i / g.L + 1; c <= c1; ++c) {
+      const D A = SA[inst * pstride + (long long)c * g.n + i];
+      const D B = SB[inst * pstride + (long long)c * g.n + i];
+      const D v = add_rn<D>(screen_exact_score<D, DIST, RP, false>(A, B, nullptr), rec[c * g.L].p);
+      if (v > best) best = v;
+    }
+  }
+  LB[(long long)inst * g.n + i] = best;
+}
+
+// One (row block, k-chunk) tile of one level, screened, RUNNING sums.  Same tiling, tiers, partial/combine protocol and
+// counters as level_tile_screen_kernel.
+template <int DIST, bool RP, bool AUDIT, int BR>
+__global__ void __launch_bounds__(BR, 8)
+level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const float4* __restrict__ recf,
+                             const longlong2* __restrict__ pfx, const FxInfo* __restrict__ fx,
+                             const double* __restrict__ SA, const double* __restrict__ SB,
+                             const double* __restrict__ LB, double* __restrict__ part_val,
+                             int* __restrict__ part_arg, unsigned long long* __restrict__ counters,
+                             const int* __restrict__ dev_flags, const float* __restrict__ bmax, int nblk,
+                             int* __restrict__ tile_stamp, int stamp, int stamp_stride) {
+  using D = double;
+  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
+  constexpr int BK = BR;
+  constexpr int U = 8;
+  constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
+  constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
+  __shared__ float4 sbuf[2][BK];
+  __shared__ float s_pmax[2][BR / 32];
+  constexpr bool kLogTab = (DIST == DIST_POISSON);
+  __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
+  if (kLogTab) {
+    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
+  }
+
+  const int inst = blockIdx.y;
+  rec += (long long)inst * g.rec_stride;
+  recf += (long long)inst * g.rec_stride;
+  pfx += (long long)inst * g.rec_stride;
+  LB += (long long)inst * g.n;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  part_val += inst * pstride;
+  part_arg += inst * pstride;
+  const FxInfo F = fx[inst];
+
+  int rb, c;
+  decode_tile(g, blockIdx.x, rb, c);
+  const int tid = threadIdx.x;
+  const int i0 = rb * BR;
+  const int i = i0 + tid;
+  const int k_lo = max(c * g.L + 1, i0 + 1);
+  const int k_hi = min((c + 1) * g.L, g.kmax);
+  const bool diag_tile = (c == rb / g.G);
+
+  const int il = min(i, g.n - 1);
+  const longlong2 Pi = pfx[il];
+  float bx = 0.f, by = 0.f;
+  D best = Lim<D>::lowest();
+  int arg = -1;
+  float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
+  unsigned int nexact = 0, nviol = 0;
+  const bool mono = (FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0);
+
+  // the reference's running sums of row i through cell kw (warp-uniform kw); a tile right of the diagonal starts from the
+  // checkpoint the level-1 pass left at its chunk boundary (loaded on first use)
+  D Ar = 0, Br = 0;
+  int kw = diag_tile ? i0 : c * g.L;
+  bool loaded = diag_tile;
+  auto advance_to = [&](const int k) {
+    if (!loaded) {
+      Ar = SA[inst * pstride + (long long)c * g.n + il];
+      Br = SB[inst * pstride + (long long)c * g.n + il];
+      loaded = true;
+    }
+    int q = kw + 1;
+    if (q <= i0 + BR - 1) {  // diagonal stage: row i starts at k = i + 1
+      const int qe = min(k, i0 + BR - 1);
+      for (; q <= qe; ++q) {
+        const double2 ab = *reinterpret_cast<const double2*>(&rec[q]);
+        if (q > i) {
+          Ar = add_rn<D>(Ar, ab.x);
+          Br = add_rn<D>(Br, ab.y);
+        }
+      }
+    }
+#pragma unroll 4
+    for (; q <= k; ++q) {
+      const double2 ab = *reinterpret_cast<const double2*>(&rec[q]);
+      Ar = add_rn<D>(Ar, ab.x);
+      Br = add_rn<D>(Br, ab.y);
+    }
+    kw = max(kw, k);
+  };
+  // calls are warp-uniform and ascending in k
+  auto exact_at = [&](const int k) -> D {
+    advance_to(k);
+    return add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(Ar, Br, s_log), rec[k].p);
+  };
+  auto audit_dropped = [&](const int k, const bool valid) {
+    const D v = exact_at(k);
+    if (valid && !(v < (double)thr)) ++nviol;
+  };
+  auto fsum = [&](const longlong2 P, float& A, float& B) {
+    A = __ll2float_rn(P.x - Pi.x) * F.sca;
+    B = __ll2float_rn(P.y - Pi.y) * F.scb;
+  };
+  auto cell = [&](const int k, const float4 r, const bool valid, auto from_fixed) {
+    float A, B;
+    if constexpr (decltype(from_fixed)::value) {
+      fsum(pfx[k], A, B);
+    } else {
+      A = __fadd_rn(r.x, bx);
+      B = __fadd_rn(r.y, by);
+    }
+    const float ub = ScreenUB<DIST, RP>::eval(A, B, r.w);
+    const bool pass = valid && !(ub < thr);
+    if (__any_sync(0xffffffffu, pass)) {
+      const D v = exact_at(k);
+      if (AUDIT && valid && (double)ub < v) ++nviol;
+      ++nexact;
+      if (valid && v > best) {
+        best = v;
+        arg = k;
+        thr = fmaxf(thr, screen_rd<D>(best));
+      }
+    } else if (AUDIT) {
+      audit_dropped(k, valid);
+    }
+  };
+  using T_ = std::integral_constant<bool, true>;
+  using F_ = std::integral_constant<bool, false>;
+  auto stage_max = [&](const float4 r, const int buf) {
+    float w = ((tid & 7) == 7) ? r.z : -3.402823466e+38f;
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 8));
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 16));
+    if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
+  };
+  auto finish = [&]() {
+    if (i < g.nrows) {
+      part_val[(long long)c * g.n + i] = best;
+      part_arg[(long long)c * g.n + i] = arg;
+    }
+    if (tile_stamp && tid == 0) tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + rb] = stamp;
+    if (counters) {
+      if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
+      if (AUDIT) {
+        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+      }
+    }
+  };
+
+  if (i0 < F.ipos) {
+    // (F4) a row of this block may own non-positive range sums: no bounds, every cell with the reference's arithmetic
+    for (int k = k_lo; k <= k_hi; ++k) {
+      const D v = exact_at(k);
+      ++nexact;
+      if (k > i && v > best) {
+        best = v;
+        arg = k;
+      }
+    }
+    finish();
+    return;
+  }
+
+  if (GROUPB && mono) {
+    bmax += (long long)inst * nblk;
+    float tmax = -3.402823466e+38f;
+    for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
+    float At, Bt;
+    fsum(pfx[k_hi], At, Bt);
+    const bool lose = (i >= g.nrows) || (ScreenUB<DIST, RP>::eval(At, Bt, tmax) < thr);
+    const bool tile_dropped = __syncthreads_and(lose);
+    if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
+    if (tile_dropped) {
+      if (AUDIT)
+        for (int k = k_lo; k <= k_hi; ++k) audit_dropped(k, k > i && i < g.nrows);
+      if (!tile_stamp && i < g.nrows) {
+        part_val[(long long)c * g.n + i] = best;
+        part_arg[(long long)c * g.n + i] = arg;
+      }
+      if (AUDIT && counters) {
+        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+      }
+      return;
+    }
+  }
+  const int nk = k_hi - k_lo + 1;
+  const int nstages = (nk + BK - 1) / BK;
+  longlong2 onx;  // fixed-point prefix at the origin of the next stage (k = kb - 1)
+  {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
+    sbuf[0][tid] = r;
+    if (GROUPB) stage_max(r, 0);
+    onx = pfx[k_lo - 1];
+  }
+  for (int s = 0; s < nstages; ++s) {
+    __syncthreads();
+    const int kb = k_lo + s * BK;
+    const int kn = kb + BK + tid;
+    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_next = (s + 1 < nstages);
+    if (has_next && kn <= k_hi) nx = recf[kn];
+    fsum(onx, bx, by);  // >= 0 on every stage right of the diagonal
+    if (has_next) onx = pfx[kb + BK - 1];
+    const int cnt = min(BK, k_hi - kb + 1);
+    const float4* __restrict__ sb = sbuf[s & 1];
+    if (kb <= i0 + BR - 1) {
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
+    } else if (cnt < BK) {
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
+    } else {
+      bool skip = false;
+      if (GROUPB && mono) {
+        float pmx = s_pmax[s & 1][0];
+#pragma unroll
+        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
+        const float4 re = sb[BK - 1];
+        const float ubs = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), pmx);
+        skip = !__any_sync(0xffffffffu, !(ubs < thr));
+      }
+      if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
+      if (skip) {
+        if (AUDIT)
+          for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true);
+      } else {
+#pragma unroll 1
+        for (int kk = 0; kk < BK; kk += U) {
+          if (GROUPB && mono) {
+            const float4 re = sb[kk + U - 1];
+            const float ubg = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), re.z);
+            const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
+            if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
+            if (gdrop) {
+              if (AUDIT)
+                for (int u = 0; u < U; ++u) audit_dropped(kb + kk + u, true);
+              continue;
+            }
+          }
+          float A[U], B[U], W[U];
+          bool gt = false;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float4 r = sb[kk + u];
+            A[u] = __fadd_rn(r.x, bx);
+            B[u] = __fadd_rn(r.y, by);
+            W[u] = r.w;
+            if (FRONTIER) gt |= A[u] > B[u];
+          }
+          bool alive = false;
+          if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) alive |= !(fmaf(B[u], SCR_TINY, W[u]) < thr);
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) alive |= !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
+          }
+          if (AUDIT) {
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) cell(kb + kk + u, sb[kk + u], true, F_{});
+          } else if (__any_sync(0xffffffffu, alive)) {
+            // a survivor: walk to the group, then its U cells -- the sums are sequential (2 DADD per cell), the score
+            // evaluations that hang off them are independent chains
+            advance_to(kb + kk - 1);
+            D v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const Rec4<D> R = rec[kb + kk + u];
+              Ar = add_rn<D>(Ar, R.x);
+              Br = add_rn<D>(Br, R.y);
+              v[u] = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(Ar, Br, s_log), R.p);
+            }
+            kw = kb + kk + U - 1;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (v[u] > best) {
+                best = v[u];
+                arg = kb + kk + u;
+              }
+            thr = fmaxf(thr, screen_rd<D>(best));
+            nexact += U;
+          }
+        }
+      }
+    }
+    if (has_next) {
+      sbuf[(s + 1) & 1][tid] = nx;
+      if (GROUPB) stage_max(nx, (s + 1) & 1);
+    }
+  }
+  finish();
+}
+
+}  // namespace ps
