@@ -84,6 +84,18 @@ struct ScreenUB<DIST_POISSON, true> {  // A ln(A/B), either sign       score_imp
     const float e = fmaf(fabsf(t), 0.693147182464599609375f * 16.0f * SCR_U, fmaf(A, SCR_CA, pm));
     return fmaf(t, 0.693147182464599609375f, e);
   }
+  // One bound for every cell of a k-range of the row: A in [Af, Al], B >= Bf (the sums grow with k; needs a, b > 0 only, no
+  // sortedness).  f(A,B) = A ln(A/B) falls in B and is convex in A, so f <= max(f(Af,Bf), f(Al,Bf)) on the box.  Margins:
+  // the log term relative to |f| -- if the cell's f is negative and below the corner maximum m, then f (1 - 16u) <= m -/+ 16u |m|
+  // whatever the sign of m -- and 20u A with A <= Al.
+  static __device__ __forceinline__ float box(float Af, float Bf, float Al, float pm) {
+    const float rb = rcp_approx(Bf);
+    const float t1 = Af * lg2_approx(Af * rb);
+    const float t2 = Al * lg2_approx(Al * rb);
+    const float e1 = fmaf(fabsf(t1), 0.693147182464599609375f * 16.0f * SCR_U, t1 * 0.693147182464599609375f);
+    const float e2 = fmaf(fabsf(t2), 0.693147182464599609375f * 16.0f * SCR_U, t2 * 0.693147182464599609375f);
+    return fmaxf(e1, e2) + fmaf(Al, SCR_CA, pm);
+  }
 };
 template <>
 struct ScreenUB<DIST_GAUSSIAN, false> {  // (A > B) ? .5 (A^2/B + B) - A : 0 = (A-B)^2 / (2B)   score_impl.hpp:429-431
@@ -117,6 +129,17 @@ struct ScreenUB<DIST_RATIONAL, RP> {  // A^2 / B          score_impl.hpp:464-465
     return fmaf(gt, SCR_REL_UP, pm);
   }
 };
+
+// Bound for a whole k-range of a row from its first (Af, Bf) and last (Al, Bl) cell and the largest pm of the range.
+// Scores that never decrease when the range grows (ascending priorities): the bound at the last cell.  Poisson risk-part:
+// the box bound above.
+template <int DIST, bool RP>
+__device__ __forceinline__ float screen_range_ub(float Af, float Bf, float Al, float Bl, float pm) {
+  if constexpr (DIST == DIST_POISSON && RP)
+    return ScreenUB<DIST_POISSON, true>::box(Af, Bf, Al, pm);
+  else
+    return ScreenUB<DIST, RP>::eval(Al, Bl, pm);
+}
 
 // ---------------------------------------------------------------------------------------------
 // (P2) exact summability.  stats[inst] = {min over elements of the exponent of the lowest set bit, sum |.|}
@@ -348,6 +371,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
   // (q-1) r - (q^2-1)/2 >= (q-1)^2/2 (Gaussian mult-clust), 2 q r - q^2 >= q^2 (A^2/B, A^2/2B).  Poisson risk-part
   // (A ln(A/B), decreasing while q < 1/e) is not.
   constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
+  constexpr bool BOX = !GROUPB;  // Poisson risk-part: range tiers from the box bound, no sortedness needed
   __shared__ float4 sbuf[2][BK];
   __shared__ float s_pmax[2][BR / 32];  // per stage and warp: largest pm among the records that warp staged
   constexpr bool kLogTab = DBL && (DIST == DIST_POISSON);
@@ -379,7 +403,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
   int arg = -1;
   float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
   unsigned int nexact = 0, nviol = 0;
-  const bool mono = (FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0);
+  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
 
   auto exact_at = [&](const int k) -> D {
     const Rec4<D> R = rec[k];
@@ -425,7 +449,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
   };
 
-  if (GROUPB && mono) {
+  if (mono) {
     // tile tier: the bound at the tile's last cell with the largest pm of the tile's 128-blocks covers the whole tile
     bmax += (long long)inst * nblk;
     float tmax = -3.402823466e+38f;
@@ -433,7 +457,14 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     const Rec4<D> R = rec[k_hi];
     const float At = DBL ? __double2float_rn((double)R.x - (double)Xi) : __fadd_rn((float)R.x, bx);
     const float Bt = DBL ? __double2float_rn((double)R.y - (double)Yi) : __fadd_rn((float)R.y, by);
-    const bool lose = (i >= g.nrows) || (ScreenUB<DIST, RP>::eval(At, Bt, tmax) < thr);
+    float Af = At, Bf = Bt;
+    const int kf = max(k_lo, i + 1);  // the row's first cell in this tile
+    if (BOX) {
+      const Rec4<D> Q = rec[min(kf, k_hi)];
+      Af = DBL ? __double2float_rn((double)Q.x - (double)Xi) : __fadd_rn((float)Q.x, bx);
+      Bf = DBL ? __double2float_rn((double)Q.y - (double)Yi) : __fadd_rn((float)Q.y, by);
+    }
+    const bool lose = (i >= g.nrows) || (kf > k_hi) || (screen_range_ub<DIST, RP>(Af, Bf, At, Bt, tmax) < thr);
     const bool tile_dropped = __syncthreads_and(lose);
     if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
     if (tile_dropped) {
@@ -457,7 +488,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
     sbuf[0][tid] = r;
-    if (GROUPB) stage_max(r, 0);
+    stage_max(r, 0);
     if (DBL) onx = rec[k_lo - 1];
   }
   for (int s = 0; s < nstages; ++s) {
@@ -485,13 +516,14 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
       for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
     } else {
       bool skip = false;
-      if (GROUPB && mono) {
+      if (mono) {
         // stage tier: the bound at the stage's LAST cell with the stage's largest pm covers all 128 cells
         float pmx = s_pmax[s & 1][0];
 #pragma unroll
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
-        const float4 re = sb[BK - 1];
-        const float ubs = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), pmx);
+        const float4 re = sb[BK - 1], rf = sb[0];
+        const float ubs = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                    __fadd_rn(re.y, by), pmx);
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
       if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
@@ -501,10 +533,10 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
       } else {
 #pragma unroll 1
         for (int kk = 0; kk < BK; kk += U) {
-          if (GROUPB && mono) {
-            const float4 re = sb[kk + U - 1];
-            const float ubg =
-                ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), screen_gmax_of<D>(re));
+          if (mono) {
+            const float4 re = sb[kk + U - 1], rf = sb[kk];
+            const float ubg = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                        __fadd_rn(re.y, by), screen_gmax_of<D>(re));
             const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
             if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
             if (gdrop) {
@@ -557,7 +589,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     }
     if (has_next) {
       sbuf[(s + 1) & 1][tid] = nx;
-      if (GROUPB) stage_max(nx, (s + 1) & 1);
+      stage_max(nx, (s + 1) & 1);
     }
   }
   if (i < g.nrows) {

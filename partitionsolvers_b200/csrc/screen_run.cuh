@@ -209,6 +209,7 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
   constexpr int U = 8;
   constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
   constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
+  constexpr bool BOX = !GROUPB;  // Poisson risk-part: range tiers from the box bound, no sortedness needed
   __shared__ float4 sbuf[2][BK];
   __shared__ float s_pmax[2][BR / 32];
   constexpr bool kLogTab = (DIST == DIST_POISSON);
@@ -243,7 +244,7 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
   int arg = -1;
   float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
   unsigned int nexact = 0, nviol = 0;
-  const bool mono = (FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0);
+  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
 
   // the reference's running sums of row i through cell kw (warp-uniform kw); a tile right of the diagonal starts from the
   // checkpoint the level-1 pass left at its chunk boundary (loaded on first use)
@@ -348,13 +349,16 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
     return;
   }
 
-  if (GROUPB && mono) {
+  if (mono) {
     bmax += (long long)inst * nblk;
     float tmax = -3.402823466e+38f;
     for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
     float At, Bt;
     fsum(pfx[k_hi], At, Bt);
-    const bool lose = (i >= g.nrows) || (ScreenUB<DIST, RP>::eval(At, Bt, tmax) < thr);
+    float Af = At, Bf = Bt;
+    const int kf = max(k_lo, i + 1);  // the row's first cell in this tile
+    if (BOX) fsum(pfx[min(kf, k_hi)], Af, Bf);
+    const bool lose = (i >= g.nrows) || (kf > k_hi) || (screen_range_ub<DIST, RP>(Af, Bf, At, Bt, tmax) < thr);
     const bool tile_dropped = __syncthreads_and(lose);
     if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
     if (tile_dropped) {
@@ -378,7 +382,7 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
     sbuf[0][tid] = r;
-    if (GROUPB) stage_max(r, 0);
+    stage_max(r, 0);
     onx = pfx[k_lo - 1];
   }
   for (int s = 0; s < nstages; ++s) {
@@ -398,12 +402,13 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
       for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
     } else {
       bool skip = false;
-      if (GROUPB && mono) {
+      if (mono) {
         float pmx = s_pmax[s & 1][0];
 #pragma unroll
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
-        const float4 re = sb[BK - 1];
-        const float ubs = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), pmx);
+        const float4 re = sb[BK - 1], rf = sb[0];
+        const float ubs = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                    __fadd_rn(re.y, by), pmx);
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
       if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
@@ -413,9 +418,10 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
       } else {
 #pragma unroll 1
         for (int kk = 0; kk < BK; kk += U) {
-          if (GROUPB && mono) {
-            const float4 re = sb[kk + U - 1];
-            const float ubg = ScreenUB<DIST, RP>::eval(__fadd_rn(re.x, bx), __fadd_rn(re.y, by), re.z);
+          if (mono) {
+            const float4 re = sb[kk + U - 1], rf = sb[kk];
+            const float ubg = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                        __fadd_rn(re.y, by), re.z);
             const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
             if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
             if (gdrop) {
@@ -472,7 +478,7 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
     }
     if (has_next) {
       sbuf[(s + 1) & 1][tid] = nx;
-      if (GROUPB) stage_max(nx, (s + 1) & 1);
+      stage_max(nx, (s + 1) & 1);
     }
   }
   finish();
