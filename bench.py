@@ -479,6 +479,25 @@ def main():
             small[nm] = {"n": c["n"], "T": c["T"], "dtype": np.dtype(dt_small).name,
                          "ms_per_call_host_buffers": 1e3 * (time.perf_counter() - t0) / 20}
         line["small_configs"] = small
+        # ---- every score of BASELINE configs[2] at full size (n=100000, T=16): Poisson on planted counts, Gaussian and
+        # Rational on the real-valued mixture of solver_tests.py:145-146; device-timed host-buffer calls, best of 3
+        if rank == 0:
+            names = {0: "gaussian", 1: "poisson", 2: "rational"}
+            per_score = {}
+            for dt_s in (np.float64, np.float32):
+                a_p, b_p = synth.CONFIGS["C3"]["gen"](dt_s)
+                a_g, b_g = synth.CONFIGS["C3R"]["gen"](dt_s)
+                for d_s, rp_s in ((1, False), (1, True), (0, False), (0, True), (2, False)):
+                    aa, bb = (a_p, b_p) if d_s == 1 else (a_g, b_g)
+                    best = 1e30
+                    for _ in range(3):
+                        ctx.solve_raw(aa, bb, T, d_s, rp_s, dtype=dt_s, want_perm=False)
+                        best = min(best, ctx.timings()["total_ms"])
+                    key = f"{names[d_s]}_{'rp' if rp_s else 'mc'}_{'f64' if dt_s == np.float64 else 'f32'}"
+                    per_score[key] = {"ms": best, "value": synth.nominal_cells(n, T) / (best * 1e-3),
+                                      "level_kernel": {0: "exhaustive", 1: "screened, exact sums",
+                                                       2: "screened, running sums"}[ctx.timings()["screen_used"]]}
+            line["c3_all_scores"] = per_score
         if world > 1:
             # ---- one large instance, rows of every level sharded block-cyclically over the ranks with an NCCL
             # all-gather of the level vector per level (BASELINE configs[4] shape at a size that runs in seconds)

@@ -593,8 +593,14 @@ level1_running_kernel(int n, int L, int nch_alloc, long long rec_stride, int dis
             B = add_rn<D>(B, sb[kk].y);
           }
         }
+      } else if (cnt == BK) {
+        // full stage: constant trip count, so the loop is nothing but LDS.128 + two dependent adds per cell
+#pragma unroll 16
+        for (int kk = 0; kk < BK; ++kk) {
+          A = add_rn<D>(A, sb[kk].x);
+          B = add_rn<D>(B, sb[kk].y);
+        }
       } else {
-#pragma unroll 8
         for (int kk = 0; kk < cnt; ++kk) {
           A = add_rn<D>(A, sb[kk].x);
           B = add_rn<D>(B, sb[kk].y);
