@@ -52,6 +52,9 @@ struct Geom {
   // rb_first + rb_step * m, m = 0..NRB-1 (NRB counts OWNED blocks).  Unsharded: 0, 1.
   int rb_first, rb_step;
   const int2* tile_map;   // optional table tile -> (rb, c) in launch order; nullptr = decode arithmetically
+  // SA/SB checkpoints may be kept at a finer spacing than the k-chunks (screen_run.cuh, float inputs): the sums at chunk
+  // boundary c L live in row c * sa_mul of arrays with sa_nch rows per instance.  Default: 1, nch_alloc.
+  int sa_mul, sa_nch;
 };
 
 __host__ __device__ inline int geom_count_tiles(int NCH, int G, int NRB, int rb_first, int rb_step) {
@@ -419,8 +422,9 @@ last_level_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
   const int k_lo = c * g.L + 1, k_hi = min((c + 1) * g.L, g.kmax);
   const D X0 = rec[0].x, Y0 = rec[0].y;  // PREFIX: scan values at row 0 (= 0)
   if (tid == 0) {
-    carry[0] = (RUNNING && c > 0) ? SA[inst * pstride + (long long)c * g.n] : (D)0;
-    carry[1] = (RUNNING && c > 0) ? SB[inst * pstride + (long long)c * g.n] : (D)0;
+    const long long so = inst * (long long)g.sa_nch * g.n + (long long)c * g.sa_mul * g.n;
+    carry[0] = (RUNNING && c > 0) ? SA[so] : (D)0;
+    carry[1] = (RUNNING && c > 0) ? SB[so] : (D)0;
   }
   D best = Lim<D>::lowest();
   int arg = -1;

@@ -39,7 +39,7 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp, fxinfo, pfx;
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp, fxinfo, pfx, cpA, cpB, ipos;
   int stamp = 0;  // last stamp handed to a screened level (tile_stamp holds the stamp of the level that wrote a tile)
   int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
@@ -246,6 +246,27 @@ struct ScreenRunLaunch {
   }
 };
 
+struct ScreenRun32Launch {
+  using Fn = void (*)(ps::Geom, const ps::Rec4<float>*, const float*, const float*, long long, const int*, const float*,
+                      float*, int*, unsigned long long*, const int*, const float*, int, int*, int, int);
+  using LbFn = void (*)(ps::Geom, const ps::Rec4<float>*, float4*, const float*, const float*, long long, float*, float*,
+                        int);
+  static bool supported(int dist, int rp) { return dist == PS_DIST_RATIONAL || (dist == PS_DIST_GAUSSIAN && rp); }
+  static Fn pick(int dist, int rp, int audit) {
+    using namespace ps;
+    if (dist == PS_DIST_GAUSSIAN && rp)
+      return audit ? (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, true, true, BR>
+                   : (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, true, false, BR>;
+    return audit ? (Fn)level_tile_screen_run32_kernel<DIST_RATIONAL, false, true, BR>
+                 : (Fn)level_tile_screen_run32_kernel<DIST_RATIONAL, false, false, BR>;
+  }
+  static LbFn pick_lb(int dist, int rp) {
+    using namespace ps;
+    if (dist == PS_DIST_GAUSSIAN && rp) return (LbFn)screen_lb_run32_kernel<DIST_GAUSSIAN, true>;
+    return (LbFn)screen_lb_run32_kernel<DIST_RATIONAL, false>;
+  }
+};
+
 ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int rb_step, int tile_rows = BR) {
   ps::Geom g;
   g.n = n;
@@ -262,6 +283,8 @@ ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int
   g.rb_step = rb_step;
   g.ntiles = ps::geom_count_tiles(g.NCH, g.G, g.NRB, rb_first, rb_step);
   g.tile_map = nullptr;
+  g.sa_mul = 1;
+  g.sa_nch = nch_alloc;
   return g;
 }
 
@@ -404,7 +427,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       ps::screen_stats_init_kernel<<<cdiv(R, 256), 256, 0, st>>>(R, d_st);
       const int bx = std::max(1, std::min(cdiv(n, 256 * 4), std::max(1, 2048 / R)));
       ps::screen_stats_kernel<D><<<dim3(bx, R), 256, 0, st>>>(n, d_a, d_b, d_st);
-      ps::screen_decide_kernel<D><<<cdiv(R, 256), 256, 0, st>>>(R, d_st, (int*)ctx->scalar.p);
+      ps::screen_decide_kernel<D><<<cdiv(R, 256), 256, 0, st>>>(R, d_st, (int*)ctx->scalar.p, n);
       ctx->launches += 3;
       if (sizeof(D) == 8) {  // fixed-point shifts and conditions of the running-sum screen (screen_run.cuh) -> flag bit 3
         PS_TRY(ensure(ctx, ctx->fxinfo, (size_t)R * sizeof(ps::FxInfo)));
@@ -427,7 +450,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   ps::Rec4<D>* recs[2] = {rec0, rec1};
   const D* d_as = (const D*)ctx->a_s.p;
   const D* d_bs = (const D*)ctx->b_s.p;
-  int fast = 0, screen = 0, screen_run = 0;
+  int fast = 0, screen = 0, screen_run = 0, screen_run32 = 0;
+  const int cp_rows = n / ps::SCR_BLOCK + 1;  // float running-sum screen: one checkpoint row per 128-block boundary
   if (want_fast) {  // the precheck ran right after the inputs arrived; its flags are on the host by now
     PS_CUDA(ctx, cudaEventSynchronize(e_flags));
     host_flags = *ctx->pinned_flags;
@@ -438,6 +462,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     // (measured crossover against the exhaustive kernel: n ~ 16000, tools/run_c3r.py; audit runs take it at any size)
     screen_run = want_screen && fast && !screen && sizeof(D) == 8 && (host_flags & 8) == 0 &&
                  (n >= 16384 || p.screen == 2);
+    // float inputs whose sums round, A^2/B scores: bounds from the running sums themselves (per-block checkpoints)
+    screen_run32 = want_screen && fast && !screen && sizeof(D) == 4 && ScreenRun32Launch::supported(p.dist, rp) &&
+                   (host_flags & 16) == 0 && (n >= 16384 || p.screen == 2) &&
+                   (double)R * cp_rows * n * 8.0 <= 8e9;
   }
   if (screen) running = 0;  // exactly summable: prefix differences ARE the reference's running sums, bit for bit
   if (running) {
@@ -467,7 +495,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
   // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);
   // at most ~200 chunks so that the per-chunk partials stay small
-  if ((screen || screen_run) && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
+  if ((screen || screen_run || screen_run32) && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
   const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
   const long long pstride = (long long)nch_alloc * n;
   PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
@@ -494,16 +522,30 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 8 * sizeof(unsigned long long), st));
     return PS_OK;
   };
+  // checkpoints of the running sums: at the k-chunk boundaries, or (float running-sum screen) at every 128-block boundary
+  const int sa_L = screen_run32 ? ps::SCR_BLOCK : L;
+  const int sa_nch = screen_run32 ? cp_rows : nch_alloc;
   if (running) {
-    if (nch_alloc > 1) {
-      PS_TRY(ensure(ctx, ctx->SA, R * pstride * sizeof(D)));
-      PS_TRY(ensure(ctx, ctx->SB, R * pstride * sizeof(D)));
-      d_SA = (D*)ctx->SA.p;
-      d_SB = (D*)ctx->SB.p;
+    if (sa_nch > 1) {
+      DevBuf& bufA = screen_run32 ? ctx->cpA : ctx->SA;
+      DevBuf& bufB = screen_run32 ? ctx->cpB : ctx->SB;
+      PS_TRY(ensure(ctx, bufA, (size_t)R * sa_nch * n * sizeof(D)));
+      PS_TRY(ensure(ctx, bufB, (size_t)R * sa_nch * n * sizeof(D)));
+      d_SA = (D*)bufA.p;
+      d_SB = (D*)bufB.p;
     }
     ps::level1_running_kernel<D, BR><<<dim3(cdiv(n, BR), R), BR, 0, st>>>(
-        n, L, nch_alloc, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
+        n, sa_L, sa_nch, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
         0, 1, nullptr);
+    if constexpr (sizeof(D) == 4) {
+      if (screen_run32) {
+        PS_TRY(ensure(ctx, ctx->ipos, (size_t)R * sizeof(int)));
+        PS_CUDA(ctx, cudaMemsetAsync(ctx->ipos.p, 0, (size_t)R * sizeof(int), st));
+        ps::ipos_kernel<<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, d_as, (int*)ctx->ipos.p);
+        ctx->launches++;
+        PS_TRY(screen_buffers());
+      }
+    }
     if constexpr (sizeof(D) == 8) {
       if (screen_run) {
         PS_TRY(ensure(ctx, ctx->recf, 2 * R * rec_stride * sizeof(float4)));
@@ -568,6 +610,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (j == Tc && Tc >= 2) {
       // last level: row 0 only -> k-parallel kernel, one CTA per chunk (128-row geometry)
       g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, BR);
+      g.sa_mul = L / sa_L;
+      g.sa_nch = sa_nch;
       fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
     } else {
       if (g.ntiles >= 2048) {
@@ -581,7 +625,20 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         }
         g.tile_map = (const int2*)ctx->tile_map.p;
       }
-      if (screen_run) {
+      if (screen_run32) {
+        if constexpr (sizeof(D) == 4) {
+          auto fn_lb32 = ScreenRun32Launch::pick_lb(p.dist, rp);
+          auto fn_run32 = ScreenRun32Launch::pick(p.dist, rp, p.screen == 2);
+          const long long cp_stride = (long long)cp_rows * n;
+          fn_lb32<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, (float4*)rin, d_SA, d_SB, cp_stride, d_lb,
+                                                               (float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2);
+          fn_run32<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, cp_stride, (const int*)ctx->ipos.p, d_lb, d_pv,
+                                                     d_pa, d_cnt, (const int*)ctx->scalar.p,
+                                                     (const float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2,
+                                                     (int*)ctx->tile_stamp.p, ++ctx->stamp, cdiv(n, BR));
+          ctx->launches++;
+        }
+      } else if (screen_run) {
         if constexpr (sizeof(D) == 8) {
           auto fn_lbr = ScreenRunLaunch::pick_lb(p.dist, rp);
           auto fn_run = ScreenRunLaunch::pick(p.dist, rp, p.screen == 2);
@@ -611,7 +668,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
         g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
         ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
-        ((screen || screen_run) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp, cdiv(n, BR));
+        ((screen || screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp,
+        cdiv(n, BR));
     ctx->launches += 2;
     if (timed) {
       lev_ev.push_back({e0, e1});
@@ -630,8 +688,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   ps::backtrace_bounds_kernel<<<cdiv((long long)R * nS, 128), 128, 0, st>>>(R, n, Tc, p.sweep ? 1 : 0, d_ns,
                                                                            d_bounds);
   ps::backtrace_scores_kernel<D><<<cdiv((long long)R * nS * Tc, 128), 128, 0, st>>>(
-      R, n, Tc, p.sweep ? 1 : 0, p.dist, rp, running, d_bounds, d_as, d_bs, rec0, rec_stride, d_SA, d_SB, L,
-      nch_alloc, d_scores);
+      R, n, Tc, p.sweep ? 1 : 0, p.dist, rp, running, d_bounds, d_as, d_bs, rec0, rec_stride, d_SA, d_SB, sa_L,
+      sa_nch, d_scores);
   ctx->launches += 2;
   PS_CUDA(ctx, cudaGetLastError());
   PS_TRY(mark(ctx, &e_bt));
@@ -648,12 +706,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(copy_out(res->subset_scores, d_scores, (size_t)R * nS * Tc * sizeof(D)));
   PS_TRY(copy_out(res->max_score, d_ms, R * table_stride * sizeof(D)));
   PS_TRY(copy_out(res->next_start, d_ns, R * table_stride * sizeof(int)));
-  if (screen || screen_run)
+  if (screen || screen_run || screen_run32)
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   PS_TRY(mark(ctx, &e_end));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
-  ctx->tm.screen_used = screen ? 1 : (screen_run ? 2 : 0);
-  if (screen || screen_run) {
+  ctx->tm.screen_used = screen ? 1 : ((screen_run || screen_run32) ? 2 : 0);
+  if (screen || screen_run || screen_run32) {
     unsigned long long cnt[8];
     memcpy(cnt, ctx->pinned_flags + 2, sizeof(cnt));
     ctx->tm.screen_exact_cells = (long long)cnt[0] * 32;
@@ -1021,7 +1079,7 @@ void ps_destroy(ps_ctx* ctx) {
                     &ctx->a_s,   &ctx->b_s,      &ctx->rec,      &ctx->SA,      &ctx->SB,     &ctx->part_val,
                     &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->sort_hist,
                     &ctx->scalar, &ctx->recf,    &ctx->lb,       &ctx->scr_stats, &ctx->scr_counters, &ctx->tile_map,
-                    &ctx->scr_bmax, &ctx->tile_stamp, &ctx->fxinfo, &ctx->pfx};
+                    &ctx->scr_bmax, &ctx->tile_stamp, &ctx->fxinfo, &ctx->pfx, &ctx->cpA, &ctx->cpB, &ctx->ipos};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);

@@ -216,9 +216,10 @@ screen_stats_kernel(int n, const D* __restrict__ a, const D* __restrict__ b, Scr
   }
 }
 template <typename D>
-__global__ void screen_decide_kernel(int R, const ScreenStats* __restrict__ st, int* __restrict__ flags) {
+__global__ void screen_decide_kernel(int R, const ScreenStats* __restrict__ st, int* __restrict__ flags, int n = 0) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
+  if (st[r].n_nonpos > n / 8) atomicOr(flags, 16);  // too many rows without bounds for the running-sum screens
   constexpr int P = (sizeof(D) == 8) ? 53 : 24;
   // the double sums are exact whenever the instance qualifies; the 2^-20 slack covers their rounding when it does not
   const double slack = 1.0 - 9.5367431640625e-07;

@@ -484,4 +484,308 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
   finish();
 }
 
+
+// =====================================================================================================================
+// FLOAT inputs whose sums round.  The reference's float running sums carry up to m u of rounding after m terms, so no
+// bound derived from the TRUE sums can be tight.  Here every sum a bound is formed from IS a reference running sum:
+//   * the level-1 pass leaves every row's running sums at EVERY 128-block boundary (checkpoints, 8 n^2/128 bytes);
+//   * the tile and stage tiers take the row's sums at the end of the tile / stage straight from the checkpoints;
+//   * a stage that survives is walked from its starting checkpoint (one packed FADD2 per cell), group by group; the group
+//     tier bounds at the group's last cell, the cell tier at every cell, survivors are evaluated on the spot.
+// Supported scores: the A^2/B family (Rational, Gaussian risk-part).  Monotonicity on the running sums themselves: adding an
+// element with priority r to sums (A, B), q = A/B, changes A^2/B by b (2 q r - q^2) >= 0 whenever r >= q/2; the running
+// ratio exceeds the true ratio of the range (<= r, priorities ascending) by at most a factor 1 + 2 m u < 2.  The m' additions
+// between a cell and the cell the bound is formed at round: S(k') >= S(k) (1 - 3 m' u), carried as 1 + 64u (group, m' <= 7),
+// 1 + 512u (stage) and 1 + (3 L + 64) u (tile).  The cell tier needs no monotonicity: its inputs are exact, the margins of
+// screen.cuh cover MUFU.RCP, the bound's own roundings and the reference's.  Rows i < ipos (some a <= 0 to their right) take
+// no bounds.  Audit mode re-evaluates every dropped cell.
+// =====================================================================================================================
+__global__ void ipos_kernel(int n, const float* __restrict__ as, int* __restrict__ ipos) {
+  const int inst = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = 0;
+  if (k < n && !(as[(long long)inst * n + k] > 0.f)) v = k + 1;
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(&ipos[inst], v);
+}
+
+// Row lower bounds from checkpoint cells (i, 128 m): a coarse sweep over the row's blocks, then every block around the best.
+template <int DIST, bool RP>
+__global__ void __launch_bounds__(128)
+screen_lb_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, float4* __restrict__ recf,
+                       const float* __restrict__ SA, const float* __restrict__ SB, long long cp_stride,
+                       float* __restrict__ LB, float* __restrict__ bmax, int nblk) {
+  using D = float;
+  const int inst = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nrows) return;
+  rec += (long long)inst * g.rec_stride;
+  recf += (long long)inst * g.rec_stride;
+  SA += inst * cp_stride;
+  SB += inst * cp_stride;
+  if ((i & (SCR_BLOCK - 1)) == 0) {
+    float m = -3.402823466e+38f;
+    const int ke = min(i + SCR_BLOCK, g.n);
+    for (int k = i + 1; k <= ke; ++k) m = fmaxf(m, screen_pm_of<D>(recf[k]));
+    bmax[(long long)inst * nblk + i / SCR_BLOCK] = m;
+  }
+  if ((i & 7) == 0 && i + 8 <= g.n) {
+    float m = screen_pm_of<D>(recf[i + 1]);
+#pragma unroll
+    for (int q = 2; q <= 8; ++q) m = fmaxf(m, screen_pm_of<D>(recf[i + q]));
+    recf[i + 8].w = m;
+  }
+  const int m0 = i / SCR_BLOCK + 1, m1 = g.kmax / SCR_BLOCK;  // boundaries 128 m in (i, kmax]
+  D best = Lim<D>::lowest();
+  int mb = m0;
+  auto probe = [&](int m) {
+    const D A = SA[(long long)m * g.n + i], B = SB[(long long)m * g.n + i];
+    const D v = add_rn<D>(screen_exact_score<D, DIST, RP, false>(A, B, nullptr), rec[m * SCR_BLOCK].p);
+    if (v > best) {
+      best = v;
+      mb = m;
+    }
+  };
+  if (m1 >= m0) {
+    const int len = m1 - m0 + 1;
+    const int sc = max(1, len / 32);
+    for (int m = m0; m <= m1; m += sc) probe(m);
+    probe(m1);
+    if (sc > 1) {
+      const int lo = max(m0, mb - sc), hi = min(m1, mb + sc);
+      for (int m = lo; m <= hi; ++m) probe(m);
+    }
+  }
+  LB[(long long)inst * g.n + i] = best;
+}
+
+template <int DIST, bool RP, bool AUDIT, int BR>
+__global__ void __launch_bounds__(BR)
+level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, const float* __restrict__ SA,
+                               const float* __restrict__ SB, long long cp_stride, const int* __restrict__ ipos,
+                               const float* __restrict__ LB, float* __restrict__ part_val, int* __restrict__ part_arg,
+                               unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
+                               const float* __restrict__ bmax, int nblk, int* __restrict__ tile_stamp, int stamp,
+                               int stamp_stride) {
+  using D = float;
+  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
+  static_assert(DIST == DIST_RATIONAL || (DIST == DIST_GAUSSIAN && RP), "A^2/B family");
+  constexpr int BK = BR;
+  constexpr int U = 8;
+  constexpr float REL_GROUP = 1.0f + 64.0f * SCR_U, REL_STAGE = 1.0f + 512.0f * SCR_U;
+  __shared__ float4 sbuf[2][BK];
+  __shared__ float s_pmax[2][BR / 32];
+
+  const int inst = blockIdx.y;
+  rec += (long long)inst * g.rec_stride;
+  LB += (long long)inst * g.n;
+  SA += inst * cp_stride;
+  SB += inst * cp_stride;
+  const long long pstride = (long long)g.nch_alloc * g.n;
+  part_val += inst * pstride;
+  part_arg += inst * pstride;
+  const float4* __restrict__ recf = reinterpret_cast<const float4*>(rec);
+
+  int rb, c;
+  decode_tile(g, blockIdx.x, rb, c);
+  const int tid = threadIdx.x;
+  const int i0 = rb * BR;
+  const int i = i0 + tid;
+  const int k_lo = max(c * g.L + 1, i0 + 1);
+  const int k_hi = min((c + 1) * g.L, g.kmax);
+  const bool diag_tile = (c == rb / g.G);
+  const int il = min(i, g.n - 1);
+
+  D best = Lim<D>::lowest();
+  int arg = -1;
+  float thr = LB[min(il, max(g.nrows - 1, 0))];
+  unsigned int nexact = 0, nviol = 0;
+  const bool mono = dev_flags && (dev_flags[1] == 0);
+  // running sums through cell kb - 1 at the top of every stage
+  float2 S = make_float2(0.f, 0.f);
+  auto checkpoint = [&](const int kbnd) -> float2 {  // kbnd: multiple of 128, > i for every row of the block
+    const long long o = (long long)(kbnd / SCR_BLOCK) * g.n + il;
+    return make_float2(SA[o], SB[o]);
+  };
+  auto step = [&](const float4 r) { S = __fadd2_rn(S, make_float2(r.x, r.y)); };
+  auto exact_here = [&](const float4 r) -> D {
+    return add_rn<D>(screen_exact_score<D, DIST, RP, false>(S.x, S.y, nullptr), r.z);
+  };
+  // one cell on its own (diagonal, ragged, forced and audit paths): walk, bound, vote, evaluate
+  auto cell = [&](const int k, const float4 r, const bool valid, const bool forced) {
+    if (valid) step(r);
+    const float ub = ScreenUB<DIST, RP>::eval(S.x, S.y, screen_pm_of<D>(r));
+    const bool pass = valid && (forced || !(ub < thr));
+    if (__any_sync(0xffffffffu, pass)) {
+      const D v = exact_here(r);
+      if (AUDIT && valid && !forced && (double)ub < (double)v) ++nviol;
+      ++nexact;
+      if (valid && v > best) {
+        best = v;
+        arg = k;
+        thr = fmaxf(thr, best);
+      }
+    } else if (AUDIT && valid) {
+      if (!(exact_here(r) < thr)) ++nviol;
+    }
+  };
+  // audit of a dropped k-range [ka, kb]: walk it and check every cell against the threshold it was dropped with
+  auto audit_range = [&](const int ka, const int kb) {
+    for (int k = ka; k <= kb; ++k) {
+      const float4 r = recf[k];
+      if (k > i) {
+        step(r);
+        if (i < g.nrows && !(exact_here(r) < thr)) ++nviol;
+      }
+    }
+  };
+  auto stage_max = [&](const float4 r, const int buf) {
+    float w = ((tid & 7) == 7) ? r.w : -3.402823466e+38f;
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 8));
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 16));
+    if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
+  };
+  auto flush_counters = [&]() {
+    if (counters) {
+      if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
+      if (AUDIT) {
+        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+      }
+    }
+  };
+  if (!diag_tile) S = checkpoint(c * g.L);
+
+  const bool forced = (i0 < ipos[inst]);
+  if (!forced && mono && (k_hi % SCR_BLOCK) == 0 && k_hi >= i0 + BR) {
+    // tile tier: the row's sums at the tile's last cell are a checkpoint
+    bmax += (long long)inst * nblk;
+    float tmax = -3.402823466e+38f;
+    for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
+    const float2 E = checkpoint(k_hi);
+    const float rel = 1.0f + (3.0f * (float)g.L + 64.0f) * SCR_U;
+    const bool lose = (i >= g.nrows) || (ScreenUB<DIST, RP>::eval(E.x, E.y, tmax) * rel < thr);
+    const bool tile_dropped = __syncthreads_and(lose);
+    if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
+    if (tile_dropped) {
+      if (AUDIT) audit_range(k_lo, k_hi);
+      if (!tile_stamp && i < g.nrows) {
+        part_val[(long long)c * g.n + i] = best;
+        part_arg[(long long)c * g.n + i] = arg;
+      }
+      nexact = 0;
+      flush_counters();
+      return;
+    }
+  }
+  const int nk = k_hi - k_lo + 1;
+  const int nstages = (nk + BK - 1) / BK;
+  {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
+    sbuf[0][tid] = r;
+    stage_max(r, 0);
+  }
+  for (int s = 0; s < nstages; ++s) {
+    __syncthreads();
+    const int kb = k_lo + s * BK;
+    const int kn = kb + BK + tid;
+    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_next = (s + 1 < nstages);
+    if (has_next && kn <= k_hi) nx = recf[kn];
+    const int cnt = min(BK, k_hi - kb + 1);
+    const float4* __restrict__ sb = sbuf[s & 1];
+    if (kb <= i0 + BR - 1 || cnt < BK || forced) {
+      // diagonal stage (row i only sees k > i), ragged last stage, rows that take no bounds: cell by cell
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, forced);
+    } else {
+      const float2 E = checkpoint(kb + BK - 1);  // the row's sums at the stage's last cell
+      bool skip = false;
+      if (mono) {
+        float pmx = s_pmax[s & 1][0];
+#pragma unroll
+        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
+        const float ubs = ScreenUB<DIST, RP>::eval(E.x, E.y, pmx) * REL_STAGE;
+        skip = !__any_sync(0xffffffffu, !(ubs < thr));
+      }
+      if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
+      if (skip) {
+        if (AUDIT) {
+          for (int kk = 0; kk < BK; ++kk) {
+            step(sb[kk]);
+            if (!(exact_here(sb[kk]) < thr)) ++nviol;
+          }
+        }
+        S = E;
+      } else {
+#pragma unroll 1
+        for (int kk = 0; kk < BK; kk += U) {
+          float2 W[U];  // the row's running sums at the U cells of the group
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            step(sb[kk + u]);
+            W[u] = S;
+          }
+          if (mono) {
+            const float ubg = ScreenUB<DIST, RP>::eval(W[U - 1].x, W[U - 1].y, sb[kk + U - 1].w) * REL_GROUP;
+            const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
+            if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
+            if (gdrop) {
+              if (AUDIT) {
+#pragma unroll 1
+                for (int u = 0; u < U; ++u) {
+                  const D v = add_rn<D>(screen_exact_score<D, DIST, RP, false>(W[u].x, W[u].y, nullptr), sb[kk + u].z);
+                  if (!(v < thr)) ++nviol;
+                }
+              }
+              continue;
+            }
+          }
+          bool alive = false;
+          float ub[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            ub[u] = ScreenUB<DIST, RP>::eval(W[u].x, W[u].y, screen_pm_of<D>(sb[kk + u]));
+            alive |= !(ub[u] < thr);
+          }
+          const bool ev = __any_sync(0xffffffffu, alive);
+          if (AUDIT || ev) {
+            D v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              v[u] = add_rn<D>(screen_exact_score<D, DIST, RP, false>(W[u].x, W[u].y, nullptr), sb[kk + u].z);
+            if (AUDIT) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                if ((double)ub[u] < (double)v[u]) ++nviol;  // a cell bound that was too low
+                if (!ev && !(v[u] < thr)) ++nviol;           // a dropped cell that does not lose
+              }
+            }
+            if (ev) {
+#pragma unroll
+              for (int u = 0; u < U; ++u)
+                if (v[u] > best) {
+                  best = v[u];
+                  arg = kb + kk + u;
+                }
+              thr = fmaxf(thr, best);
+              nexact += U;
+            }
+          }
+        }
+      }
+    }
+    if (has_next) {
+      sbuf[(s + 1) & 1][tid] = nx;
+      stage_max(nx, (s + 1) & 1);
+    }
+  }
+  if (i < g.nrows) {
+    part_val[(long long)c * g.n + i] = best;
+    part_arg[(long long)c * g.n + i] = arg;
+  }
+  if (tile_stamp && tid == 0) tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + rb] = stamp;
+  flush_counters();
+}
+
 }  // namespace ps

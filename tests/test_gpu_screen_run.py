@@ -114,8 +114,8 @@ def test_conditions_of_the_fixed_point_bounds(ctx):
     scr = ctx.solve_raw(a3, b, T, 1, False, dtype=F64, levels=True)
     assert ctx.timings()["screen_used"] == 2
     _same_tables(exh, scr)
-    # float inputs keep the exhaustive kernel (their running sums carry m u_float of rounding)
-    ctx.solve_raw(a.astype(np.float32), b.astype(np.float32), T, 2, False, dtype=np.float32)
+    # float inputs: only the scores the float running-sum screen supports leave the exhaustive kernel
+    ctx.solve_raw(a.astype(np.float32), b.astype(np.float32), T, 1, False, dtype=np.float32)
     assert ctx.timings()["screen_used"] == 0
 
 
@@ -124,5 +124,70 @@ def test_full_size_rational(ctx):
     a, b = synth.CONFIGS["C3R"]["gen"](F64)
     exh = ctx.solve_raw(a, b, 4, 2, False, dtype=F64, levels=True, screen=1)
     scr = ctx.solve_raw(a, b, 4, 2, False, dtype=F64, levels=True, screen=0)
+    assert ctx.timings()["screen_used"] == 2
+    _same_tables(exh, scr)
+
+
+# ------------------------------------------------------------------------------------------------ float inputs
+F32 = np.float32
+F32_SCORES = [(0, True), (2, False)]  # the A^2/B family (screen_run.cuh, second half)
+
+
+@pytest.mark.parametrize("dist,rp", F32_SCORES)
+def test_float_running_screen_equals_exhaustive_and_audit_is_clean(ctx, dist, rp):
+    n, T = 20000, 6
+    for positive in (True, False):  # False: some a <= 0, the first row blocks take no bounds
+        a, b = _real_valued(n, 6, synth.SEED + 70, positive=positive)
+        a, b = a.astype(F32), b.astype(F32)
+        exh = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, levels=True, sweep=True, screen=1)
+        assert ctx.timings()["screen_used"] == 0
+        scr = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, levels=True, sweep=True, screen=0)
+        t = ctx.timings()
+        assert t["screen_used"] == 2
+        assert 0 < t["screen_exact_cells"] < 0.5 * sum(t["level_cells"][:-1])
+        _same_tables(exh, scr)
+        aud = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, levels=True, sweep=True, screen=2)
+        ta = ctx.timings()
+        assert ta["screen_used"] == 2 and ta["screen_violations"] == 0
+        _same_tables(exh, aud)
+
+
+def test_float_running_screen_matches_oracle(oracle, ctx):
+    n, T = 6100, 5
+    for name, (a, b) in (("tract", synth.tract_like(n, 4, seed=synth.SEED + 71, dtype=F32)),
+                         ("mixture", synth.gaussian_mixture(n, 5, seed=synth.SEED + 72, dtype=F32))):
+        for dist, rp in F32_SCORES:
+            ref = oracle.solve("port", a, b, T, dist, rp, dtype=F32)
+            raw = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, perm=ref["perm"], levels=True, screen=2)
+            t = ctx.timings()
+            assert t["screen_used"] == 2 and t["screen_violations"] == 0, (name, dist, rp)
+            assert np.array_equal(raw["next_start"], ref["next_start"]), (name, dist, rp)
+            assert np.array_equal(raw["max_score"], ref["max_score"]), (name, dist, rp)
+
+
+def test_float_running_screen_unsorted_permutation_and_batch(ctx):
+    n, T = 6500, 5
+    a, b = synth.gaussian_mixture(n, 5, seed=synth.SEED + 73, dtype=F32)
+    perm = np.random.RandomState(7).permutation(n).astype(np.int32)
+    for dist, rp in F32_SCORES:
+        exh = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, perm=perm, levels=True, screen=1)
+        aud = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, perm=perm, levels=True, screen=2)
+        t = ctx.timings()
+        assert t["screen_used"] == 2 and t["screen_violations"] == 0, (dist, rp)
+        _same_tables(exh, aud)
+    n, R = 16500, 3
+    ab = [synth.gaussian_mixture(n, 4 + r, seed=synth.SEED + 74 + r, dtype=F32) for r in range(R)]
+    a = np.stack([x[0] for x in ab])
+    b = np.stack([x[1] for x in ab])
+    exh = ctx.solve_raw(a, b, 4, 2, False, dtype=F32, levels=True, sweep=True, screen=1)
+    scr = ctx.solve_raw(a, b, 4, 2, False, dtype=F32, levels=True, sweep=True, screen=0)
+    assert ctx.timings()["screen_used"] == 2
+    _same_tables(exh, scr)
+
+
+def test_full_size_rational_float(ctx):
+    a, b = synth.CONFIGS["C3R"]["gen"](F32)
+    exh = ctx.solve_raw(a, b, 4, 2, False, dtype=F32, levels=True, screen=1)
+    scr = ctx.solve_raw(a, b, 4, 2, False, dtype=F32, levels=True, screen=0)
     assert ctx.timings()["screen_used"] == 2
     _same_tables(exh, scr)

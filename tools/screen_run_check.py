@@ -1,5 +1,5 @@
 """GPU check of the running-sum screened kernel (screen_run.cuh) on real-valued double inputs: tables identical to the
-exhaustive kernel (every maxScore_/nextStart_ cell), audit clean, timing.   python tools/screen_run_check.py [quick]"""
+exhaustive kernel (every maxScore_/nextStart_ cell), audit clean, timing.   python tools/screen_run_check.py [quick] [f32]"""
 import os
 import sys
 
@@ -8,10 +8,12 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from partitionsolvers_b200 import capi, synth  # noqa: E402
 
-quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+quick = "quick" in sys.argv[1:]
 ctx = capi.Context(0)
-dt = np.float64
+dt = np.float32 if "f32" in sys.argv[1:] else np.float64
 SCORES = ((1, False), (1, True), (0, False), (0, True), (2, False))
+if dt == np.float32:
+    SCORES = ((0, True), (2, False))  # the float running-sum screen covers the A^2/B family
 
 
 def gens(n, T):
