@@ -251,9 +251,12 @@ struct ScreenRun32Launch {
                       float*, int*, unsigned long long*, const int*, const float*, int, int*, int, int);
   using LbFn = void (*)(ps::Geom, const ps::Rec4<float>*, float4*, const float*, const float*, long long, float*, float*,
                         int);
-  static bool supported(int dist, int rp) { return dist == PS_DIST_RATIONAL || (dist == PS_DIST_GAUSSIAN && rp); }
+  static bool supported(int dist, int rp) { return dist == PS_DIST_RATIONAL || dist == PS_DIST_GAUSSIAN; }
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
+    if (dist == PS_DIST_GAUSSIAN && !rp)
+      return audit ? (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, false, true, BR>
+                   : (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, false, false, BR>;
     if (dist == PS_DIST_GAUSSIAN && rp)
       return audit ? (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, true, true, BR>
                    : (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, true, false, BR>;
@@ -262,6 +265,7 @@ struct ScreenRun32Launch {
   }
   static LbFn pick_lb(int dist, int rp) {
     using namespace ps;
+    if (dist == PS_DIST_GAUSSIAN && !rp) return (LbFn)screen_lb_run32_kernel<DIST_GAUSSIAN, false>;
     if (dist == PS_DIST_GAUSSIAN && rp) return (LbFn)screen_lb_run32_kernel<DIST_GAUSSIAN, true>;
     return (LbFn)screen_lb_run32_kernel<DIST_RATIONAL, false>;
   }

@@ -492,7 +492,7 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
 //   * the tile and stage tiers take the row's sums at the end of the tile / stage straight from the checkpoints;
 //   * a stage that survives is walked from its starting checkpoint (one packed FADD2 per cell), group by group; the group
 //     tier bounds at the group's last cell, the cell tier at every cell, survivors are evaluated on the spot.
-// Supported scores: the A^2/B family (Rational, Gaussian risk-part).  Monotonicity on the running sums themselves: adding an
+// Supported scores: the A^2/B family (Rational, Gaussian risk-part) and Gaussian mult-clust (run32_range_ub).  Monotonicity on the running sums themselves: adding an
 // element with priority r to sums (A, B), q = A/B, changes A^2/B by b (2 q r - q^2) >= 0 whenever r >= q/2; the running
 // ratio exceeds the true ratio of the range (<= r, priorities ascending) by at most a factor 1 + 2 m u < 2.  The m' additions
 // between a cell and the cell the bound is formed at round: S(k') >= S(k) (1 - 3 m' u), carried as 1 + 64u (group, m' <= 7),
@@ -500,6 +500,34 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
 // screen.cuh cover MUFU.RCP, the bound's own roundings and the reference's.  Rows i < ipos (some a <= 0 to their right) take
 // no bounds.  Audit mode re-evaluates every dropped cell.
 // =====================================================================================================================
+// Bound for every cell of a k-range of row i from the row's RUNNING sums (A, B) at the range's last cell k', the largest pm
+// of the range, span = number of additions between the range's first and last cell, len = k' - i.
+template <int DIST, bool RP>
+__device__ __forceinline__ float run32_range_ub(float A, float B, float pm, float span, float len) {
+  if constexpr (DIST == DIST_GAUSSIAN && !RP) {
+    // g = (A - B)^2 / (2B) for A > B, else 0.  Adding an element of priority r raises g whenever r >= (q + 1) / 2.  Along the
+    // exact continuation of the running sums q <= r (1 + 2 gam), gam = 1.01 len u, so a decrease needs q < 1 + 4.1 gam, where
+    // g <= 8.4 gam^2 B: every cell of the range has g <= g(end) + 8.4 gam^2 B(end).  The span roundings move (A, B) by span u
+    // relatively: |dg| <= 2 span u A (q - 1), and at most 2 (span u)^2 B where the sign of A - B flips.  Carried: 12 gam^2 B
+    // and (8 + 2 span + 8) u on A (q - 1).
+    const float gam = len * (1.01f * SCR_U);
+    const float slack = 12.0f * gam * gam;
+    if (A > B) {
+      const float dif = A - B;
+      const float h = dif * rcp_approx(B);
+      const float gt = (0.5f * dif) * h;
+      float e = fmaf(A * h, (2.0f * span + 16.0f) * SCR_U, pm);
+      e = fmaf(A, SCR_TINY, e);
+      e = fmaf(B, slack, e);
+      return fmaf(gt, SCR_REL_UP, e);
+    }
+    return fmaf(B, SCR_TINY + slack, pm);
+  } else {
+    // A^2/B family: S(k') >= S(k) (1 - 3 span u) on the running sums (header above)
+    return ScreenUB<DIST, RP>::eval(A, B, pm) * (1.0f + (3.0f * span + 40.0f) * SCR_U);
+  }
+}
+
 __global__ void ipos_kernel(int n, const float* __restrict__ as, int* __restrict__ ipos) {
   const int inst = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -569,10 +597,9 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
                                int stamp_stride) {
   using D = float;
   static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
-  static_assert(DIST == DIST_RATIONAL || (DIST == DIST_GAUSSIAN && RP), "A^2/B family");
+  static_assert(DIST == DIST_RATIONAL || DIST == DIST_GAUSSIAN, "A^2/B family and Gaussian mult-clust");
   constexpr int BK = BR;
   constexpr int U = 8;
-  constexpr float REL_GROUP = 1.0f + 64.0f * SCR_U, REL_STAGE = 1.0f + 512.0f * SCR_U;
   __shared__ float4 sbuf[2][BK];
   __shared__ float s_pmax[2][BR / 32];
 
@@ -663,8 +690,8 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
     float tmax = -3.402823466e+38f;
     for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
     const float2 E = checkpoint(k_hi);
-    const float rel = 1.0f + (3.0f * (float)g.L + 64.0f) * SCR_U;
-    const bool lose = (i >= g.nrows) || (ScreenUB<DIST, RP>::eval(E.x, E.y, tmax) * rel < thr);
+    const bool lose = (i >= g.nrows) ||
+                      (run32_range_ub<DIST, RP>(E.x, E.y, tmax, (float)(g.L + 8), (float)(k_hi - i)) < thr);
     const bool tile_dropped = __syncthreads_and(lose);
     if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
     if (tile_dropped) {
@@ -705,7 +732,7 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
         float pmx = s_pmax[s & 1][0];
 #pragma unroll
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
-        const float ubs = ScreenUB<DIST, RP>::eval(E.x, E.y, pmx) * REL_STAGE;
+        const float ubs = run32_range_ub<DIST, RP>(E.x, E.y, pmx, (float)(BK + 8), (float)(kb + BK - 1 - i));
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
       if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
@@ -727,7 +754,8 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
             W[u] = S;
           }
           if (mono) {
-            const float ubg = ScreenUB<DIST, RP>::eval(W[U - 1].x, W[U - 1].y, sb[kk + U - 1].w) * REL_GROUP;
+            const float ubg = run32_range_ub<DIST, RP>(W[U - 1].x, W[U - 1].y, sb[kk + U - 1].w, (float)U,
+                                                       (float)(kb + kk + U - 1 - i));
             const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
             if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
             if (gdrop) {

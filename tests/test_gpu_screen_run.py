@@ -130,7 +130,7 @@ def test_full_size_rational(ctx):
 
 # ------------------------------------------------------------------------------------------------ float inputs
 F32 = np.float32
-F32_SCORES = [(0, True), (2, False)]  # the A^2/B family (screen_run.cuh, second half)
+F32_SCORES = [(0, False), (0, True), (2, False)]  # Gaussian and Rational (screen_run.cuh, second half)
 
 
 @pytest.mark.parametrize("dist,rp", F32_SCORES)

@@ -13,7 +13,7 @@ ctx = capi.Context(0)
 dt = np.float32 if "f32" in sys.argv[1:] else np.float64
 SCORES = ((1, False), (1, True), (0, False), (0, True), (2, False))
 if dt == np.float32:
-    SCORES = ((0, True), (2, False))  # the float running-sum screen covers the A^2/B family
+    SCORES = ((0, False), (0, True), (2, False))  # the float running-sum screen covers Gaussian and Rational
 
 
 def gens(n, T):
