@@ -509,10 +509,57 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     const float4* __restrict__ sb = sbuf[s & 1];
     if (kb <= i0 + BR - 1) {
       // diagonal stage: row i only sees k > i; the double kernel converts exact differences (kb - 1 = i0 <= i)
-      if (DBL)
+      if (DBL) {
         for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
-      else
+      } else if (AUDIT || cnt < BK) {
         for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, F_{});
+      } else {
+        // float data: Px[k] - Px[i] is exact whatever the sign, so the diagonal stage runs the group scheme of the interior
+        // stages with a per-lane mask
+#pragma unroll 1
+        for (int kk = 0; kk < BK; kk += U) {
+          const int kg = kb + kk;
+          if (mono) {
+            const float4 re = sb[kk + U - 1], rf = sb[kk];
+            const float ubg = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                        __fadd_rn(re.y, by), screen_gmax_of<D>(re));
+            // a lane with no cell in the group drops it, a lane that starts inside it keeps it, the others bound it
+            const bool keep = (kg + U - 1 > i) && (!(kg > i) || !(ubg < thr));
+            if (!__any_sync(0xffffffffu, keep)) continue;
+          }
+          float A[U], B[U], W[U];
+          bool gt = false;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float4 r = sb[kk + u];
+            A[u] = __fadd_rn(r.x, bx);
+            B[u] = __fadd_rn(r.y, by);
+            W[u] = screen_pm_of<D>(r);
+            if (FRONTIER) gt |= (kg + u > i) && (A[u] > B[u]);
+          }
+          bool alive = false;
+          if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) alive |= (kg + u > i) && !(fmaf(B[u], SCR_TINY, W[u]) < thr);
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) alive |= (kg + u > i) && !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
+          }
+          if (__any_sync(0xffffffffu, alive)) {
+            D v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = exact_at(kg + u);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if ((kg + u > i) && v[u] > best) {
+                best = v[u];
+                arg = kg + u;
+              }
+            thr = fmaxf(thr, screen_rd<D>(best));
+            nexact += U;
+          }
+        }
+      }
     } else if (cnt < BK) {
       for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
     } else {
