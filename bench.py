@@ -162,7 +162,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads_used(kind), "kind": kind,
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -176,6 +176,15 @@ def measured_peaks():
         return json.loads(out.strip().splitlines()[-1])
     except Exception:
         return None
+
+
+_RECORD_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RECORD_FD if _RECORD_FD is not None else 1, data)
 
 
 def main():
@@ -196,6 +205,12 @@ def main():
     ap.add_argument("--sharded-T", type=int, default=32)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE line, the JSON record: anything libraries write to file descriptor 1 on the way (NCCL prints
+    # its version banner there) is sent to stderr, the record goes to the saved descriptor at the end
+    sys.stdout.flush()
+    global _RECORD_FD
+    _RECORD_FD = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         reference_arm(args)
@@ -542,7 +557,7 @@ def main():
             except Exception as e:  # the port is optional extra context
                 line["cpu_baseline_all_cores"] = {"error": str(e)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -32,6 +32,19 @@ for dt in (np.float32, np.float64):
     ab, bb = synth.poisson_null(1531, seed=4, dtype=dt, replicas=5)
     ctx.solve_raw(ab, bb, 4, 1, False, dtype=dt, sweep=True)
     assert ctx.timings()["screen_used"] == 1
+# running-sum screens (csrc/screen_run.cuh): real-valued inputs, some a <= 0; audit mode takes them at any size
+for dt in (np.float64, np.float32):
+    ar, br = synth.gaussian_mixture(6143, 6, seed=7, dtype=dt)
+    for dist, rp in ((1, False), (1, True), (0, False), (0, True), (2, False)):
+        aa = np.maximum(ar, 0.5) if dist == 1 else ar
+        ctx.solve_raw(aa, br, 4, dist, rp, dtype=dt, levels=True, sweep=True, screen=2)
+        t = ctx.timings()
+        assert t["screen_violations"] == 0
+        assert t["screen_used"] == (2 if (dt == np.float64 or dist != 1) else 0), (dt, dist, rp, t["screen_used"])
+    ar, br = synth.gaussian_mixture(16511, 4, seed=8, dtype=dt)
+    ctx.solve_raw(ar, br, 3, 2, False, dtype=dt)
+    assert ctx.timings()["screen_used"] == 2
+    ctx.solve_raw(ar, br, 3, 2, False, dtype=dt, perm=np.random.RandomState(2).permutation(16511).astype(np.int32))
 ctx.selftest_mufu()
 ctx.ltss(a.astype(np.float32), b.astype(np.float32), 1)
 ctx.selftest_math(0, 1 << 16)
