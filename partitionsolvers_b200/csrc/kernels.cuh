@@ -532,15 +532,29 @@ __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int
   D best = Lim<D>::lowest();
   int arg = -1;
   if (i < g.nrows) {
-    for (int c = i / g.L; c < g.NCH; ++c) {
-      // screened levels: a tile that was dropped whole wrote nothing and left its stamp alone
-      if (tile_stamp && tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + i / BR] != stamp) continue;
-      const D v = part_val[(long long)c * g.n + i];
-      if (v > best) {
-        best = v;
-        arg = part_arg[(long long)c * g.n + i];
+    // four chunks per step so that the stamp and value loads of a step are in flight together; the split index is read
+    // once, for the winning chunk only (a partial equal to lowest() never wins: its split is -1 like the initial one)
+    int cbest = -1;
+    const int* __restrict__ stamps =
+        tile_stamp ? tile_stamp + (long long)inst * g.nch_alloc * stamp_stride + i / BR : nullptr;
+    for (int c = i / g.L; c < g.NCH; c += 4) {
+      bool live[4];
+      D v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // screened levels: a tile that was dropped whole wrote nothing and left its stamp alone
+        live[q] = (c + q < g.NCH) && (!stamps || stamps[(long long)(c + q) * stamp_stride] == stamp);
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = live[q] ? part_val[(long long)(c + q) * g.n + i] : Lim<D>::lowest();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (v[q] > best) {
+          best = v[q];
+          cbest = c + q;
+        }
     }
+    if (cbest >= 0) arg = part_arg[(long long)cbest * g.n + i];
     if (ms_row) ms_row[inst * table_stride + i] = best;
     if (ns_row) ns_row[inst * table_stride + i] = arg;
     if (rec_next) rec_next[inst * g.rec_stride + i].p = best;
@@ -559,14 +573,21 @@ __global__ void __launch_bounds__(BR)
 level1_running_kernel(int n, int L, int nch_alloc, long long rec_stride, int dist, int rp,
                       const Rec4<D>* __restrict__ rec, D* __restrict__ SA, D* __restrict__ SB,
                       D* __restrict__ ms1, int* __restrict__ ns1, long long table_stride,
-                      Rec4<D>* __restrict__ rec_next, int rb_first, int rb_step, D* __restrict__ shard_chunk) {
+                      Rec4<D>* __restrict__ rec_next, int rb_first, int rb_step, D* __restrict__ shard_chunk,
+                      int nblocks) {
   constexpr int BK = BR;
   __shared__ Rec4<D> sbuf[2][BK];
   const int inst = blockIdx.y;
   rec += (long long)inst * rec_stride;
   const long long pstride = (long long)nch_alloc * n;
-  const int rb = rb_first + rb_step * blockIdx.x;
   const int tid = threadIdx.x;
+  // The rows form a triangle: block m walks n - 128 m cells per row.  A CTA takes block m and then block nblocks-1-m, so
+  // every CTA walks the same number of cells and the SMs finish together (grid = ceil(nblocks / 2)).
+  for (int pass = 0; pass < 2; ++pass) {
+  const int m = pass ? nblocks - 1 - (int)blockIdx.x : (int)blockIdx.x;
+  if (pass && m <= (int)blockIdx.x) break;
+  if (pass) __syncthreads();
+  const int rb = rb_first + rb_step * m;
   const int i0 = rb * BR;
   const int i = i0 + tid;
   D A = 0, B = 0;
@@ -628,7 +649,8 @@ level1_running_kernel(int n, int L, int nch_alloc, long long rec_stride, int dis
     if (ns1) ns1[inst * table_stride + i] = n;
     if (rec_next) rec_next[inst * rec_stride + i].p = v;
   }
-  if (shard_chunk) shard_chunk[blockIdx.x * BR + tid] = v;
+  if (shard_chunk) shard_chunk[m * BR + tid] = v;
+  }
 }
 
 // Sharded runs, prefix records: level 1 of the owned rows, in block-cyclic chunk order.

@@ -538,9 +538,9 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       d_SA = (D*)bufA.p;
       d_SB = (D*)bufB.p;
     }
-    ps::level1_running_kernel<D, BR><<<dim3(cdiv(n, BR), R), BR, 0, st>>>(
+    ps::level1_running_kernel<D, BR><<<dim3((cdiv(n, BR) + 1) / 2, R), BR, 0, st>>>(
         n, sa_L, sa_nch, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
-        0, 1, nullptr);
+        0, 1, nullptr, cdiv(n, BR));
     if constexpr (sizeof(D) == 4) {
       if (screen_run32) {
         PS_TRY(ensure(ctx, ctx->ipos, (size_t)R * sizeof(int)));
@@ -796,9 +796,9 @@ ps_status ltss_impl(ps_ctx* ctx, int n, const float* a, const float* b, int dist
   // suffix scores S(i,n) under the mult-clust objective == level 1 of the DP
   PS_TRY(ensure(ctx, ctx->ms, (size_t)n * sizeof(D)));
   PS_TRY(ensure(ctx, ctx->ns, (size_t)n * sizeof(int)));
-  ps::level1_running_kernel<D, BR><<<dim3(cdiv(n, BR), 1), BR, 0, st>>>(
+  ps::level1_running_kernel<D, BR><<<dim3((cdiv(n, BR) + 1) / 2, 1), BR, 0, st>>>(
       n, n + BR, 1, rec_stride, dist, 0, rec0, (D*)nullptr, (D*)nullptr, (D*)ctx->ms.p, (int*)ctx->ns.p, 0,
-      (ps::Rec4<D>*)nullptr, 0, 1, (D*)nullptr);
+      (ps::Rec4<D>*)nullptr, 0, 1, (D*)nullptr, cdiv(n, BR));
   PS_TRY(ensure(ctx, ctx->part_val, 2 * (size_t)n * sizeof(D)));
   D* PA = (D*)ctx->part_val.p;
   D* PB = PA + n;
@@ -951,9 +951,9 @@ ps_status shard_level1_impl(ps_shard* s, D* my_chunk) {
           n, s->p.dist, s->p.risk_part ? 1 : 0, rec0, s->ns + n, s->rank, s->world, my_chunk);
   } else if (s->p.sum_mode == PS_SUM_RUNNING) {
     if (s->owned_blocks > 0)
-      ps::level1_running_kernel<D, BR><<<dim3(s->owned_blocks, 1), BR, 0, st>>>(
+      ps::level1_running_kernel<D, BR><<<dim3((s->owned_blocks + 1) / 2, 1), BR, 0, st>>>(
           n, s->L, s->nch_alloc, rec_stride, s->p.dist, s->p.risk_part ? 1 : 0, rec0, (D*)s->SA, (D*)s->SB,
-          (D*)nullptr, s->ns + n, 0, (ps::Rec4<D>*)nullptr, s->rank, s->world, my_chunk);
+          (D*)nullptr, s->ns + n, 0, (ps::Rec4<D>*)nullptr, s->rank, s->world, my_chunk, s->owned_blocks);
   } else {
     return PS_ERR_UNSUPPORTED;
   }

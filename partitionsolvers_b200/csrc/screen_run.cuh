@@ -153,7 +153,7 @@ __global__ void pm_from_rec_kernel(int n, long long rec_stride, const Rec4<doubl
 }
 
 // Row lower bounds for the running-sum path: the cells whose running sums are at hand are the chunk boundaries
-// (i, c L), c L > i -- all of them are evaluated (at most ~200 per row).  Also the group / block maxima of pm, as in
+// (i, c L), c L > i (at most ~200 per row) -- a coarse sweep over them, then every boundary around the best coarse sample.  Also the group / block maxima of pm, as in
 // screen_lb_kernel.
 template <int DIST, bool RP>
 __global__ void __launch_bounds__(128)
@@ -181,12 +181,25 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
   }
   D best = Lim<D>::lowest();
   if (SA) {
-    const int c1 = min(g.kmax / g.L, g.nch_alloc - 1);
-    for (int c = i / g.L + 1; c <= c1; ++c) {
+    const int c0 = i / g.L + 1, c1 = min(g.kmax / g.L, g.nch_alloc - 1);
+    int cb = c0;
+    auto probe = [&](const int c) {
       const D A = SA[inst * pstride + (long long)c * g.n + i];
       const D B = SB[inst * pstride + (long long)c * g.n + i];
       const D v = add_rn<D>(screen_exact_score<D, DIST, RP, false>(A, B, nullptr), rec[c * g.L].p);
-      if (v > best) best = v;
+      if (v > best) {
+        best = v;
+        cb = c;
+      }
+    };
+    if (c1 >= c0) {  // a coarse sweep over the row's boundaries, then every boundary around the best coarse sample
+      const int sc = max(1, (c1 - c0 + 1) / 24);
+      for (int c = c0; c <= c1; c += sc) probe(c);
+      probe(c1);
+      if (sc > 1) {
+        const int lo = max(c0, cb - sc + 1), hi = min(c1, cb + sc - 1);
+        for (int c = lo; c <= hi; ++c) probe(c);
+      }
     }
   }
   LB[(long long)inst * g.n + i] = best;

@@ -1,5 +1,5 @@
 """C3R (n=100000, T=16 Rational score on real-valued double data): timing, tier statistics, activation threshold.
-    python tools/run_c3r.py time|tiers|threshold"""
+    python tools/run_c3r.py time|tiers|threshold [f32]"""
 import os
 import sys
 
@@ -10,7 +10,7 @@ from partitionsolvers_b200 import capi, synth  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "time"
 ctx = capi.Context(0)
-dt = np.float64
+dt = np.float32 if "f32" in sys.argv[2:] else np.float64
 if mode == "time":
     a, b = synth.CONFIGS["C3R"]["gen"](dt)
     for it in range(4):
