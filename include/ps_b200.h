@@ -184,6 +184,9 @@ ps_status ps_shard_level(ps_shard* s, int j, void* my_chunk_dev);
 /* split index next_start[j][i] (host lookup of one element; valid on the owning rank, else -2) */
 ps_status ps_shard_next_start(ps_shard* s, int j, int i, int* out);
 int ps_shard_owner(const ps_shard* s, int i);
+/* scores of the `count` subsets [bounds[t], bounds[t+1]) of the sorted sequence (DP_impl.hpp:131-139: score_by_subset);
+ * HOST pointers; every rank holds the sorted inputs, any rank can answer */
+ps_status ps_shard_subset_scores(ps_shard* s, int count, const int* bounds, void* scores);
 /* 1 if this shard's levels run the screened kernel (ps_problem.screen, csrc/screen.cuh) */
 int ps_shard_screened(const ps_shard* s);
 void ps_shard_destroy(ps_shard* s);

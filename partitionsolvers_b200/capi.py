@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "ps_range_score_f64", "ps_shard_create_f64", "ps_shard_create_f32", "ps_shard_chunk_rows",
     "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",
     "ps_shard_destroy", "ps_selftest_math", "ps_eval_log_f64", "ps_eval_log_f32",
-    "ps_ltss_f32", "ps_selftest_mufu", "ps_shard_screened",
+    "ps_ltss_f32", "ps_selftest_mufu", "ps_shard_screened", "ps_shard_subset_scores",
 ]
 
 
@@ -99,6 +99,7 @@ def load():
         L.ps_shard_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ps_shard_next_start.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.ps_shard_owner.argtypes = [C.c_void_p, C.c_int]
+        L.ps_shard_subset_scores.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ps_shard_screened.argtypes = [C.c_void_p]
         L.ps_shard_destroy.argtypes = [C.c_void_p]
         L.ps_shard_destroy.restype = None

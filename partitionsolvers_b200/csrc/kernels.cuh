@@ -887,6 +887,34 @@ __global__ void backtrace_scores_kernel(int R, int n, int Tc, int sweep, int dis
   scores[g] = out;
 }
 
+// Row-sharded runs: the per-subset scores of a backtraced partition (DP_impl.hpp:131-139), one thread per subset.
+// prefix != 0: the records hold scan values of exactly summable inputs, so the difference IS the reference's running sum;
+// otherwise the subset is walked left to right like the reference does.
+template <typename D>
+__global__ void shard_subset_scores_kernel(int count, int n, int dist, int rp, int prefix,
+                                           const int* __restrict__ bounds, const Rec4<D>* __restrict__ rec,
+                                           D* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int lo = bounds[t], hi = bounds[t + 1];
+  if (!(lo >= 0 && hi >= lo && hi <= n)) {
+    out[t] = (D)nan("");
+    return;
+  }
+  D A = 0, B = 0;
+  if (prefix) {
+    A = sub_rn<D>(rec[hi].x, rec[lo].x);
+    B = sub_rn<D>(rec[hi].y, rec[lo].y);
+  } else {
+#pragma unroll 8
+    for (int k = lo + 1; k <= hi; ++k) {
+      A = add_rn<D>(A, rec[k].x);
+      B = add_rn<D>(B, rec[k].y);
+    }
+  }
+  out[t] = score_dyn<D>(dist, rp, A, B);
+}
+
 // compute_score (python_dpsolver.cpp:74-111): S(0,n) of the unsorted inputs, sequential sums.
 template <typename D>
 __global__ void range_score_kernel(int n, int dist, int rp, const D* __restrict__ a,

@@ -1028,6 +1028,26 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
   return PS_OK;
 }
 
+template <typename D>
+ps_status shard_subset_scores_impl(ps_shard* s, int count, const int* bounds, D* scores) {
+  ps_ctx* ctx = s->ctx;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = s->p.n;
+  if (count < 1 || count > n) return PS_ERR_INVALID;
+  cudaStream_t st = ctx->stream;
+  PS_TRY(ensure(ctx, ctx->bounds, (size_t)(count + 1) * sizeof(int)));
+  PS_TRY(ensure(ctx, ctx->scores, (size_t)count * sizeof(D)));
+  PS_CUDA(ctx, cudaMemcpyAsync(ctx->bounds.p, bounds, (size_t)(count + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  const int prefix = s->screen || s->p.sum_mode == PS_SUM_PREFIX;
+  ps::shard_subset_scores_kernel<D><<<cdiv(count, 32), 32, 0, st>>>(count, n, s->p.dist, s->p.risk_part ? 1 : 0, prefix,
+                                                                   (const int*)ctx->bounds.p,
+                                                                   (const ps::Rec4<D>*)s->rec, (D*)ctx->scores.p);
+  PS_CUDA(ctx, cudaGetLastError());
+  PS_CUDA(ctx, cudaMemcpyAsync(scores, ctx->scores.p, (size_t)count * sizeof(D), cudaMemcpyDeviceToHost, st));
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  return PS_OK;
+}
+
 }  // namespace
 
 // =================================================================================== C ABI
@@ -1202,6 +1222,12 @@ ps_status ps_shard_next_start(ps_shard* s, int j, int i, int* out) {
                                ctx->stream));
   PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PS_OK;
+}
+
+ps_status ps_shard_subset_scores(ps_shard* s, int count, const int* bounds, void* scores) {
+  if (!s || !bounds || !scores) return PS_ERR_INVALID;
+  return s->dtype == 4 ? shard_subset_scores_impl<float>(s, count, bounds, (float*)scores)
+                       : shard_subset_scores_impl<double>(s, count, bounds, (double*)scores);
 }
 
 int ps_shard_screened(const ps_shard* s) { return s ? s->screen : 0; }

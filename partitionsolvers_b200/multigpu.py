@@ -115,6 +115,14 @@ class CudaShardEngine:
     def range_score(self, a_seg, b_seg, dist_id, risk_part, dtype):
         return self.ctx.range_score(a_seg, b_seg, dist_id, risk_part, dtype=dtype)
 
+    def subset_scores(self, bounds, dtype):
+        """Scores of the subsets [bounds[t], bounds[t+1]) in one launch (one thread per subset)."""
+        bounds = np.ascontiguousarray(bounds, np.int32)
+        out = np.empty(len(bounds) - 1, dtype)
+        self.ctx._check(self.lib.ps_shard_subset_scores(self._h, len(out), bounds.ctypes.data_as(C.c_void_p),
+                                                        out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def close(self):
         if self._h:
             self.lib.ps_shard_destroy(self._h)
@@ -198,11 +206,16 @@ class ShardedSolver:
         self.bounds = np.array(bounds, np.int32)
         # objective value = maxScore_[T][0], held by rank 0's chunk slot 0 after the last exchange
         self.max_score_T0 = float(gathered[0].item())
-        a_host = np.asarray(a, dtype)[perm]
-        b_host = np.asarray(b, dtype)[perm]
-        self.subset_scores = np.array(
-            [engine.range_score(a_host[lo:hi], b_host[lo:hi], dist_id, risk_part, dtype)
-             for lo, hi in zip(bounds[:-1], bounds[1:])], dtype) if self.rank == 0 else None
+        if self.rank != 0:
+            self.subset_scores = None
+        elif hasattr(eng, "subset_scores"):
+            self.subset_scores = eng.subset_scores(self.bounds, dtype)
+        else:
+            a_host = np.asarray(a, dtype)[perm]
+            b_host = np.asarray(b, dtype)[perm]
+            self.subset_scores = np.array(
+                [engine.range_score(a_host[lo:hi], b_host[lo:hi], dist_id, risk_part, dtype)
+                 for lo, hi in zip(bounds[:-1], bounds[1:])], dtype)
         self.subsets = [perm[lo:hi] for lo, hi in zip(bounds[:-1], bounds[1:])]
         eng.close()
         t_end = time.perf_counter()

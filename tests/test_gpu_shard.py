@@ -49,3 +49,23 @@ def test_sharded_levels_equal_unsharded(ctx, world, dt, n):
                     assert engines[0].next_start(j, i) == -2
     for e in engines:
         e.close()
+
+
+@pytest.mark.parametrize("kind", ["counts", "real"])
+def test_sharded_solver_subset_scores(ctx, kind):
+    """ShardedSolver end to end on one rank: boundaries, subsets and the per-subset scores (ps_shard_subset_scores: one
+    thread per subset; prefix differences when the shard runs on exactly summable inputs, a left-to-right walk otherwise)
+    equal the unsharded solve bit for bit."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    n, T = 7000, 6
+    if kind == "counts":
+        a, b = synth.poisson_planted(n, 6, seed=43, dtype=np.float64)
+    else:
+        a, b = synth.tract_like(n, 4, seed=44, dtype=np.float64)
+        a = np.maximum(a, 1.0)
+    full = ctx.solve_raw(a, b, T, 1, False, dtype=np.float64)
+    sh = multigpu.ShardedSolver(multigpu.CudaShardEngine(ctx, dev), a, b, T, 1, False, dtype=np.float64)
+    assert np.array_equal(sh.bounds, full["bounds"].ravel())
+    assert np.array_equal(sh.perm, full["perm"])
+    assert np.array_equal(sh.subset_scores, full["subset_scores"].ravel())
