@@ -319,6 +319,10 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ r
     else
       recf[i + 8].w = m;
   }
+  {  // row-sharded runs: the group / block maxima above are needed for every k, the lower bound only for owned rows
+    const int rbi = i / SCR_BLOCK;
+    if (rbi < g.rb_first || (rbi - g.rb_first) % g.rb_step != 0) return;
+  }
   const D Xi = rec[i].x, Yi = rec[i].y;
   const int k0 = i + 1, k1 = g.kmax;
   const int len = k1 - k0 + 1;
