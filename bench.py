@@ -405,6 +405,19 @@ def main():
              "hbm": {"alg_bytes_per_launch": alg_bytes_per_launch,
                      "achieved_gbs": alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                      "note": "not HBM-bound: algorithmic traffic is (4w+4)n bytes per level"}}
+        if screened and pk.get("warp_instructions_per_cell"):
+            # The screened kernel dismisses most cells in groups, so the algorithmic flop count says little about it (it
+            # exceeds the FP32 peak).  What bounds it is instruction ISSUE: one warp instruction per SM sub-partition and
+            # cycle.  achieved = executed warp instructions per cell (ncu, profiles/level_kernel_summary.json) x cells of
+            # the timed launches / 32 / their CUDA-event time; peak = 148 SMs x 4 sub-partitions x SM clock.
+            ipc = pk["warp_instructions_per_cell"]
+            issue_peak = 148 * 4 * 1.965e9 / 1e12
+            issue_ach = ipc * res["level_cells_sum"] / 32.0 / lev_s / 1e12
+            r["algorithmic_flops"] = {"achieved": r["achieved"], "peak": r["peak"], "unit": "TFLOP/s",
+                                      "frac": r["frac"], "peak_source": r["peak_source"]}
+            r.update({"bound": "issue", "achieved": issue_ach, "peak": issue_peak, "unit": "T warp-instructions/s",
+                      "frac": issue_ach / issue_peak,
+                      "peak_source": "148 SMs x 4 sub-partitions x 1.965 GHz, one warp instruction per cycle each"})
         if screened:
             r["screen"] = {
                 "exact_cell_fraction": res["exact_cells"] / max(1.0, res["level_cells_sum"]),
@@ -412,8 +425,8 @@ def main():
                 "issue_slot_utilisation": pk.get("issue_active_pct"),
                 "note": "cells are bounded in float, singly or 8 / 128 at a time where the score is monotone in k; "
                         "only cells that can still be the row maximum are evaluated with the reference's arithmetic. "
-                        "The algorithmic count still charges every cell, so frac may exceed 1: the kernel's own "
-                        "ceiling is instruction issue (see issue_slot_utilisation from ncu, profiles/)"}
+                        "The algorithmic flop count (algorithmic_flops) still charges every cell, so its frac exceeds 1; "
+                        "the roofline reported is instruction issue"}
         else:
             r["sfu"] = {"ops_per_cell": 1,
                         "what": "one MUFU reciprocal per evaluated cell (division seed); log is table-driven, no MUFU",
