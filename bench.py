@@ -560,6 +560,22 @@ def main():
                 "sample": f"one {'reference DPSolver' if kind == 'reference' else 'oracle port'} solve at n={n_s}, "
                           f"T={T}, {args.dtype}, same generator ({t:.2f} s); the reference cannot allocate n=100000"}
             try:
+                # the reference's native-threaded variant on the replica workload: independent DPSolver<float>
+                # constructions dispatched on its own ThreadPool (threadpool.hpp:105-113, the call pattern of
+                # sweep_parallel__DP, python_dpsolver.cpp:263-316); hardware_concurrency()-1 workers
+                from oracle import oracle_py as O
+                c4r = synth.CONFIGS["C4"]
+                r_cpu = 2 * max(1, (os.cpu_count() or 2) - 1)
+                a_r, b_r = synth.poisson_null(c4r["n"], seed=synth.SEED + 4, dtype=np.float32, replicas=r_cpu)
+                t_pool, _, workers = O.time_pool_ref(a_r, b_r, c4r["T"], c4r["dist"], c4r["risk_part"])
+                line["cpu_replicas_baseline"] = {
+                    "value": r_cpu / t_pool, "unit": "replicas/s", "cores": workers, "kind": "reference",
+                    "host_cores": os.cpu_count(),
+                    "sample": f"{r_cpu} null-model replicas (n={c4r['n']}, T={c4r['T']}, f32) on the reference's own "
+                              f"ThreadPool, {workers} workers ({t_pool:.2f} s)"}
+            except Exception as e:
+                line["cpu_replicas_baseline"] = {"error": str(e)}
+            try:
                 from oracle import oracle_py as O
                 n_p = 20000
                 ap_, bp_ = cfg["gen"](dtype, n_p)
