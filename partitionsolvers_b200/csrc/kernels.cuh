@@ -509,58 +509,81 @@ __device__ __forceinline__ float screen_rd(D v) {
 // first maximum, exactly like the reference's scan over k.  Writes maxScore_[j][i], nextStart_[j][i]
 // and the p field of the NEXT level's records.  Sharded runs also emit the value in block-cyclic
 // "chunk" order for the all-gather.
-template <typename D, int BR>
+template <typename D, int BR, int CW = 1>
 __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int* __restrict__ part_arg,
                                D* __restrict__ ms_row, int* __restrict__ ns_row, long long table_stride,
                                Rec4<D>* __restrict__ rec_next, D* __restrict__ shard_chunk,
                                float* __restrict__ pm_next, const int* __restrict__ tile_stamp = nullptr,
                                int stamp = 0, int stamp_stride = 0) {
+  // CW lanes share a row: lane q folds the q-th part of the row's chunks (contiguous, ascending), then the parts are merged
+  // in ascending order with the same strict > -- the first maximum still wins.  A row's fold is a chain of dependent L2
+  // round trips; with many chunks (large n) splitting it four ways shortens the chain and quadruples the loads in flight;
+  // instances with few chunks (replica batches) take CW = 1.
   const int inst = blockIdx.y;
   const long long pstride = (long long)g.nch_alloc * g.n;
   part_val += inst * pstride;
   part_arg += inst * pstride;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;  // index among owned rows
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = gt / CW, q = gt % CW;  // index among owned rows, quarter
   int i;
+  bool row_ok = true;
   if (g.rb_step == 1 && g.rb_first == 0) {
     i = m;  // unsharded: rows are contiguous whatever the tile height of the level kernel
-    if (i >= g.nrows) return;
+    row_ok = i < g.nrows;
   } else {
-    if (m >= g.NRB * BR) return;
+    row_ok = m < g.NRB * BR;
     const int rb = g.rb_first + g.rb_step * (m / BR);
     i = rb * BR + (m % BR);
   }
   D best = Lim<D>::lowest();
-  int arg = -1;
-  if (i < g.nrows) {
-    // four chunks per step so that the stamp and value loads of a step are in flight together; the split index is read
-    // once, for the winning chunk only (a partial equal to lowest() never wins: its split is -1 like the initial one)
-    int cbest = -1;
+  int cbest = -1;
+  if (row_ok && i < g.nrows) {
+    const int c_first = i / g.L;
+    const int per = (g.NCH - c_first + CW - 1) / CW;
+    const int c0 = c_first + q * per, c1 = min(g.NCH, c0 + per);
     const int* __restrict__ stamps =
         tile_stamp ? tile_stamp + (long long)inst * g.nch_alloc * stamp_stride + i / BR : nullptr;
-    for (int c = i / g.L; c < g.NCH; c += 4) {
+    for (int c = c0; c < c1; c += 4) {
       bool live[4];
       D v[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int u = 0; u < 4; ++u) {
         // screened levels: a tile that was dropped whole wrote nothing and left its stamp alone
-        live[q] = (c + q < g.NCH) && (!stamps || stamps[(long long)(c + q) * stamp_stride] == stamp);
+        live[u] = (c + u < c1) && (!stamps || stamps[(long long)(c + u) * stamp_stride] == stamp);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = live[q] ? part_val[(long long)(c + q) * g.n + i] : Lim<D>::lowest();
+      for (int u = 0; u < 4; ++u) v[u] = live[u] ? part_val[(long long)(c + u) * g.n + i] : Lim<D>::lowest();
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (v[q] > best) {
-          best = v[q];
-          cbest = c + q;
+      for (int u = 0; u < 4; ++u)
+        if (v[u] > best) {
+          best = v[u];
+          cbest = c + u;
         }
     }
-    if (cbest >= 0) arg = part_arg[(long long)cbest * g.n + i];
-    if (ms_row) ms_row[inst * table_stride + i] = best;
-    if (ns_row) ns_row[inst * table_stride + i] = arg;
-    if (rec_next) rec_next[inst * g.rec_stride + i].p = best;
-    if (pm_next) pm_next[(inst * g.rec_stride + i) * 4 + 3] = screen_pm<D>(best);  // .w of the float record
   }
-  if (shard_chunk) shard_chunk[m] = best;
+  // ordered merge over the CW lanes of the row (lanes of a row are adjacent; all 32 lanes take part in the shuffles)
+  const unsigned int lane = threadIdx.x & 31u, base = lane & ~(unsigned)(CW - 1);
+  D mb = __shfl_sync(0xffffffffu, best, base);
+  int mc = __shfl_sync(0xffffffffu, cbest, base);
+#pragma unroll
+  for (int u = 1; u < CW; ++u) {
+    const D ob = __shfl_sync(0xffffffffu, best, base + u);
+    const int oc = __shfl_sync(0xffffffffu, cbest, base + u);
+    if (ob > mb) {
+      mb = ob;
+      mc = oc;
+    }
+  }
+  if (q != 0 || !row_ok) return;
+  if (i < g.nrows) {
+    // the split index is read once, for the winning chunk only (a partial equal to lowest() never wins: split -1)
+    const int arg = (mc >= 0) ? part_arg[(long long)mc * g.n + i] : -1;
+    if (ms_row) ms_row[inst * table_stride + i] = mb;
+    if (ns_row) ns_row[inst * table_stride + i] = arg;
+    if (rec_next) rec_next[inst * g.rec_stride + i].p = mb;
+    if (pm_next) pm_next[(inst * g.rec_stride + i) * 4 + 3] = screen_pm<D>(mb);  // .w of the float record
+  }
+  if (shard_chunk) shard_chunk[m] = (i < g.nrows) ? mb : Lim<D>::lowest();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -669,7 +669,9 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       }
     }
     if (timed) PS_TRY(mark(ctx, &e1));
-    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * tile_rows, 256), R), 256, 0, st>>>(
+    const bool wide_combine = g.NCH >= 32;  // four lanes per row once a row has enough chunks to fold
+    auto fn_combine = wide_combine ? ps::combine_kernel<D, BR, 4> : ps::combine_kernel<D, BR, 1>;
+    fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
         g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
         ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
         ((screen || screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp,
@@ -1011,7 +1013,7 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
     fn_lb<<<dim3(cdiv(g.nrows, 128), 1), 128, 0, st>>>(g, rin, rf, (D*)s->lb, s->bmax, n / ps::SCR_BLOCK + 2);
     fn_scr<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, rf, (const D*)s->lb, (D*)s->part_val, s->part_arg, s->counters,
                                              s->dflags, s->bmax, n / ps::SCR_BLOCK + 2, nullptr, 0, 0);
-    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
+    ps::combine_kernel<D, BR, 4><<<dim3(cdiv(4LL * g.NRB * BR, 256), 1), 256, 0, st>>>(
         g, (const D*)s->part_val, s->part_arg, (D*)nullptr, s->ns + (long long)j * n, 0,
         (ps::Rec4<D>*)nullptr, my_chunk, nullptr);
   } else if (g.ntiles > 0) {
@@ -1019,7 +1021,7 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
     auto fn = LevelLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, running, s->fast);
     fn<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, (const D*)s->SA, (const D*)s->SB, (D*)s->part_val,
                                          s->part_arg);
-    ps::combine_kernel<D, BR><<<dim3(cdiv((long long)g.NRB * BR, 256), 1), 256, 0, st>>>(
+    ps::combine_kernel<D, BR, 4><<<dim3(cdiv(4LL * g.NRB * BR, 256), 1), 256, 0, st>>>(
         g, (const D*)s->part_val, s->part_arg, (D*)nullptr, s->ns + (long long)j * n, 0,
         (ps::Rec4<D>*)nullptr, my_chunk, nullptr);
   }

@@ -369,6 +369,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
   static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
   constexpr int BK = BR;
   constexpr int U = 8;  // cells per group
+  constexpr int GQ = 4;  // groups whose bounds are formed together
   constexpr bool DBL = (sizeof(D) == 8);
   constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;  // scores that are 0 unless A > B
   // Scores that never decrease when a row's range is extended to the right (priorities ascending, a > 0): with
@@ -584,19 +585,36 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
           for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true);
       } else {
 #pragma unroll 1
-        for (int kk = 0; kk < BK; kk += U) {
+        for (int kq = 0; kq < BK; kq += GQ * U) {
+          // group tier, GQ groups at a time: their bound chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, FMA) are independent and
+          // overlap; a group kept on a threshold that a group before it raises afterwards is merely kept once too often
+          unsigned int keepm = (1u << GQ) - 1u;
           if (mono) {
-            const float4 re = sb[kk + U - 1], rf = sb[kk];
-            const float ubg = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
-                                                        __fadd_rn(re.y, by), screen_gmax_of<D>(re));
-            const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
-            if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
-            if (gdrop) {
-              if (AUDIT)
-                for (int u = 0; u < U; ++u) audit_dropped(kb + kk + u, true);
-              continue;
+            float ubg[GQ];
+#pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+              const float4 re = sb[kq + q * U + U - 1], rf = sb[kq + q * U];
+              ubg[q] = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                 __fadd_rn(re.y, by), screen_gmax_of<D>(re));
             }
+            keepm = 0;
+#pragma unroll
+            for (int q = 0; q < GQ; ++q)
+              if (__any_sync(0xffffffffu, !(ubg[q] < thr))) keepm |= 1u << q;
+            if (AUDIT) {
+              for (int q = 0; q < GQ; ++q) {
+                const bool gdrop = !((keepm >> q) & 1u);
+                if (counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
+                if (gdrop)
+                  for (int u = 0; u < U; ++u) audit_dropped(kb + kq + q * U + u, true);
+              }
+            }
+            if (!keepm) continue;
           }
+#pragma unroll 1
+          for (int q = 0; q < GQ; ++q) {
+          if (!((keepm >> q) & 1u)) continue;
+          const int kk = kq + q * U;
           // U independent chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA-pipe operations): their latencies overlap,
           // one vote decides for the group
           float A[U], B[U], W[U];
@@ -635,6 +653,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
               }
             thr = fmaxf(thr, screen_rd<D>(best));
             nexact += U;
+          }
           }
         }
       }

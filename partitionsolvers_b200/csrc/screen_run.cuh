@@ -220,6 +220,7 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
   static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
   constexpr int BK = BR;
   constexpr int U = 8;
+  constexpr int GQ = AUDIT ? 1 : 4;  // groups whose bounds are formed together
   constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
   constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
   constexpr bool BOX = !GROUPB;  // Poisson risk-part: range tiers from the box bound, no sortedness needed
@@ -430,19 +431,33 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
           for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true);
       } else {
 #pragma unroll 1
-        for (int kk = 0; kk < BK; kk += U) {
+        for (int kq = 0; kq < BK; kq += GQ * U) {
+          // group tier, GQ groups at a time (independent bound chains); audit runs keep ascending k: one group at a time
+          unsigned int keepm = (1u << GQ) - 1u;
           if (mono) {
-            const float4 re = sb[kk + U - 1], rf = sb[kk];
-            const float ubg = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
-                                                        __fadd_rn(re.y, by), re.z);
-            const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
-            if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
-            if (gdrop) {
-              if (AUDIT)
-                for (int u = 0; u < U; ++u) audit_dropped(kb + kk + u, true);
-              continue;
+            float ubg[GQ];
+#pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+              const float4 re = sb[kq + q * U + U - 1], rf = sb[kq + q * U];
+              ubg[q] = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                 __fadd_rn(re.y, by), re.z);
             }
+            keepm = 0;
+#pragma unroll
+            for (int q = 0; q < GQ; ++q)
+              if (__any_sync(0xffffffffu, !(ubg[q] < thr))) keepm |= 1u << q;
+            if (AUDIT) {  // GQ == 1
+              const bool gdrop = !(keepm & 1u);
+              if (counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
+              if (gdrop)
+                for (int u = 0; u < U; ++u) audit_dropped(kb + kq + u, true);
+            }
+            if (!keepm) continue;
           }
+#pragma unroll 1
+          for (int q = 0; q < GQ; ++q) {
+          if (!((keepm >> q) & 1u)) continue;
+          const int kk = kq + q * U;
           float A[U], B[U], W[U];
           bool gt = false;
 #pragma unroll
@@ -485,6 +500,7 @@ level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
               }
             thr = fmaxf(thr, screen_rd<D>(best));
             nexact += U;
+          }
           }
         }
       }
