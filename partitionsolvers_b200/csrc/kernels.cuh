@@ -817,6 +817,120 @@ build_rec_prefix_kernel(int n, long long rec_stride, const D* __restrict__ as, c
   }
 }
 
+// PREFIX records of EXACTLY SUMMABLE inputs (the screened path, screen.cuh P2): every partial sum is representable, so any
+// order of additions gives the reference's values and the scan can spread over the machine.  Three small kernels: sums of
+// 1024-element blocks, exclusive scan of the block sums (one CTA per instance), block-local scan + offset.
+constexpr int PFX_BLOCK = 1024;  // elements per CTA (256 threads x 4)
+template <typename D>
+__global__ void __launch_bounds__(256)
+prefix_block_sums_kernel(int n, int nb, const D* __restrict__ as, const D* __restrict__ bs, D* __restrict__ pa,
+                         D* __restrict__ pb) {
+  __shared__ D wa[8], wb[8];
+  const int inst = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+  as += (long long)inst * n;
+  bs += (long long)inst * n;
+  D ta = 0, tb = 0;
+  const int k0 = blk * PFX_BLOCK + tid * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (k0 + q < n) {
+      ta = add_rn<D>(ta, as[k0 + q]);
+      tb = add_rn<D>(tb, bs[k0 + q]);
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    ta = add_rn<D>(ta, __shfl_xor_sync(0xffffffffu, ta, o));
+    tb = add_rn<D>(tb, __shfl_xor_sync(0xffffffffu, tb, o));
+  }
+  if ((tid & 31) == 0) {
+    wa[tid >> 5] = ta;
+    wb[tid >> 5] = tb;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    D ra = 0, rb = 0;
+    for (int w = 0; w < 8; ++w) {
+      ra = add_rn<D>(ra, wa[w]);
+      rb = add_rn<D>(rb, wb[w]);
+    }
+    pa[(long long)inst * nb + blk] = ra;
+    pb[(long long)inst * nb + blk] = rb;
+  }
+}
+template <typename D>
+__global__ void prefix_scan_partials_kernel(int nb, D* __restrict__ pa, D* __restrict__ pb) {
+  // exclusive scan of the block sums of one instance; nb is small (n / 1024): thread 0 walks a, thread 1 walks b
+  if (threadIdx.x > 1) return;
+  D* p = (threadIdx.x ? pb : pa) + (long long)blockIdx.x * nb;
+  D run = 0;
+  for (int q = 0; q < nb; ++q) {
+    const D v = p[q];
+    p[q] = run;
+    run = add_rn<D>(run, v);
+  }
+}
+template <typename D>
+__global__ void __launch_bounds__(256)
+prefix_write_kernel(int n, int nb, long long rec_stride, const D* __restrict__ as, const D* __restrict__ bs,
+                    const D* __restrict__ pa, const D* __restrict__ pb, Rec4<D>* __restrict__ rec0,
+                    Rec4<D>* __restrict__ rec1) {
+  __shared__ D wa[8], wb[8];
+  const int inst = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  as += (long long)inst * n;
+  bs += (long long)inst * n;
+  rec0 += inst * rec_stride;
+  rec1 += inst * rec_stride;
+  const int k0 = blk * PFX_BLOCK + tid * 4;
+  D xa[4], xb[4];
+  D ta = 0, tb = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    xa[q] = (k0 + q < n) ? as[k0 + q] : (D)0;
+    xb[q] = (k0 + q < n) ? bs[k0 + q] : (D)0;
+    ta = add_rn<D>(ta, xa[q]);
+    tb = add_rn<D>(tb, xb[q]);
+  }
+  // inclusive scan of the thread totals inside the warp, then of the warp totals
+  D sa = ta, sb = tb;
+  for (int o = 1; o < 32; o <<= 1) {
+    const D ua = __shfl_up_sync(0xffffffffu, sa, o), ub = __shfl_up_sync(0xffffffffu, sb, o);
+    if (lane >= o) {
+      sa = add_rn<D>(sa, ua);
+      sb = add_rn<D>(sb, ub);
+    }
+  }
+  if (lane == 31) {
+    wa[wid] = sa;
+    wb[wid] = sb;
+  }
+  __syncthreads();
+  D oa = pa[(long long)inst * nb + blk], ob = pb[(long long)inst * nb + blk];
+  for (int w = 0; w < wid; ++w) {
+    oa = add_rn<D>(oa, wa[w]);
+    ob = add_rn<D>(ob, wb[w]);
+  }
+  D ra = add_rn<D>(oa, sub_rn<D>(sa, ta)), rb = add_rn<D>(ob, sub_rn<D>(sb, tb));  // sums before this thread's elements
+  if (blk == 0 && tid == 0) {
+    Rec4<D> z;
+    z.x = z.y = z.p = z.w = 0;
+    rec0[0] = z;
+    rec1[0] = z;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (k0 + q < n) {
+      ra = add_rn<D>(ra, xa[q]);
+      rb = add_rn<D>(rb, xb[q]);
+      Rec4<D> r;
+      r.x = ra;
+      r.y = rb;
+      r.p = 0;
+      r.w = 0;
+      rec0[k0 + q + 1] = r;
+      rec1[k0 + q + 1] = r;
+    }
+  }
+}
+
 template <typename D>
 __global__ void init_tables_kernel(long long total, int n, D* __restrict__ ms, int* __restrict__ ns) {
   // row 0 of every instance: 0 / -1; all other rows: lowest() / -1  (DP_impl.hpp:83-95)

@@ -475,6 +475,16 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   if (running) {
     ps::build_rec_running_kernel<D><<<dim3(cdiv(n + 1, 256), R), 256, 0, st>>>(n, rec_stride, d_as, d_bs,
                                                                               rec0, rec1);
+  } else if (screen && n >= 4 * ps::PFX_BLOCK) {
+    // exactly summable inputs: the order of additions does not matter, the scan spreads over the machine
+    const int nb = cdiv(n, ps::PFX_BLOCK);
+    PS_TRY(ensure(ctx, ctx->key_in, std::max<size_t>(ctx->key_in.cap, (size_t)2 * R * nb * sizeof(D))));
+    D* d_pa = (D*)ctx->key_in.p;  // the sort is done with its key buffers
+    D* d_pb = d_pa + (size_t)R * nb;
+    ps::prefix_block_sums_kernel<D><<<dim3(nb, R), 256, 0, st>>>(n, nb, d_as, d_bs, d_pa, d_pb);
+    ps::prefix_scan_partials_kernel<D><<<R, 32, 0, st>>>(nb, d_pa, d_pb);
+    ps::prefix_write_kernel<D><<<dim3(nb, R), 256, 0, st>>>(n, nb, rec_stride, d_as, d_bs, d_pa, d_pb, rec0, rec1);
+    ctx->launches += 2;
   } else {
     ps::build_rec_prefix_kernel<D, 1024><<<R, 1024, 0, st>>>(n, rec_stride, d_as, d_bs, rec0, rec1);
   }
