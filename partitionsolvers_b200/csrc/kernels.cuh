@@ -642,11 +642,37 @@ level1_running_kernel(int n, int L, int nch_alloc, long long rec_stride, int dis
           }
         }
       } else if (cnt == BK) {
-        // full stage: constant trip count, so the loop is nothing but LDS.128 + two dependent adds per cell
-#pragma unroll 16
-        for (int kk = 0; kk < BK; ++kk) {
-          A = add_rn<D>(A, sb[kk].x);
-          B = add_rn<D>(B, sb[kk].y);
+        // full stage: constant trip count.  The walk runs at ~2.7 warps per scheduler (one thread per row), too few to hide
+        // the shared-memory latency behind other warps, so the records are read eight ahead of the two dependent add chains.
+        constexpr int PF = 8;
+        D xa[PF], xb[PF];
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+          xa[q] = sb[q].x;
+          xb[q] = sb[q].y;
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += PF) {
+          D na[PF], nb[PF];
+          if (kk + PF < BK) {
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+              na[q] = sb[kk + PF + q].x;
+              nb[q] = sb[kk + PF + q].y;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < PF; ++q) {
+            A = add_rn<D>(A, xa[q]);
+            B = add_rn<D>(B, xb[q]);
+          }
+          if (kk + PF < BK) {
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+              xa[q] = na[q];
+              xb[q] = nb[q];
+            }
+          }
         }
       } else {
         for (int kk = 0; kk < cnt; ++kk) {
