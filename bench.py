@@ -507,6 +507,23 @@ def main():
             small[nm] = {"n": c["n"], "T": c["T"], "dtype": np.dtype(dt_small).name,
                          "ms_per_call_host_buffers": 1e3 * (time.perf_counter() - t0) / 20}
         line["small_configs"] = small
+        # ---- OLS partition-size sweep (BASELINE configs[3], second half): one pass to level 64 serves every S = 1..64
+        # (DP_impl.hpp:200-230), then the elbow regression (find_optimal_t); planted 4-level mixture as in
+        # solver_tests.py:181-201
+        if rank == 0:
+            from partitionsolvers_b200 import host as H
+            rs_o = np.random.RandomState(synth.SEED + 6)
+            a_o = (rs_o.choice([-20., -10., 10., 20.], size=5000) + rs_o.normal(0., 1., size=5000)).astype(np.float32)
+            b_o = np.ones(5000, np.float32)
+            H.DPSolver(5000, 64, a_o, b_o, 0, True, True, sweep_down=True, find_optimal_t=True, dtype=np.float32, ctx=ctx)
+            t0 = time.perf_counter()
+            s_o = H.DPSolver(5000, 64, a_o, b_o, 0, True, True, sweep_down=True, find_optimal_t=True, dtype=np.float32,
+                             ctx=ctx)
+            line["ols_sweep"] = {"n": 5000, "T_max": 64, "dtype": "f32", "score": "Gaussian risk-part",
+                                 "seconds": time.perf_counter() - t0, "device_ms": ctx.timings()["total_ms"],
+                                 "optimal_num_clusters_OLS": int(s_o.get_optimal_num_clusters_OLS_extern()),
+                                 "planted_levels": 4,
+                                 "what": "one solve to level 64 + 64 backtraces + host OLS (reference: find_optimal_t)"}
         # ---- every score of BASELINE configs[2] at full size (n=100000, T=16): Poisson on planted counts, Gaussian and
         # Rational on the real-valued mixture of solver_tests.py:145-146; device-timed host-buffer calls, best of 3
         if rank == 0:
