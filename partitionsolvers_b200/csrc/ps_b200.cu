@@ -628,8 +628,9 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       g.sa_nch = sa_nch;
       fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
     } else {
-      if (g.ntiles >= 2048) {
-        // tile -> (row block, chunk) table, rebuilt only when the geometry changes (kmax shrinks by one per level)
+      if ((long long)g.ntiles * R >= 2048) {
+        // tile -> (row block, chunk) table (one per geometry, shared by the instances of a batch), rebuilt only when the
+        // geometry changes (kmax shrinks by one per level)
         if (ctx->map_key[0] != g.NCH || ctx->map_key[1] != g.G || ctx->map_key[2] != g.NRB ||
             ctx->map_key[3] != g.ntiles) {
           PS_TRY(ensure(ctx, ctx->tile_map, (size_t)g.ntiles * sizeof(int2)));
