@@ -336,7 +336,7 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ r
       kb = k;
     }
   };
-  const int ns = max(4, min(32, len >> 7));
+  const int ns = max(4, min(32, len >> 8));
   const int sc = max(1, len / ns);
   for (int k = k0; k <= k1; k += sc) probe(k);
   probe(k1);
