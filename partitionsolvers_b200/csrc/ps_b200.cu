@@ -35,6 +35,7 @@ struct DevBuf {
 struct ps_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host -> device copies of the later parts of a large batch (solve_pipelined)
   std::string err;
   ps_timings tm;
   // grow-only device workspaces
@@ -351,7 +352,90 @@ ps_status sort_stage(ps_ctx* ctx, const ps_problem& p, const D* d_a, const D* d_
 }
 
 template <typename D>
-ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res) {
+ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res,
+                     const D* staged_a = nullptr, const D* staged_b = nullptr);
+
+// Large batches of independent instances from HOST buffers (randomization replicas): the batch is cut into parts; all
+// host -> device copies are queued on a second stream at once, and each part is solved as soon as its inputs have arrived,
+// so the copies of the later parts run under the kernels of the earlier ones.  Results are those of one call.
+template <typename D>
+ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D* b, ps_result* res, int parts) {
+  const int n = p.n, R = p.batch, Tc = std::min(p.T, n);
+  const int nS = p.sweep ? Tc + 1 : 1;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) PS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  const long long total = (long long)R * n;
+  PS_TRY(ensure(ctx, ctx->a_in, total * sizeof(D)));
+  PS_TRY(ensure(ctx, ctx->b_in, total * sizeof(D)));
+  D* d_a = (D*)ctx->a_in.p;
+  D* d_b = (D*)ctx->b_in.p;
+  const int per = cdiv(R, parts);
+  std::vector<cudaEvent_t> arrived;
+  // buffers of an earlier call may still be read by kernels on the compute stream
+  PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int r0 = 0; r0 < R; r0 += per) {
+    const long long off = (long long)r0 * n, cnt = (long long)std::min(per, R - r0) * n;
+    PS_CUDA(ctx, cudaMemcpyAsync(d_a + off, a + off, cnt * sizeof(D), cudaMemcpyHostToDevice, ctx->copy_stream));
+    PS_CUDA(ctx, cudaMemcpyAsync(d_b + off, b + off, cnt * sizeof(D), cudaMemcpyHostToDevice, ctx->copy_stream));
+    cudaEvent_t e;
+    PS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    PS_CUDA(ctx, cudaEventRecord(e, ctx->copy_stream));
+    arrived.push_back(e);
+  }
+  ps_timings agg;
+  memset(&agg, 0, sizeof(agg));
+  ps_status st = PS_OK;
+  int part = 0;
+  for (int r0 = 0; r0 < R && st == PS_OK; r0 += per, ++part) {
+    const int rk = std::min(per, R - r0);
+    const long long off = (long long)r0 * n;
+    ps_problem pk = p;
+    pk.batch = rk;
+    if (p.perm) pk.perm = p.perm + off;
+    ps_result rk_res = *res;
+    if (res->perm) rk_res.perm = res->perm + off;
+    if (res->bounds) rk_res.bounds = res->bounds + (long long)r0 * nS * (Tc + 1);
+    if (res->subset_scores) rk_res.subset_scores = (D*)res->subset_scores + (long long)r0 * nS * Tc;
+    if (res->max_score) rk_res.max_score = (D*)res->max_score + (long long)r0 * (Tc + 1) * n;
+    if (res->next_start) rk_res.next_start = res->next_start + (long long)r0 * (Tc + 1) * n;
+    cudaError_t ce = cudaStreamWaitEvent(ctx->stream, arrived[part], 0);
+    if (ce != cudaSuccess) {
+      ctx->err = std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(ce);
+      st = PS_ERR_CUDA;
+      break;
+    }
+    st = solve_impl<D>(ctx, &pk, a + off, b + off, &rk_res, d_a + off, d_b + off);
+    if (st != PS_OK) break;
+    const ps_timings& t = ctx->tm;
+    agg.total_ms += t.total_ms;
+    agg.sort_scan_ms += t.sort_scan_ms;
+    agg.prepass_ms += t.prepass_ms;
+    agg.levels_ms += t.levels_ms;
+    agg.backtrace_ms += t.backtrace_ms;
+    agg.d2h_ms += t.d2h_ms;
+    agg.n_levels = t.n_levels;
+    for (int q = 0; q < t.n_levels; ++q) {
+      agg.level_ms[q] += t.level_ms[q];
+      agg.level_cells[q] += t.level_cells[q];
+    }
+    agg.kernel_launches += t.kernel_launches;
+    agg.d2h_bytes += t.d2h_bytes;
+    agg.screen_used = t.screen_used;
+    agg.screen_exact_cells += t.screen_exact_cells;
+    agg.screen_violations += t.screen_violations;
+    for (int q = 0; q < 6; ++q) agg.screen_tiers[q] += t.screen_tiers[q];
+  }
+  cudaStreamSynchronize(ctx->copy_stream);
+  for (cudaEvent_t e : arrived) cudaEventDestroy(e);
+  if (st != PS_OK) return st;
+  agg.h2d_bytes = 2 * total * (long long)sizeof(D) + (p.perm ? total * (long long)sizeof(int) : 0);
+  ctx->tm = agg;
+  return PS_OK;
+}
+
+template <typename D>
+ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res, const D* staged_a,
+                     const D* staged_b) {
   if (!ctx) return PS_ERR_INVALID;
   ctx->err.clear();
   if (!pp || !a || !b || !res) {
@@ -380,6 +464,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     return PS_ERR_INVALID;
   }
   const int n = p.n, R = p.batch;
+  if (!staged_a && !p.on_device && R >= 256 && (long long)R * n * sizeof(D) >= (16LL << 20))
+    return solve_pipelined<D>(ctx, p, a, b, res, 4);
   const int Tc = std::min(p.T, n);  // DP_impl.hpp:37-38
   int running = (p.sum_mode == PS_SUM_RUNNING);  // cleared below when the screened path takes over (exact sums)
   const int rp = p.risk_part ? 1 : 0;
@@ -402,7 +488,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // ---- inputs
   const D* d_a = a;
   const D* d_b = b;
-  if (!p.on_device) {
+  if (staged_a) {  // inputs already on the device (a part of a pipelined batch)
+    d_a = staged_a;
+    d_b = staged_b;
+  } else if (!p.on_device) {
     PS_TRY(ensure(ctx, ctx->a_in, total * sizeof(D)));
     PS_TRY(ensure(ctx, ctx->b_in, total * sizeof(D)));
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->a_in.p, a, total * sizeof(D), in_kind, st));
@@ -1122,6 +1211,7 @@ void ps_destroy(ps_ctx* ctx) {
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 

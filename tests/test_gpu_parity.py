@@ -309,3 +309,17 @@ def test_one_million_elements_sampled_rows(oracle, ctx):
     # level 1 itself: S(i, n) for a few i
     for i in (0, 12345, n - 1):
         assert r["max_score"][1][i] == oracle.range_score(a_s, b_s, 1, False, i, n, dtype=np.float64)
+
+
+def test_large_host_batch_is_pipelined_with_identical_results(ctx):
+    """Host-buffer batches of >= 256 instances and >= 16 MB are cut into parts whose copies overlap the kernels of the
+    parts before them (solve_pipelined): same outputs as the same instances solved in smaller, unpipelined calls."""
+    n, T, R = 7000, 4, 320
+    a, b = synth.poisson_null(n, seed=synth.SEED + 90, dtype=np.float64, replicas=R)
+    whole = ctx.solve_raw(a, b, T, 1, False, dtype=np.float64, levels=True, sweep=True)
+    t = ctx.timings()
+    assert t["h2d_bytes"] == 2 * R * n * 8 and t["kernel_launches"] > 0
+    for lo, hi in ((0, 150), (150, 320)):
+        part = ctx.solve_raw(a[lo:hi], b[lo:hi], T, 1, False, dtype=np.float64, levels=True, sweep=True)
+        for k in ("perm", "bounds", "subset_scores", "max_score", "next_start"):
+            assert np.array_equal(whole[k][lo:hi], part[k]), (k, lo)
