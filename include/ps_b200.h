@@ -65,7 +65,9 @@ typedef struct ps_problem {
   int sort_mode;   /* PS_SORT_*                                                                       */
   const int* perm; /* PS_SORT_GIVEN: [batch][n] permutation, position -> original index              */
   int sweep;       /* 0: backtrace S=T only (DP_impl.hpp:226-228); 1: every S=T..1 (:203-214)         */
-  int batch;       /* independent instances R>=1 (replicas); a,b are [R][n] row-major                 */
+  int batch;       /* independent instances R>=1 (replicas); a,b are [R][n] row-major.  Host-buffer    */
+                   /* batches of >= 256 instances and >= 16 MB are solved in four parts whose copies   */
+                   /* overlap the kernels of the parts before them (same outputs as one call)          */
   int on_device;   /* 1: a, b, perm AND every ps_result pointer are device pointers on ctx's device   */
   int no_fast_math;/* debug: 1 = never take the range-prechecked branch-free math path (csrc/math_fast.cuh);  */
                    /*        2 = take it, but not the packed two-rows-per-thread float kernel               */
