@@ -552,12 +552,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     // screening needs positive sums for every score (relative error of the float range sums) and exact summability
     screen = want_screen && fast && (host_flags & 2) == 0 && (host_flags & 4) == 0;
     // double inputs whose sums round: float bounds from fixed-point prefix sums, survivors from the reference's running sums
-    // (measured crossover against the exhaustive kernel: n ~ 16000, tools/run_c3r.py; audit runs take it at any size)
+    // (measured crossover against the exhaustive kernel at T = 8: n ~ 14000 for double, ~ 10000 for float, tools/run_c3r.py threshold; audit runs take it at any size)
     screen_run = want_screen && fast && !screen && sizeof(D) == 8 && (host_flags & 8) == 0 &&
-                 (n >= 16384 || p.screen == 2);
+                 (n >= 14336 || p.screen == 2);
     // float inputs whose sums round, A^2/B scores: bounds from the running sums themselves (per-block checkpoints)
     screen_run32 = want_screen && fast && !screen && sizeof(D) == 4 && ScreenRun32Launch::supported(p.dist, rp) &&
-                   (host_flags & 16) == 0 && (n >= 16384 || p.screen == 2) &&
+                   (host_flags & 16) == 0 && (n >= 10240 || p.screen == 2) &&
                    (double)R * cp_rows * n * 8.0 <= 8e9;
   }
   if (screen) running = 0;  // exactly summable: prefix differences ARE the reference's running sums, bit for bit

@@ -32,7 +32,7 @@ elif mode == "tiers":
               "| groups kept %.2f%% of all" % (100 * gk * 8 * 32 / cells),
               "| exact %.2f%%" % (100 * t["screen_exact_cells"] / cells))
 else:
-    for n in (4000, 6000, 8000, 10000, 12000, 16000):
+    for n in (6000, 8000, 10000, 12000, 14000, 16000, 20000):
         a, b = synth.gaussian_mixture(n, 8, seed=synth.SEED + 3, dtype=dt)
         out = []
         for scr in (1, 0):
