@@ -16,6 +16,12 @@ count, BASELINE.json); `actual_cells_per_s` is the exact (i,k) count / time.
           value = N * n^2*T / max-over-ranks time.  The replica workload (configs[3]) is reported in
           "mc_replicas" (4096 instances split over the ranks).
 
+Extras on the same JSON line (skipped by --no-extras): other_level_kernel (the exhaustive kernel on the headline workload),
+variants (other precision, other sum mode), c3_all_scores (every score x objective x precision at n=100000, T=16),
+mc_replicas + cpu_replicas_baseline (configs[3] next to the reference's ThreadPool variant), ols_sweep, null_table_paper_scale,
+small_configs (configs[0], [1]), sharded (N > 1: configs[4], rows sharded with an NCCL all-gather per level), cpu_baseline,
+cpu_baseline_all_cores.  stdout carries exactly one line.
+
 --impl reference times the reference's own CPU solver (oracle/_ref = the unmodified reference headers;
 the port only if that library is absent) on a bounded sample of the same workload.
 """
