@@ -55,6 +55,8 @@ struct Geom {
   // SA/SB checkpoints may be kept at a finer spacing than the k-chunks (screen_run.cuh, float inputs): the sums at chunk
   // boundary c L live in row c * sa_mul of arrays with sa_nch rows per instance.  Default: 1, nch_alloc.
   int sa_mul, sa_nch;
+  // live-tile kernels (screen.cuh): partial slots per k-chunk (an expensive tile is split into up to nsub parts); default 1
+  int nsub;
 };
 
 __host__ __device__ inline int geom_count_tiles(int NCH, int G, int NRB, int rb_first, int rb_step) {

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -40,7 +41,8 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp, fxinfo, pfx, cpA, cpB, ipos;
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp, fxinfo, pfx, cpA, cpB, ipos,
+      live, rb_info, live_hdr, kbest, rb_slots, rb_cnt;  // live-tile protocol of the screened levels (screen.cuh)
   int stamp = 0;  // last stamp handed to a screened level (tile_stamp holds the stamp of the level that wrote a tile)
   int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
@@ -48,6 +50,9 @@ struct ps_ctx {
   long long launches = 0;
   int* pinned_flags = nullptr;  // [0] range/exactness flags, [2..5] screen counters (as 2 x u64)
   int last_fast = 0;
+  int dbg_level = 0;  // development: record per-tile times of this level (PS_DEBUG_LEVEL)
+  DevBuf dbg;
+  int sm_count = 148;
 };
 
 struct ps_shard {
@@ -72,6 +77,12 @@ struct ps_shard {
   int2* tile_map = nullptr;
   int map_key[4] = {-1, -1, -1, -1};
   unsigned long long* counters = nullptr;
+  int4* live = nullptr;        // live-tile protocol of the screened levels (screen.cuh)
+  unsigned int* rb_info = nullptr;  // per-tile stage masks
+  ps::LiveHdr* live_hdr = nullptr;  // one header per level
+  int* kbest = nullptr;             // per row: position of the best lower-bound sample (cost hint)
+  int* rb_slots = nullptr;          // per row block: slots that hold a partial, ascending
+  int* rb_cnt = nullptr;
 };
 
 namespace {
@@ -187,14 +198,34 @@ struct LastLevelLaunch {
 
 template <typename D>
 struct ScreenLaunch {
+  // screened level, exactly summable inputs (screen.cuh): select kernel (range tiers -> compacted list of live tiles) and
+  // the persistent live-tile kernel (group / cell tiers + the fold of a finished row block)
+  using SelFn = void (*)(ps::Geom, const ps::Rec4<D>*, const D*, const float*, int, const int*, int4*, long long,
+                         unsigned int*, int, ps::LiveHdr*, unsigned long long*, const int*, int*, int*);
   using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*, const int*,
-                      const float*, int, int*, int, int);
-  using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, float4*, D*, float*, int);
+                      const int4*, long long, ps::LiveHdr*, unsigned long long*);
+  using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, float4*, D*, float*, int, int*);
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
 #define PS_PICK(DI, RPV)                                                             \
-  return audit ? (Fn)level_tile_screen_kernel<D, DI, RPV, true, BR>                  \
-               : (Fn)level_tile_screen_kernel<D, DI, RPV, false, BR>;
+  return audit ? (Fn)level_live_screen_kernel<D, DI, RPV, true, BR>                  \
+               : (Fn)level_live_screen_kernel<D, DI, RPV, false, BR>;
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: PS_PICK(DIST_GAUSSIAN, false)
+      case 1: PS_PICK(DIST_GAUSSIAN, true)
+      case 2: PS_PICK(DIST_POISSON, false)
+      case 3: PS_PICK(DIST_POISSON, true)
+      default: PS_PICK(DIST_RATIONAL, false)
+    }
+#undef PS_PICK
+  }
+  static SelFn pick_select(int dist, int rp, int audit, int tpr) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                                               \
+  return audit ? (tpr == 4 ? (SelFn)screen_select_kernel<D, DI, RPV, true, 4>                          \
+                           : (SelFn)screen_select_kernel<D, DI, RPV, true, 1>)                         \
+               : (tpr == 4 ? (SelFn)screen_select_kernel<D, DI, RPV, false, 4>                         \
+                           : (SelFn)screen_select_kernel<D, DI, RPV, false, 1>);
     switch (dist * 2 + (rp ? 1 : 0)) {
       case 0: PS_PICK(DIST_GAUSSIAN, false)
       case 1: PS_PICK(DIST_GAUSSIAN, true)
@@ -290,6 +321,7 @@ ps::Geom make_geom(int n, int j, int Tc, int L, int nch_alloc, int rb_first, int
   g.tile_map = nullptr;
   g.sa_mul = 1;
   g.sa_nch = nch_alloc;
+  g.nsub = 1;
   return g;
 }
 
@@ -508,6 +540,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   const bool want_fast = running && p.no_fast_math != 1;
   // screened levels (screen.cuh): worth it once a level has enough cells to amortise the extra launch
   const bool want_screen = want_fast && p.screen != 1 && p.no_fast_math == 0 && std::min(p.T, n) >= 3 && n >= 512 &&
+                           n <= 4000000 &&            // tile geometry of the live-tile kernels (<= 32 stages, <= 1000 chunks)
                            (long long)n * R >= 6000;  // measured crossover (tools/screen_threshold.py)
   if (want_fast) {
     PS_TRY(ensure(ctx, ctx->scalar, 64));
@@ -599,8 +632,15 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);
   // at most ~200 chunks so that the per-chunk partials stay small
   if ((screen || screen_run || screen_run32) && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
+  if (screen) {
+    L = std::min(L, ps::SCR_MAX_G * BR);                   // the live-stage mask of a tile is one 32-bit word
+    L = std::max(L, cdiv(cdiv(n, 1000), BR) * BR);         // <= 1000 chunks: per-chunk staging of the select kernel
+  }
   const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
-  const long long pstride = (long long)nch_alloc * n;
+  // live-tile kernels: partial slots per k-chunk.  One big instance: the tiles around a row block's maximum are split into
+  // two work items (otherwise a single tile runs for most of a level; measured: 2 beats 1 and 4 at L = 512); batches have enough tiles to level the SMs
+  int nsub = (screen && R < 64 && p.screen != 2) ? std::min(2, L / BR) : 1;
+  const long long pstride = (long long)nch_alloc * nsub * n;
   PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
   PS_TRY(ensure(ctx, ctx->part_arg, R * pstride * sizeof(int)));
   D* d_pv = (D*)ctx->part_val.p;
@@ -623,6 +663,19 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     }
     PS_TRY(ensure(ctx, ctx->scr_counters, 8 * sizeof(unsigned long long)));
     PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 8 * sizeof(unsigned long long), st));
+    // live-tile protocol: the compacted tile list (every tile could be live), one segment record per row block, one header
+    // (tiles appended, cursor) per level
+    PS_TRY(ensure(ctx, ctx->live, (size_t)ps::SCR_CLASSES * R * nch_alloc * nsub * cdiv(n, BR) * sizeof(int4)));
+    PS_TRY(ensure(ctx, ctx->rb_info, (size_t)R * nch_alloc * nsub * cdiv(n, BR) * sizeof(unsigned int)));  // per-slot stage masks
+    PS_TRY(ensure(ctx, ctx->live_hdr, (size_t)(Tc + 2) * sizeof(ps::LiveHdr)));
+    PS_TRY(ensure(ctx, ctx->kbest, (size_t)R * n * sizeof(int)));
+    PS_TRY(ensure(ctx, ctx->rb_slots, (size_t)R * nch_alloc * nsub * cdiv(n, BR) * sizeof(int)));
+    PS_TRY(ensure(ctx, ctx->rb_cnt, (size_t)R * cdiv(n, BR) * sizeof(int)));
+    PS_CUDA(ctx, cudaMemsetAsync(ctx->live_hdr.p, 0, (size_t)(Tc + 2) * sizeof(ps::LiveHdr), st));
+    if (ctx->dbg_level) {
+      PS_TRY(ensure(ctx, ctx->dbg, (size_t)R * nch_alloc * nsub * cdiv(n, BR) * 32));
+      PS_CUDA(ctx, cudaMemsetAsync(ctx->dbg.p, 0, (size_t)R * nch_alloc * nsub * cdiv(n, BR) * 32, st));
+    }
     return PS_OK;
   };
   // checkpoints of the running sums: at the k-chunk boundaries, or (float running-sum screen) at every 128-block boundary
@@ -699,6 +752,9 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   }
   auto fn_last = LastLevelLaunch<D>::pick(p.dist, rp, running, fast);
   auto fn_scr = ScreenLaunch<D>::pick(p.dist, rp, p.screen == 2);
+  // select kernel: four threads per row once a row block has enough tiles to share out
+  const int sel_tpr = (nch_alloc >= 32) ? 4 : 1;
+  auto fn_sel = ScreenLaunch<D>::pick_select(p.dist, rp, p.screen == 2, sel_tpr);
   auto fn_lb = ScreenLaunch<D>::pick_lb(p.dist, rp);
   D* d_lb = (D*)ctx->lb.p;
   unsigned long long* d_cnt = (unsigned long long*)ctx->scr_counters.p;
@@ -708,6 +764,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     const ps::Rec4<D>* rin = recs[(j - 1) & 1];
     ps::Rec4<D>* rout = recs[j & 1];
     const bool timed = (j - 2) < PS_MAX_TIMED_LEVELS;
+    bool fused_fold = false;  // the level kernel wrote maxScore_ / nextStart_ itself (live-tile kernels)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) PS_TRY(mark(ctx, &e0));
     if (j == Tc && Tc >= 2) {
@@ -717,7 +774,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       g.sa_nch = sa_nch;
       fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
     } else {
-      if ((long long)g.ntiles * R >= 2048) {
+      if (!screen && (long long)g.ntiles * R >= 2048) {
         // tile -> (row block, chunk) table (one per geometry, shared by the instances of a batch), rebuilt only when the
         // geometry changes (kmax shrinks by one per level)
         if (ctx->map_key[0] != g.NCH || ctx->map_key[1] != g.G || ctx->map_key[2] != g.NRB ||
@@ -756,27 +813,53 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
           ctx->launches++;
         }
       } else if (screen) {
-        // row lower bounds from a few exactly evaluated cells, then the screened tiles
+        // row lower bounds from a few exactly evaluated cells; range tiers for every tile -> compacted list of live tiles;
+        // persistent CTAs work the list off and fold finished row blocks (no combine launch)
         fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, (float*)ctx->scr_bmax.p,
-                                                           n / ps::SCR_BLOCK + 2);
-        fn_scr<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt,
-                                                 (const int*)ctx->scalar.p, (const float*)ctx->scr_bmax.p,
-                                                 n / ps::SCR_BLOCK + 2, (int*)ctx->tile_stamp.p, ++ctx->stamp,
-                                                 cdiv(n, BR));
-        ctx->launches++;
+                                                           n / ps::SCR_BLOCK + 2, (int*)ctx->kbest.p);
+        ps::LiveHdr* hdr = (ps::LiveHdr*)ctx->live_hdr.p + j;
+        const long long live_cap = (long long)R * nch_alloc * nsub * cdiv(n, BR);
+        g.nsub = nsub;
+        fn_sel<<<dim3(g.NRB, R), 128 * sel_tpr, (size_t)g.NCH * (4 * sizeof(D) + 12 + nsub), st>>>(
+            g, rin, d_lb, (const float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2, (const int*)ctx->scalar.p,
+            (int4*)ctx->live.p, live_cap, (unsigned int*)ctx->rb_info.p, cdiv(n, BR), hdr, d_cnt,
+            (const int*)ctx->kbest.p, (int*)ctx->rb_slots.p, (int*)ctx->rb_cnt.p);
+        ps::LevelOut<D> lo;
+        lo.ms_row = d_ms + (long long)j * n;
+        lo.ns_row = d_ns + (long long)j * n;
+        lo.table_stride = table_stride;
+        lo.rec_next = rout;
+        lo.pm_next = (sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr;
+        lo.shard_chunk = nullptr;
+        // persistent CTAs, 8 per SM (64 registers): they pull tiles until the list is empty
+        const int grid_live = (int)std::min<long long>((long long)g.ntiles * R * nsub, (long long)ctx->sm_count * 8);
+        fn_scr<<<grid_live, BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt, (const int*)ctx->scalar.p,
+                                         (const int4*)ctx->live.p, live_cap, hdr,
+                                         (ctx->dbg_level == j) ? (unsigned long long*)ctx->dbg.p : nullptr);
+        if (g.NCH >= 32)  // four lanes per row once a row has enough chunks to fold
+          ps::screen_fold_kernel<D, BR, 4><<<dim3(g.NRB, R), BR * 4, 0, st>>>(
+              g, (const int*)ctx->rb_slots.p, (const int*)ctx->rb_cnt.p, cdiv(n, BR), d_pv, d_pa, lo);
+        else
+          ps::screen_fold_kernel<D, BR, 1><<<dim3(g.NRB, R), BR, 0, st>>>(
+              g, (const int*)ctx->rb_slots.p, (const int*)ctx->rb_cnt.p, cdiv(n, BR), d_pv, d_pa, lo);
+        ctx->launches += 3;
+        fused_fold = true;
       } else {
         fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
       }
     }
     if (timed) PS_TRY(mark(ctx, &e1));
-    const bool wide_combine = g.NCH >= 32;  // four lanes per row once a row has enough chunks to fold
-    auto fn_combine = wide_combine ? ps::combine_kernel<D, BR, 4> : ps::combine_kernel<D, BR, 1>;
-    fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
-        g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
-        ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
-        ((screen || screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp,
-        cdiv(n, BR));
-    ctx->launches += 2;
+    if (!fused_fold) {
+      const bool wide_combine = g.NCH >= 32;  // four lanes per row once a row has enough chunks to fold
+      auto fn_combine = wide_combine ? ps::combine_kernel<D, BR, 4> : ps::combine_kernel<D, BR, 1>;
+      fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
+          g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
+          ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
+          ((screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp,
+          cdiv(n, BR));
+      ctx->launches++;
+    }
+    ctx->launches++;
     if (timed) {
       lev_ev.push_back({e0, e1});
       ctx->tm.level_cells[j - 2] = level_cells(n, j, Tc) * R;
@@ -816,6 +899,16 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   PS_TRY(mark(ctx, &e_end));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->dbg_level && screen && ctx->dbg.p) {
+    const size_t cnt = (size_t)R * nch_alloc * nsub * cdiv(n, BR) * 4;
+    std::vector<unsigned long long> h(cnt);
+    cudaMemcpy(h.data(), ctx->dbg.p, cnt * 8, cudaMemcpyDeviceToHost);
+    const char* path = getenv("PS_DEBUG_FILE");
+    if (FILE* f = fopen(path ? path : "tile_times.bin", "wb")) {
+      fwrite(h.data(), 8, cnt, f);
+      fclose(f);
+    }
+  }
   ctx->tm.screen_used = screen ? 1 : ((screen_run || screen_run32) ? 2 : 0);
   if (screen || screen_run || screen_run32) {
     unsigned long long cnt[8];
@@ -983,7 +1076,7 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
     PS_CUDA(ctx, cudaMalloc((void**)&s->dflags, 2 * sizeof(int)));
     PS_CUDA(ctx, cudaMemsetAsync(s->dflags, 0, 2 * sizeof(int), st));
     ps::range_check_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, a_s, b_s, s->dflags);
-    const bool want_screen = pp->screen != 1 && pp->screen != 2 && pp->no_fast_math == 0 && Tc >= 3 && n >= 6000;
+    const bool want_screen = pp->screen != 1 && pp->screen != 2 && pp->no_fast_math == 0 && Tc >= 3 && n >= 6000 && n <= 4000000;
     if (want_screen) {
       PS_TRY(ensure(ctx, ctx->scr_stats, sizeof(ps::ScreenStats)));
       ps::ScreenStats* d_st = (ps::ScreenStats*)ctx->scr_stats.p;
@@ -1001,6 +1094,8 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   if (s->screen) {
     running = 0;  // exactly summable inputs: prefix differences are the reference's running sums, bit for bit
     s->L = std::min(s->L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
+    s->L = std::min(s->L, ps::SCR_MAX_G * BR);
+    s->L = std::max(s->L, cdiv(cdiv(n, 1000), BR) * BR);
     s->nch_alloc = std::max(1, cdiv(std::max(1, n - 1), s->L));
   }
   const long long pstride = (long long)s->nch_alloc * n;
@@ -1015,8 +1110,15 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   if (s->screen) {
     PS_CUDA(ctx, cudaMalloc(&s->lb, (size_t)n * sizeof(D)));
     PS_CUDA(ctx, cudaMalloc((void**)&s->bmax, (size_t)(n / ps::SCR_BLOCK + 2) * sizeof(float)));
-    PS_CUDA(ctx, cudaMalloc((void**)&s->counters, 2 * sizeof(unsigned long long)));
-    PS_CUDA(ctx, cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned long long), st));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->counters, 8 * sizeof(unsigned long long)));
+    PS_CUDA(ctx, cudaMemsetAsync(s->counters, 0, 8 * sizeof(unsigned long long), st));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->live, (size_t)ps::SCR_CLASSES * s->nch_alloc * (s->owned_blocks + 1) * sizeof(int4)));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->rb_info, (size_t)s->nch_alloc * cdiv(n, BR) * sizeof(unsigned int)));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->kbest, (size_t)n * sizeof(int)));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->rb_slots, (size_t)s->nch_alloc * cdiv(n, BR) * sizeof(int)));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->rb_cnt, (size_t)cdiv(n, BR) * sizeof(int)));
+    PS_CUDA(ctx, cudaMalloc((void**)&s->live_hdr, (size_t)(Tc + 2) * sizeof(ps::LiveHdr)));
+    PS_CUDA(ctx, cudaMemsetAsync(s->live_hdr, 0, (size_t)(Tc + 2) * sizeof(ps::LiveHdr), st));
   }
   if (running)
     ps::build_rec_running_kernel<D><<<dim3(cdiv(n + 1, 256), 1), 256, 0, st>>>(n, rec_stride, a_s, b_s, rec0,
@@ -1096,26 +1198,30 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
   cudaStream_t st = ctx->stream;
   PS_CUDA(ctx, cudaMemsetAsync(my_chunk, 0, (size_t)s->chunk_rows * sizeof(D), st));
   if (g.ntiles > 0 && s->screen && j < Tc) {
-    if (g.ntiles >= 2048) {
-      if (s->map_key[0] != g.NCH || s->map_key[1] != g.G || s->map_key[2] != g.NRB || s->map_key[3] != g.ntiles) {
-        if (s->tile_map) PS_CUDA(ctx, cudaFree(s->tile_map));
-        s->tile_map = nullptr;
-        PS_CUDA(ctx, cudaMalloc((void**)&s->tile_map, (size_t)g.ntiles * sizeof(int2)));
-        ps::build_tile_map_kernel<<<cdiv(g.ntiles, 128), 128, 0, st>>>(g, s->tile_map);
-        s->map_key[0] = g.NCH, s->map_key[1] = g.G, s->map_key[2] = g.NRB, s->map_key[3] = g.ntiles;
-      }
-      g.tile_map = s->tile_map;
-    }
-    // lower bounds and pm maxima for every row / record (cheap; each rank needs them for all k), owned tiles only
+    // lower bounds and pm maxima for every row / record (cheap; each rank needs them for all k); range tiers, live tiles and
+    // the fold for owned row blocks only
     float4* rf = (sizeof(D) == 8) ? s->recf + (long long)s->cur * rec_stride : (float4*)rin;
-    auto fn_lb = ScreenLaunch<D>::pick_lb(s->p.dist, s->p.risk_part ? 1 : 0);
-    auto fn_scr = ScreenLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, 0);
-    fn_lb<<<dim3(cdiv(g.nrows, 128), 1), 128, 0, st>>>(g, rin, rf, (D*)s->lb, s->bmax, n / ps::SCR_BLOCK + 2);
-    fn_scr<<<dim3(g.ntiles, 1), BR, 0, st>>>(g, rin, rf, (const D*)s->lb, (D*)s->part_val, s->part_arg, s->counters,
-                                             s->dflags, s->bmax, n / ps::SCR_BLOCK + 2, nullptr, 0, 0);
-    ps::combine_kernel<D, BR, 4><<<dim3(cdiv(4LL * g.NRB * BR, 256), 1), 256, 0, st>>>(
-        g, (const D*)s->part_val, s->part_arg, (D*)nullptr, s->ns + (long long)j * n, 0,
-        (ps::Rec4<D>*)nullptr, my_chunk, nullptr);
+    const int rp = s->p.risk_part ? 1 : 0;
+    auto fn_lb = ScreenLaunch<D>::pick_lb(s->p.dist, rp);
+    const int sel_tpr = (s->nch_alloc >= 32) ? 4 : 1;
+    auto fn_sel = ScreenLaunch<D>::pick_select(s->p.dist, rp, 0, sel_tpr);
+    auto fn_scr = ScreenLaunch<D>::pick(s->p.dist, rp, 0);
+    fn_lb<<<dim3(cdiv(g.nrows, 128), 1), 128, 0, st>>>(g, rin, rf, (D*)s->lb, s->bmax, n / ps::SCR_BLOCK + 2, s->kbest);
+    const long long live_cap = (long long)s->nch_alloc * (s->owned_blocks + 1);
+    fn_sel<<<dim3(g.NRB, 1), 128 * sel_tpr, (size_t)g.NCH * (4 * sizeof(D) + 12 + 1), st>>>(
+        g, rin, (const D*)s->lb, s->bmax, n / ps::SCR_BLOCK + 2, s->dflags, s->live, live_cap, s->rb_info, cdiv(n, BR),
+        s->live_hdr + j, s->counters, s->kbest, s->rb_slots, s->rb_cnt);
+    ps::LevelOut<D> lo;
+    lo.ms_row = nullptr;
+    lo.ns_row = s->ns + (long long)j * n;
+    lo.table_stride = 0;
+    lo.rec_next = nullptr;
+    lo.pm_next = nullptr;
+    lo.shard_chunk = my_chunk;
+    fn_scr<<<std::min(g.ntiles, ctx->sm_count * 8), BR, 0, st>>>(g, rin, rf, (const D*)s->lb, (D*)s->part_val, s->part_arg,
+                                                        s->counters, s->dflags, s->live, live_cap, s->live_hdr + j, nullptr);
+    ps::screen_fold_kernel<D, BR, 4><<<dim3(g.NRB, 1), BR * 4, 0, st>>>(g, s->rb_slots, s->rb_cnt, cdiv(n, BR),
+                                                                       (const D*)s->part_val, s->part_arg, lo);
   } else if (g.ntiles > 0) {
     const int running = (s->p.sum_mode == PS_SUM_RUNNING) && !s->screen;
     auto fn = LevelLaunch<D>::pick(s->p.dist, s->p.risk_part ? 1 : 0, running, s->fast);
@@ -1193,6 +1299,11 @@ ps_status ps_create(ps_ctx** out, int device) {
     return PS_ERR_CUDA;
   }
   memset(&ctx->tm, 0, sizeof(ctx->tm));
+  if (const char* e = getenv("PS_DEBUG_LEVEL")) ctx->dbg_level = atoi(e);
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
+  }
   *out = ctx;
   return PS_OK;
 }
@@ -1205,7 +1316,8 @@ void ps_destroy(ps_ctx* ctx) {
                     &ctx->a_s,   &ctx->b_s,      &ctx->rec,      &ctx->SA,      &ctx->SB,     &ctx->part_val,
                     &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->sort_hist,
                     &ctx->scalar, &ctx->recf,    &ctx->lb,       &ctx->scr_stats, &ctx->scr_counters, &ctx->tile_map,
-                    &ctx->scr_bmax, &ctx->tile_stamp, &ctx->fxinfo, &ctx->pfx, &ctx->cpA, &ctx->cpB, &ctx->ipos};
+                    &ctx->scr_bmax, &ctx->tile_stamp, &ctx->fxinfo, &ctx->pfx, &ctx->cpA, &ctx->cpB, &ctx->ipos,
+                    &ctx->live, &ctx->rb_info, &ctx->live_hdr, &ctx->kbest, &ctx->rb_slots, &ctx->rb_cnt};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -1349,6 +1461,12 @@ void ps_shard_destroy(ps_shard* s) {
   cudaFree(s->dflags);
   cudaFree(s->tile_map);
   cudaFree(s->counters);
+  cudaFree(s->live);
+  cudaFree(s->rb_info);
+  cudaFree(s->live_hdr);
+  cudaFree(s->kbest);
+  cudaFree(s->rb_slots);
+  cudaFree(s->rb_cnt);
   delete s;
 }
 

@@ -298,7 +298,7 @@ __device__ __forceinline__ D screen_exact_score(D A, D B, const GlogEntry* s_log
 template <typename D, int DIST, bool RP>
 __global__ void __launch_bounds__(128)
 screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ recf, D* __restrict__ LB,
-                 float* __restrict__ bmax, int nblk) {
+                 float* __restrict__ bmax, int nblk, int* __restrict__ kbest = nullptr) {
   const int inst = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nrows) return;
@@ -336,69 +336,325 @@ screen_lb_kernel(Geom g, const Rec4<D>* __restrict__ rec, float4* __restrict__ r
       kb = k;
     }
   };
+  // a sweep k = lo, lo + step, ... <= hi, four samples at a time: the record loads of a batch are independent and issued
+  // together (one thread walks one row, so nothing else hides their latency); ties keep the earlier sample
+  auto sweep = [&](const int lo, const int hi, const int step) {
+    for (int k = lo; k <= hi; k += 4 * step) {
+      Rec4<D> r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = rec[min(k + u * step, hi)];
+      D v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = add_rn<D>(screen_exact_score<D, DIST, RP, false>(sub_rn<D>(r[u].x, Xi), sub_rn<D>(r[u].y, Yi), nullptr), r[u].p);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k + u * step <= hi && v[u] > best) {
+          best = v[u];
+          kb = k + u * step;
+        }
+    }
+  };
   const int ns = max(4, min(32, len >> 8));
   const int sc = max(1, len / ns);
-  for (int k = k0; k <= k1; k += sc) probe(k);
+  sweep(k0, k1, sc);
   probe(k1);
   if (sc > 1) {
     const int lo = max(k0, kb - sc), hi = min(k1, kb + sc);
-    const int sf = max(1, (hi - lo) / ns);
-    for (int k = lo; k <= hi; k += sf) probe(k);
+    sweep(lo, hi, max(1, (hi - lo) / ns));
   }
   LB[(long long)inst * g.n + i] = best;
+  if (kbest) kbest[(long long)inst * g.n + i] = kb;  // where the row's best sample sits: the select kernel's cost hint
 }
 
 // ---------------------------------------------------------------------------------------------
-// One (row block, k-chunk) tile of one level, screened.  Same tiling, launch order and partial/combine protocol as
-// level_tile_kernel; a stage = one 128-block of k.  Four tiers, cheapest first:
-//   tile   (scores monotone in k) ONE bound for the whole tile, before anything is staged;
-//   stage  (scores monotone in k) ONE bound per 128 cells: S(i,k) <= S(i,k_last), pm[k] <= largest pm of the stage;
-//   group  (same) one bound per 8 cells, with the group's largest pm;
+// Screened level = four launches:
+//   screen_lb_kernel      row lower bounds + group / block maxima of pm (above);
+//   screen_select_kernel  the RANGE tiers for every (row block, k-chunk) tile, before anything heavy is launched: one bound
+//                         per (row, tile) and, where that does not already lose, one per (row, 128-cell stage) -- S at the
+//                         stage's last cell + the stage's largest pm.  A tile none of whose stages can hold a row maximum is
+//                         dropped here; the others are appended, with their mask of live stages, to a compacted list
+//                         (one list per cost class); every tile's mask is also kept for the fold;
+//   level_live_screen_kernel   persistent CTAs pull live tiles from that list (atomic cursor) and run the group and cell
+//                         tiers on the live stages only.  Dropped tiles cost nothing;
+//   screen_fold_kernel    folds every row block's partials over its live tiles only, in ascending k (strict >: first maximum
+//                         wins, as in combine_kernel) and writes maxScore_[j], nextStart_[j] and the next level's p / pm.
+// Tiers inside a live tile, cheapest first:
+//   stage  (scores monotone in k) re-checked with the threshold the tile has raised so far;
+//   group  one bound per 8 cells, with the group's largest pm;
 //   cell   one bound per cell, 8 independent chains, one vote; a group with a survivor is evaluated exactly.
 // Monotonicity needs ascending priorities (dev_flags[1] == 0, screen_sorted_kernel).
 // counters[0] += warp-cells evaluated exactly, counters[1] += audit violations (a dropped cell that does not lose);
-// audit runs also count tiles kept/dropped [2,3], warp-stages kept/dropped [4,5], warp-groups kept/dropped [6,7].
+// audit runs list EVERY tile (so that the dropped ones can be re-evaluated cell by cell) and also count tiles kept/dropped
+// [2,3], warp-stages kept/dropped [4,5], warp-groups kept/dropped [6,7].
 // ---------------------------------------------------------------------------------------------
+// Live tiles are appended to one of SCR_CLASSES lists by expected cost (share of the tile's (row, stage) pairs the range
+// tiers left alive): the tiles that hold a row block's maximum are evaluated almost entirely with the reference's arithmetic
+// and take 10-100x longer than a tile that merely touches the neighbourhood, so the persistent CTAs take the expensive
+// classes first and the cheap tiles fill the tail.
+constexpr int SCR_CLASSES = 4;
+struct LiveHdr {
+  int nlive[SCR_CLASSES];  // tiles appended to each class list by the select kernel of this level
+  int cursor;              // next tile a persistent CTA takes (classes in order)
+  int pad[3];
+};
+constexpr int SCR_MAX_G = 32;  // stages per tile: the live-stage mask of a tile is one 32-bit word
+
+// SCR_SEL_TPR threads share a row (each takes every SCR_SEL_TPR-th batch of four tiles): one thread per row leaves ~5 warps
+// per scheduler on a 782-block level and the bound chains (LDS, DADD, F2F, MUFU.RCP, MUFU.LG2) run at their latency.
+// Instances with few chunks (replica batches) take one thread per row.
+template <typename D, int DIST, bool RP, bool AUDIT, int SCR_SEL_TPR>
+__global__ void __launch_bounds__(SCR_BLOCK * SCR_SEL_TPR)
+screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__ LB, const float* __restrict__ bmax,
+                     int nblk, const int* __restrict__ dev_flags, int4* __restrict__ live, long long live_cap,
+                     unsigned int* __restrict__ tile_mask, int rb_stride, LiveHdr* __restrict__ hdr,
+                     unsigned long long* __restrict__ counters, const int* __restrict__ kbest,
+                     int* __restrict__ rb_slots, int* __restrict__ rb_cnt) {
+  constexpr int BR = SCR_BLOCK;
+  constexpr int NT = BR * SCR_SEL_TPR;  // threads per CTA
+  constexpr bool DBL = (sizeof(D) == 8);
+  constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
+  constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
+  constexpr bool BOX = !GROUPB;
+  // per chunk of this row block: live-stage mask, the record at the tile's last cell (and, box bound, at the first cell of a
+  // tile right of the diagonal), the largest pm of the tile -- staged once so that the per-row loop below reads shared memory
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  D* s_ex = reinterpret_cast<D*>(s_raw);                  // [NCH] x at k_hi
+  D* s_ey = s_ex + g.NCH;                                 // [NCH] y at k_hi
+  D* s_fx = s_ey + g.NCH;                                 // [NCH] x at k_lo (BOX)
+  D* s_fy = s_fx + g.NCH;                                 // [NCH]
+  float* s_tmax = reinterpret_cast<float*>(s_fy + g.NCH);  // [NCH]
+  unsigned int* s_mask = reinterpret_cast<unsigned int*>(s_tmax + g.NCH);  // [NCH]
+  unsigned int* s_cost = s_mask + g.NCH;  // [NCH] live (row, stage) pairs of the tile
+  unsigned char* s_emit = reinterpret_cast<unsigned char*>(s_cost + g.NCH);  // [NCH * nsub] slot has a list entry
+  __shared__ int s_cmin, s_cmax;          // chunks that hold the best samples of this block's rows: the "ridge" 
+  const int inst = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // highest row blocks first: their segments lead the list, so the persistent CTAs start on the expensive tiles (rows past
+  // the A = B frontier) and the cheap low rows fill the tail
+  const int rb = g.rb_first + g.rb_step * (g.NRB - 1 - (int)blockIdx.x);
+  const int part = tid / BR;  // warp-uniform: which share of the tiles this thread takes for its row
+  const int i0 = rb * BR, i = i0 + (tid & (BR - 1));
+  rec += (long long)inst * g.rec_stride;
+  LB += (long long)inst * g.n;
+  bmax += (long long)inst * nblk;
+  const int c_diag = rb / g.G;
+  if (tid == 0) {
+    s_cmin = 0x7fffffff;
+    s_cmax = -1;
+  }
+  for (int c = c_diag + tid; c < g.NCH; c += NT) {
+    const int k_lo = max(c * g.L + 1, i0 + 1);
+    const int k_hi = min((c + 1) * g.L, g.kmax);
+    s_mask[c] = 0u;
+    s_cost[c] = 0u;
+    float tmax = -3.402823466e+38f;
+    for (int b = (k_lo - 1) / BR; b <= (k_hi - 1) / BR; ++b) tmax = fmaxf(tmax, bmax[b]);
+    s_tmax[c] = tmax;
+    const Rec4<D> E = rec[max(k_hi, 0)];
+    s_ex[c] = E.x;
+    s_ey[c] = E.y;
+    if (BOX) {
+      const Rec4<D> F = rec[min(k_lo, g.n)];
+      s_fx[c] = F.x;
+      s_fy[c] = F.y;
+    }
+  }
+  __syncthreads();
+  const int il = min(i, g.n - 1);
+  const D Xi = rec[il].x, Yi = rec[il].y;
+  const float bx = -(float)Xi, by = -(float)Yi;  // float data: Px[k] - Px[i] is exact
+  const float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
+  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
+  const bool row_ok = i < g.nrows;
+  if (kbest) {
+    // the chunk of the row's best sample; the row maximum and the cells that survive the bounds lie around it
+    const int cb = row_ok ? (max(kbest[(long long)inst * g.n + i], 1) - 1) / g.L : -1;
+    const int lo = __reduce_min_sync(0xffffffffu, row_ok ? cb : 0x7fffffff);
+    const int hi = __reduce_max_sync(0xffffffffu, cb);
+    if (lane == 0) {
+      atomicMin(&s_cmin, lo);
+      atomicMax(&s_cmax, hi);
+    }
+  }
+  auto fsum2 = [&](const D x, const D y, float& A, float& B) {
+    A = DBL ? __double2float_rn((double)x - (double)Xi) : __fadd_rn((float)x, bx);
+    B = DBL ? __double2float_rn((double)y - (double)Yi) : __fadd_rn((float)y, by);
+  };
+  auto fsums = [&](const int k, float& A, float& B) {
+    const Rec4<D> R = rec[k];
+    fsum2(R.x, R.y, A, B);
+  };
+  // stage tier of one tile for this thread's row: the tile bound per 128-block -- S at the stage's last cell, the stage's own
+  // largest pm -- then the warp's mask / live-pair count go to shared memory
+  auto stage_tier = [&](const int c, const bool lose) {
+    const int k_lo = max(c * g.L + 1, i0 + 1);
+    const int k_hi = min((c + 1) * g.L, g.kmax);
+    const int nst = (k_hi - k_lo + BR) / BR;
+    unsigned int m = 0u;
+#pragma unroll 4
+    for (int s = 0; s < nst; ++s) {
+      const int kb = k_lo + s * BR, ke = min(kb + BR - 1, k_hi);
+      float Ae, Be;
+      fsums(ke, Ae, Be);
+      float A0 = Ae, B0 = Be;
+      const int k0 = max(kb, i + 1);
+      if (BOX) fsums(min(k0, ke), A0, B0);
+      const bool lose_s = lose || (k0 > ke) || (screen_range_ub<DIST, RP>(A0, B0, Ae, Be, bmax[(kb - 1) / BR]) < thr);
+      if (!lose_s) m |= 1u << s;
+    }
+    const unsigned int pairs = __reduce_add_sync(0xffffffffu, (unsigned int)__popc(m));
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (lane == 0 && m) {
+      atomicOr(&s_mask[c], m);
+      atomicAdd(&s_cost[c], pairs);
+    }
+  };
+  if (!mono) {
+    // no range tiers (caller-supplied order that is not sorted by priority): every stage of every tile is live
+    for (int c = c_diag + tid; c < g.NCH; c += NT) {
+      const int k_lo = max(c * g.L + 1, i0 + 1);
+      const int k_hi = min((c + 1) * g.L, g.kmax);
+      const int nst = (k_hi - k_lo + BR) / BR;
+      s_mask[c] = (k_hi >= k_lo) ? (nst >= 32 ? 0xffffffffu : ((1u << nst) - 1u)) : 0u;
+      s_cost[c] = (unsigned int)BR * (unsigned int)max(nst, 0);
+    }
+  } else {
+    // tile tier: the bound at the tile's last cell with the largest pm of the tile's 128-blocks covers the whole tile.  Four
+    // tiles per step: their bound chains are independent, and one vote dismisses all four (most tiles lose for every row)
+    for (int c4 = c_diag + 4 * part; c4 < g.NCH; c4 += 4 * SCR_SEL_TPR) {
+      if (c4 + 3 < g.NCH && c4 > c_diag) {
+        // all four at once: S at the last cell of the fourth tile with the largest pm of the four covers them all; far from
+        // the row maxima this loses for every row and the four separate bounds are never formed
+        const int ce = c4 + 3;
+        float At, Bt;
+        fsum2(s_ex[ce], s_ey[ce], At, Bt);
+        float Af = At, Bf = Bt;
+        if (BOX) fsum2(s_fx[c4], s_fy[c4], Af, Bf);
+        const float pm4 = fmaxf(fmaxf(s_tmax[c4], s_tmax[c4 + 1]), fmaxf(s_tmax[c4 + 2], s_tmax[ce]));
+        const bool lose4 = !row_ok || (screen_range_ub<DIST, RP>(Af, Bf, At, Bt, pm4) < thr);
+        if (!__any_sync(0xffffffffu, !lose4)) continue;
+      }
+      bool lose[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = min(c4 + u, g.NCH - 1);
+        const int k_lo = max(c * g.L + 1, i0 + 1);
+        const int k_hi = min((c + 1) * g.L, g.kmax);
+        float At, Bt;
+        fsum2(s_ex[c], s_ey[c], At, Bt);
+        float Af = At, Bf = Bt;
+        const int kf = max(k_lo, i + 1);  // the row's first cell in this tile
+        if (BOX) {
+          if (c == c_diag)
+            fsums(min(kf, k_hi), Af, Bf);
+          else
+            fsum2(s_fx[c], s_fy[c], Af, Bf);
+        }
+        lose[u] = !row_ok || (c4 + u >= g.NCH) || (kf > k_hi) ||
+                  (screen_range_ub<DIST, RP>(Af, Bf, At, Bt, s_tmax[c]) < thr);
+      }
+      if (!__any_sync(0xffffffffu, !(lose[0] && lose[1] && lose[2] && lose[3]))) continue;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (__any_sync(0xffffffffu, !lose[u])) stage_tier(c4 + u, lose[u]);
+    }
+  }
+  __syncthreads();
+  // Every partial slot's mask goes to tile_mask (the fold reads it); live tiles are appended to the list of their cost
+  // class.  A tile has g.nsub partial slots: the expensive classes are split into up to nsub list entries (consecutive runs of
+  // stages, one slot each) so that no single work item dominates the level; the others use their first slot.
+  const int nsub = g.nsub;
+  tile_mask += ((long long)inst * rb_stride + rb) * g.nch_alloc * nsub;
+  for (int cb = c_diag + (tid & ~31); cb < g.NCH; cb += NT) {  // warp-uniform trip count: all 32 lanes vote
+    const int c = cb + lane;
+    const bool in = c < g.NCH;
+    const int k_lo = max(c * g.L + 1, i0 + 1);
+    const int k_hi = min((c + 1) * g.L, g.kmax);
+    const int nst = (k_hi - k_lo + BR) / BR;
+    const unsigned int mk = in ? s_mask[c] : 0u;
+    const bool take = in && (k_hi >= k_lo) && (AUDIT || mk != 0u);
+    int cls = SCR_CLASSES - 1;
+    if (take) {
+      // cost class: 0 = the tile holds the best sample of some row of the block (most of its cells will be evaluated with
+      // the reference's arithmetic), 1 = next to such a tile, 2 / 3 = the rest by the share of live (row, stage) pairs
+      const unsigned int full = (unsigned int)BR * (unsigned int)nst;
+      const unsigned int cost = s_cost[c];
+      const int cmin = s_cmin, cmax = s_cmax;
+      if (kbest && c >= cmin && c <= cmax)
+        cls = 0;
+      else if (kbest && c >= cmin - 1 && c <= cmax + 1)
+        cls = 1;
+      else
+        cls = (2u * cost >= full) ? 2 : 3;
+    }
+    const bool split = take && !AUDIT && nsub > 1 && cls <= 1;
+    const int per = max(1, (nst + nsub - 1) / nsub);  // stages per part of a split tile
+    for (int h = 0; h < nsub; ++h) {
+      unsigned int sub = (h == 0) ? mk : 0u;
+      if (split) sub = (h * per < 32) ? (mk & (((per >= 32) ? 0xffffffffu : ((1u << per) - 1u)) << (h * per))) : 0u;
+      if (in) tile_mask[c * nsub + h] = sub;
+      const bool emit = take && (split ? (sub != 0u) : (h == 0));
+      if (in) s_emit[c * nsub + h] = emit ? 1 : 0;
+      // warp-aggregated append: one atomic per class present in the warp
+      const unsigned int peers = __match_any_sync(0xffffffffu, emit ? cls : -1);
+      if (emit) {
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&hdr->nlive[cls], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        live[(long long)cls * live_cap + base + __popc(peers & ((1u << lane) - 1u))] =
+            make_int4(inst, rb, c * nsub + h, (int)sub);
+      }
+    }
+  }
+  // the row block's slots that hold a partial, ascending (= ascending k): the fold reads exactly these
+  __syncthreads();
+  if (tid < 32) {
+    rb_slots += ((long long)inst * rb_stride + rb) * g.nch_alloc * nsub;
+    int pos = 0;
+    for (int sb = c_diag * nsub; sb < g.NCH * nsub; sb += 32) {
+      const int sl = sb + lane;
+      const bool on = (sl < g.NCH * nsub) && s_emit[sl];
+      const unsigned int bal = __ballot_sync(0xffffffffu, on);
+      if (on) rb_slots[pos + __popc(bal & ((1u << lane) - 1u))] = sl;
+      pos += __popc(bal);
+    }
+    if (lane == 0) rb_cnt[(long long)inst * rb_stride + rb] = pos;
+  }
+}
+
+// global -> shared copies that bypass the register file (the exact-arithmetic records of a stage: 32 B per k for double data)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One live tile: group and cell tiers on the live stages, partials to part_val / part_arg.
 template <typename D, int DIST, bool RP, bool AUDIT, int BR>
-__global__ void __launch_bounds__(BR)
-level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* __restrict__ recf,
-                         const D* __restrict__ LB, D* __restrict__ part_val, int* __restrict__ part_arg,
-                         unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
-                         const float* __restrict__ bmax, int nblk, int* __restrict__ tile_stamp, int stamp,
-                         int stamp_stride) {
-  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
+__device__ __forceinline__ void screen_live_tile(const Geom& g, const int inst, const int rb, const int slot,
+                                                 const unsigned int stage_mask, const Rec4<D>* __restrict__ rec,
+                                                 const float4* __restrict__ recf, const D* __restrict__ LB,
+                                                 D* __restrict__ part_val, int* __restrict__ part_arg,
+                                                 unsigned long long* __restrict__ counters, const bool mono,
+                                                 float4 (*sbuf)[BR], float (*s_pmax)[BR / 32],
+                                                 Rec4<D>* sdbl, const GlogEntry* __restrict__ s_log) {
   constexpr int BK = BR;
-  constexpr int U = 8;  // cells per group
+  constexpr int U = 8;   // cells per group
   constexpr int GQ = 4;  // groups whose bounds are formed together
   constexpr bool DBL = (sizeof(D) == 8);
   constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;  // scores that are 0 unless A > B
   // Scores that never decrease when a row's range is extended to the right (priorities ascending, a > 0): with
   // r = a_k/b_k >= q = A/B,  dS/db = r ln q + 1 - q >= q ln q + 1 - q >= 0 (Poisson mult-clust, q > 1; S = 0 below),
   // (q-1) r - (q^2-1)/2 >= (q-1)^2/2 (Gaussian mult-clust), 2 q r - q^2 >= q^2 (A^2/B, A^2/2B).  Poisson risk-part
-  // (A ln(A/B), decreasing while q < 1/e) is not.
-  constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
-  constexpr bool BOX = !GROUPB;  // Poisson risk-part: range tiers from the box bound, no sortedness needed
-  __shared__ float4 sbuf[2][BK];
-  __shared__ float s_pmax[2][BR / 32];  // per stage and warp: largest pm among the records that warp staged
+  // (A ln(A/B), decreasing while q < 1/e) is not: its range tiers use the box bound, which needs no sortedness.
   constexpr bool kLogTab = DBL && (DIST == DIST_POISSON);
-  __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
-  if (kLogTab) {
-    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
-  }
-
-  const int inst = blockIdx.y;
-  rec += (long long)inst * g.rec_stride;
-  recf += (long long)inst * g.rec_stride;
-  LB += (long long)inst * g.n;
-  const long long pstride = (long long)g.nch_alloc * g.n;
-  part_val += inst * pstride;
-  part_arg += inst * pstride;
-
-  int rb, c;
-  decode_tile(g, blockIdx.x, rb, c);
   const int tid = threadIdx.x;
   const int i0 = rb * BR;
   const int i = i0 + tid;
+  const int c = slot / g.nsub;  // the k-chunk; the partial goes to the entry's own slot
   const int k_lo = max(c * g.L + 1, i0 + 1);
   const int k_hi = min((c + 1) * g.L, g.kmax);
 
@@ -407,23 +663,42 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
   float bx = -(float)Xi, by = -(float)Yi;  // float: At = Px[k] - Px[i], exact.  double: set per stage
   D best = Lim<D>::lowest();
   int arg = -1;
-  float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
+  const float thr0 = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);  // the threshold the select kernel dropped with
+  float thr = thr0;
   unsigned int nexact = 0, nviol = 0;
-  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
 
+  // The records the reference's arithmetic reads are staged with the float ones: float data -- the screening record IS the
+  // level record {Px, Py, p, -}; double data -- a second shared buffer filled by cp.async.  k lies in the stage in flight.
+  int kbase = 0, buf = 0;
   auto exact_at = [&](const int k) -> D {
-    const Rec4<D> R = rec[k];
-    return add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(R.x, Xi), sub_rn<D>(R.y, Yi), s_log), R.p);
+    D Rx, Ry, Rp;
+    if constexpr (DBL) {
+      const Rec4<D>& R = sdbl[buf * BR + (k - kbase)];
+      Rx = R.x, Ry = R.y, Rp = R.p;
+    } else {
+      const float4 r = sbuf[buf][k - kbase];
+      Rx = r.x, Ry = r.y, Rp = r.z;
+    }
+    return add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(sub_rn<D>(Rx, Xi), sub_rn<D>(Ry, Yi), s_log), Rp);
+  };
+  auto stage_dbl = [&](const int kb, const int b) {  // this thread's record of the stage starting at kb -> sdbl[b]
+    if constexpr (DBL) {
+      if (kb + tid <= k_hi) {
+        cp_async16(&sdbl[b * BR + tid], &rec[kb + tid]);
+        cp_async16(reinterpret_cast<char*>(&sdbl[b * BR + tid]) + 16, reinterpret_cast<const char*>(&rec[kb + tid]) + 16);
+      }
+      cp_async_commit();
+    }
   };
   // audit: a dropped cell must lose against the threshold it was dropped with
-  auto audit_dropped = [&](const int k, const bool valid) {
-    if (valid && !((double)exact_at(k) < (double)thr)) ++nviol;
+  auto audit_dropped = [&](const int k, const bool valid, const float t) {
+    if (valid && !((double)exact_at(k) < (double)t)) ++nviol;
   };
   // one cell on its own: bound, vote, exact evaluation of the warp if any lane survives (diagonal and ragged stages)
   auto cell = [&](const int k, const float4 r, const bool valid, auto from_double) {
     float A, B;
     if constexpr (decltype(from_double)::value) {
-      const Rec4<D> R = rec[k];
+      const Rec4<D>& R = sdbl[buf * BR + (k - kbase)];
       A = __double2float_rn((double)R.x - (double)Xi);
       B = __double2float_rn((double)R.y - (double)Yi);
     } else {
@@ -442,7 +717,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
         thr = fmaxf(thr, screen_rd<D>(best));
       }
     } else if (AUDIT) {
-      audit_dropped(k, valid);
+      audit_dropped(k, valid, thr);
     }
   };
   using T_ = std::integral_constant<bool, true>;
@@ -455,64 +730,47 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
   };
 
-  if (mono) {
-    // tile tier: the bound at the tile's last cell with the largest pm of the tile's 128-blocks covers the whole tile
-    bmax += (long long)inst * nblk;
-    float tmax = -3.402823466e+38f;
-    for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
-    const Rec4<D> R = rec[k_hi];
-    const float At = DBL ? __double2float_rn((double)R.x - (double)Xi) : __fadd_rn((float)R.x, bx);
-    const float Bt = DBL ? __double2float_rn((double)R.y - (double)Yi) : __fadd_rn((float)R.y, by);
-    float Af = At, Bf = Bt;
-    const int kf = max(k_lo, i + 1);  // the row's first cell in this tile
-    if (BOX) {
-      const Rec4<D> Q = rec[min(kf, k_hi)];
-      Af = DBL ? __double2float_rn((double)Q.x - (double)Xi) : __fadd_rn((float)Q.x, bx);
-      Bf = DBL ? __double2float_rn((double)Q.y - (double)Yi) : __fadd_rn((float)Q.y, by);
-    }
-    const bool lose = (i >= g.nrows) || (kf > k_hi) || (screen_range_ub<DIST, RP>(Af, Bf, At, Bt, tmax) < thr);
-    const bool tile_dropped = __syncthreads_and(lose);
-    if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
-    if (tile_dropped) {
-      if (AUDIT)
-        for (int k = max(k_lo, i + 1); k <= k_hi; ++k) audit_dropped(k, i < g.nrows);
-      if (!tile_stamp && i < g.nrows) {  // with stamps a dropped tile writes nothing: combine_kernel skips it
-        part_val[(long long)c * g.n + i] = best;
-        part_arg[(long long)c * g.n + i] = arg;
-      }
-      if (AUDIT && counters) {
-        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
-        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
-      }
-      return;
-    }
-  }
   const int nk = k_hi - k_lo + 1;
   const int nstages = (nk + BK - 1) / BK;
-  Rec4<D> onx;  // double: record at the origin of the next stage (k = kb - 1)
-  {
+  if (AUDIT && counters && tid == 0) atomicAdd(&counters[stage_mask ? 2 : 3], 1ULL);
+  // live stages in ascending k; audit runs walk every stage and re-evaluate the cells of the dropped ones
+  unsigned int todo = AUDIT ? (nstages >= 32 ? 0xffffffffu : ((1u << nstages) - 1u)) : stage_mask;
+  int s = todo ? (__ffs(todo) - 1) : -1;
+  Rec4<D> onx;  // double: record at the origin of the staged stage (k = kb - 1)
+  onx.x = onx.y = onx.p = onx.w = 0;
+  if (s >= 0) {
+    const int kb = k_lo + s * BK;
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
+    if (kb + tid <= k_hi) r = recf[kb + tid];
     sbuf[0][tid] = r;
     stage_max(r, 0);
-    if (DBL) onx = rec[k_lo - 1];
+    if (DBL) onx = rec[kb - 1];
+    stage_dbl(kb, 0);
+    if (DBL) cp_async_wait_all();
   }
-  for (int s = 0; s < nstages; ++s) {
+  while (s >= 0) {
     __syncthreads();
+    todo &= todo - 1u;
+    const int sn = todo ? (__ffs(todo) - 1) : -1;  // next live stage: its records are fetched while this one is processed
     const int kb = k_lo + s * BK;
-    const int kn = kb + BK + tid;
+    kbase = kb;
+    if (sn >= 0) stage_dbl(k_lo + sn * BK, buf ^ 1);
     float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool has_next = (s + 1 < nstages);
-    if (has_next && kn <= k_hi) nx = recf[kn];
+    if (sn >= 0 && k_lo + sn * BK + tid <= k_hi) nx = recf[k_lo + sn * BK + tid];
     if (DBL) {
       // At = lx[k] + bx with bx = fl32(P[kb-1] - P[i]) >= 0 on every stage right of the diagonal
       bx = __double2float_rn((double)onx.x - (double)Xi);
       by = __double2float_rn((double)onx.y - (double)Yi);
-      if (has_next) onx = rec[kb + BK - 1];
+      if (sn >= 0) onx = rec[k_lo + sn * BK - 1];
     }
     const int cnt = min(BK, k_hi - kb + 1);
-    const float4* __restrict__ sb = sbuf[s & 1];
-    if (kb <= i0 + BR - 1) {
+    const float4* __restrict__ sb = sbuf[buf];
+    const bool sel_dropped = AUDIT && !((stage_mask >> s) & 1u);
+    if (sel_dropped) {
+      // (audit) a stage the select kernel dropped: every cell must lose against the row's initial threshold
+      if (counters && (tid & 31) == 0) atomicAdd(&counters[5], 1ULL);
+      for (int kk = 0; kk < cnt; ++kk) audit_dropped(kb + kk, (kb + kk > i) && (i < g.nrows), thr0);
+    } else if (kb <= i0 + BR - 1) {
       // diagonal stage: row i only sees k > i; the double kernel converts exact differences (kb - 1 = i0 <= i)
       if (DBL) {
         for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
@@ -570,10 +828,11 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
     } else {
       bool skip = false;
       if (mono) {
-        // stage tier: the bound at the stage's LAST cell with the stage's largest pm covers all 128 cells
-        float pmx = s_pmax[s & 1][0];
+        // stage tier again, now against the threshold this tile has raised: the bound at the stage's LAST cell with the
+        // stage's largest pm covers all 128 cells
+        float pmx = s_pmax[buf][0];
 #pragma unroll
-        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
+        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[buf][w]);
         const float4 re = sb[BK - 1], rf = sb[0];
         const float ubs = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
                                                     __fadd_rn(re.y, by), pmx);
@@ -582,7 +841,7 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
       if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
       if (skip) {
         if (AUDIT)
-          for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true);
+          for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true, thr);
       } else {
 #pragma unroll 1
         for (int kq = 0; kq < BK; kq += GQ * U) {
@@ -606,73 +865,215 @@ level_tile_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* 
                 const bool gdrop = !((keepm >> q) & 1u);
                 if (counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
                 if (gdrop)
-                  for (int u = 0; u < U; ++u) audit_dropped(kb + kq + q * U + u, true);
+                  for (int u = 0; u < U; ++u) audit_dropped(kb + kq + q * U + u, true, thr);
               }
             }
             if (!keepm) continue;
           }
 #pragma unroll 1
           for (int q = 0; q < GQ; ++q) {
-          if (!((keepm >> q) & 1u)) continue;
-          const int kk = kq + q * U;
-          // U independent chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA-pipe operations): their latencies overlap,
-          // one vote decides for the group
-          float A[U], B[U], W[U];
-          bool gt = false;
+            if (!((keepm >> q) & 1u)) continue;
+            const int kk = kq + q * U;
+            // U independent chains (LDS, 2 adds, MUFU.RCP, MUFU.LG2, 4-5 FMA-pipe operations): their latencies overlap,
+            // one vote decides for the group
+            float A[U], B[U], W[U];
+            bool gt = false;
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const float4 r = sb[kk + u];
-            A[u] = __fadd_rn(r.x, bx);
-            B[u] = __fadd_rn(r.y, by);
-            W[u] = screen_pm_of<D>(r);
-            if (FRONTIER) gt |= A[u] > B[u];
-          }
-          bool alive = false;
-          if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
-            // the whole 32 x U patch is on the S = 0 side of the A = B frontier
+            for (int u = 0; u < U; ++u) {
+              const float4 r = sb[kk + u];
+              A[u] = __fadd_rn(r.x, bx);
+              B[u] = __fadd_rn(r.y, by);
+              W[u] = screen_pm_of<D>(r);
+              if (FRONTIER) gt |= A[u] > B[u];
+            }
+            bool alive = false;
+            if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
+              // the whole 32 x U patch is on the S = 0 side of the A = B frontier
 #pragma unroll
-            for (int u = 0; u < U; ++u) alive |= !(fmaf(B[u], SCR_TINY, W[u]) < thr);
-          } else {
+              for (int u = 0; u < U; ++u) alive |= !(fmaf(B[u], SCR_TINY, W[u]) < thr);
+            } else {
 #pragma unroll
-            for (int u = 0; u < U; ++u) alive |= !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
-          }
-          if (AUDIT) {
+              for (int u = 0; u < U; ++u) alive |= !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
+            }
+            if (AUDIT) {
 #pragma unroll 1
-            for (int u = 0; u < U; ++u) cell(kb + kk + u, sb[kk + u], true, F_{});
-          } else if (__any_sync(0xffffffffu, alive)) {
-            // a survivor: the group lies in the neighbourhood of the row maximum, where most cells survive --
-            // evaluate all U exactly (independent chains, loads issued together), then take them in ascending k
-            D v[U];
+              for (int u = 0; u < U; ++u) cell(kb + kk + u, sb[kk + u], true, F_{});
+            } else if (__any_sync(0xffffffffu, alive)) {
+              // a survivor: the group lies in the neighbourhood of the row maximum, where most cells survive --
+              // evaluate all U exactly (independent chains, loads issued together), then take them in ascending k
+              D v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = exact_at(kb + kk + u);
+              for (int u = 0; u < U; ++u) v[u] = exact_at(kb + kk + u);
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-              if (v[u] > best) {
-                best = v[u];
-                arg = kb + kk + u;
-              }
-            thr = fmaxf(thr, screen_rd<D>(best));
-            nexact += U;
-          }
+              for (int u = 0; u < U; ++u)
+                if (v[u] > best) {
+                  best = v[u];
+                  arg = kb + kk + u;
+                }
+              thr = fmaxf(thr, screen_rd<D>(best));
+              nexact += U;
+            }
           }
         }
       }
     }
-    if (has_next) {
-      sbuf[(s + 1) & 1][tid] = nx;
-      stage_max(nx, (s + 1) & 1);
+    if (sn >= 0) {
+      sbuf[buf ^ 1][tid] = nx;
+      stage_max(nx, buf ^ 1);
+      if (DBL) cp_async_wait_all();
     }
+    buf ^= 1;
+    s = sn;
   }
   if (i < g.nrows) {
-    part_val[(long long)c * g.n + i] = best;
-    part_arg[(long long)c * g.n + i] = arg;
+    part_val[(long long)slot * g.n + i] = best;
+    part_arg[(long long)slot * g.n + i] = arg;
   }
-  if (tile_stamp && tid == 0) tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + rb] = stamp;
   if (counters) {
     if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
     if (AUDIT) {
       for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
       if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+    }
+  }
+}
+
+// Outputs of a level, written by screen_fold_kernel (what combine_kernel writes on the exhaustive path): maxScore_[j], nextStart_[j], the p field of the next level's records, its float image pm (double
+// data), and for row-sharded runs the value in block-cyclic chunk order.
+template <typename D>
+struct LevelOut {
+  D* ms_row;               // maxScore_[j] of instance 0 (nullptr: not kept)
+  int* ns_row;             // nextStart_[j] of instance 0
+  long long table_stride;  // elements between instances in ms / ns
+  Rec4<D>* rec_next;       // next level's records (p field), instance 0
+  float* pm_next;          // float4 screening records of the next level viewed as floats (.w), or nullptr
+  D* shard_chunk;          // row-sharded runs: owned rows in block-cyclic order, or nullptr
+};
+
+// Fold the partials of every row block over its live tiles (ascending chunks = ascending k; strict > keeps the first
+// maximum, exactly like the reference's scan over k) and write the level's outputs.  CW lanes share a row: lane q folds the
+// q-th part of the segment, the parts are merged in ascending order with the same strict >.
+template <typename D, int BR, int CW>
+__global__ void __launch_bounds__(BR * CW)
+screen_fold_kernel(Geom g, const int* __restrict__ rb_slots, const int* __restrict__ rb_cnt, int rb_stride,
+                   const D* __restrict__ part_val, const int* __restrict__ part_arg, LevelOut<D> out) {
+  const int inst = blockIdx.y;
+  const int rb = g.rb_first + g.rb_step * (int)blockIdx.x;
+  const int r = threadIdx.x / CW, q = threadIdx.x % CW;
+  const int i = rb * BR + r;
+  const long long pstride = (long long)g.nch_alloc * g.nsub * g.n;
+  part_val += inst * pstride;
+  part_arg += inst * pstride;
+  rb_slots += ((long long)inst * rb_stride + rb) * g.nch_alloc * g.nsub;
+  const int cnt = rb_cnt[(long long)inst * rb_stride + rb];
+  D best = Lim<D>::lowest();
+  int cbest = -1;
+  if (i < g.nrows) {
+    const int per = (cnt + CW - 1) / CW;
+    const int e0 = q * per, e1 = min(cnt, e0 + per);
+    for (int e = e0; e < e1; e += 4) {
+      int sl[4];
+      D v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sl[u] = (e + u < e1) ? rb_slots[e + u] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (sl[u] >= 0) ? part_val[(long long)sl[u] * g.n + i] : Lim<D>::lowest();
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v[u] > best) {
+          best = v[u];
+          cbest = sl[u];
+        }
+    }
+  }
+  const unsigned int lane = threadIdx.x & 31u, base = lane & ~(unsigned)(CW - 1);
+  D mb = __shfl_sync(0xffffffffu, best, base);
+  int mc = __shfl_sync(0xffffffffu, cbest, base);
+#pragma unroll
+  for (int u = 1; u < CW; ++u) {
+    const D ob = __shfl_sync(0xffffffffu, best, base + u);
+    const int oc = __shfl_sync(0xffffffffu, cbest, base + u);
+    if (ob > mb) {
+      mb = ob;
+      mc = oc;
+    }
+  }
+  if (q != 0) return;
+  if (i < g.nrows) {
+    // the split index is read once, for the winning chunk only (a partial equal to lowest() never wins: split -1)
+    const int arg = (mc >= 0) ? part_arg[(long long)mc * g.n + i] : -1;
+    if (out.ms_row) out.ms_row[inst * out.table_stride + i] = mb;
+    if (out.ns_row) out.ns_row[inst * out.table_stride + i] = arg;
+    if (out.rec_next) out.rec_next[inst * g.rec_stride + i].p = mb;
+    if (out.pm_next) out.pm_next[(inst * g.rec_stride + i) * 4 + 3] = screen_pm<D>(mb);
+  }
+  if (out.shard_chunk) {
+    const int m = (rb - g.rb_first) / g.rb_step;
+    out.shard_chunk[(long long)m * BR + r] = (i < g.nrows) ? mb : Lim<D>::lowest();
+  }
+}
+
+template <typename D, int DIST, bool RP, bool AUDIT, int BR>
+__global__ void __launch_bounds__(BR, 8)
+level_live_screen_kernel(Geom g, const Rec4<D>* __restrict__ rec, const float4* __restrict__ recf,
+                         const D* __restrict__ LB, D* __restrict__ part_val, int* __restrict__ part_arg,
+                         unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
+                         const int4* __restrict__ live, long long live_cap, LiveHdr* __restrict__ hdr,
+                         unsigned long long* __restrict__ dbg) {
+  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
+  constexpr bool DBL = (sizeof(D) == 8);
+  constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
+  constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
+  constexpr bool BOX = !GROUPB;
+  __shared__ float4 sbuf[2][BR];
+  __shared__ float s_pmax[2][BR / 32];  // per stage and warp: largest pm among the records that warp staged
+  __shared__ Rec4<D> sdbl[DBL ? 2 * BR : 1];  // double data: the level records of the stage in flight / the next one
+  constexpr bool kLogTab = DBL && (DIST == DIST_POISSON);
+  __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
+  __shared__ int s_next;
+  if (kLogTab) {
+    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
+  }
+  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
+  const long long pstride = (long long)g.nch_alloc * g.nsub * g.n;
+  const int tid = threadIdx.x;
+  // class boundaries in the order the tiles are taken (final: the select kernel of this level has completed)
+  int cum[SCR_CLASSES];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int q = 0; q < SCR_CLASSES; ++q) {
+      acc += hdr->nlive[q];
+      cum[q] = acc;
+    }
+  }
+  const int nlive = cum[SCR_CLASSES - 1];
+  for (;;) {
+    __syncthreads();  // the previous tile is done with the shared buffers and with s_next
+    if (tid == 0) s_next = atomicAdd(&hdr->cursor, 1);  // persistent CTAs pull the next tile
+    __syncthreads();
+    const int t = s_next;
+    if (t >= nlive) break;
+    int cls = 0;
+#pragma unroll
+    for (int q = 0; q < SCR_CLASSES - 1; ++q) cls += (t >= cum[q]) ? 1 : 0;
+    const int4 e = live[(long long)cls * live_cap + (t - (cls ? cum[cls - 1] : 0))];
+    const int inst = e.x, rb = e.y, slot = e.z;
+    unsigned long long t0 = 0;  // dbg: development aid (PS_DEBUG_LEVEL), per-tile start / end / SM / class
+    if (dbg && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    screen_live_tile<D, DIST, RP, AUDIT, BR>(g, inst, rb, slot, (unsigned int)e.w, rec + (long long)inst * g.rec_stride,
+                                             recf + (long long)inst * g.rec_stride, LB + (long long)inst * g.n,
+                                             part_val + inst * pstride, part_arg + inst * pstride, counters, mono, sbuf,
+                                             s_pmax, sdbl, s_log);
+    if (dbg && tid == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      dbg[4 * (long long)t + 0] = t0;
+      dbg[4 * (long long)t + 1] = t1;
+      dbg[4 * (long long)t + 2] = ((unsigned long long)smid << 32) | (unsigned int)cls;
+      dbg[4 * (long long)t + 3] = ((unsigned long long)(unsigned int)rb << 32) | (unsigned int)slot;
     }
   }
 }
