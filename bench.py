@@ -101,7 +101,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baselines
-def cpu_reference_sample(dtype, target_s, quiet=True):
+def cpu_reference_sample(dtype, target_s, quiet=True, instances=1):
     """Time the reference's own solver on a bounded sample of the headline workload: same score,
     objective, T and input distribution, smaller n (its three n x n tables do not fit at n=100k)."""
     from oracle import oracle_py as O
@@ -119,9 +119,10 @@ def cpu_reference_sample(dtype, target_s, quiet=True):
         ram = psutil.virtual_memory().available
     except Exception:
         ram = 32 << 30
-    n_mem = int(np.sqrt(0.4 * ram / (3 * w))) if kind == "reference" else 10 ** 9
+    # the reference allocates three (n+1)^2 tables (score_impl.hpp:238-239): memory, not a fixed cap, bounds the sample
+    n_mem = int(np.sqrt(0.6 * ram / (3 * w) / max(1, instances))) if kind == "reference" else 10 ** 9
     n_s = int(n_cal * np.sqrt(max(target_s, t_cal) / max(t_cal, 1e-4)))
-    n_s = max(n_cal, min(n_s, n_mem, 24000 if kind == "reference" else 60000))
+    n_s = max(n_cal, min(n_s, n_mem, 100000))
     n_s = (n_s // 500) * 500
     return which, kind, n_s
 
@@ -132,6 +133,70 @@ def run_cpu_solver(which, dtype, n_s):
     a, b = cfg["gen"](dtype, n_s)
     t, score = O.time_solve(which, a, b, cfg["T"], cfg["dist"], cfg["risk_part"], dtype=dtype)
     return t, score
+
+
+def hostile_inputs(kind, n, dt):
+    """Inputs on which exact branch-and-bound cannot prune (tests/test_gpu_ties.py uses the same generators)."""
+    rs = np.random.RandomState(77)
+    if kind == "constant_ratio":  # a = 3 b: every priority ties and every cell of a row ties in exact arithmetic
+        b = rs.randint(1, 200, n).astype(np.float64)
+        return (3.0 * b).astype(dt), b.astype(dt)
+    if kind == "one_two":  # gtest_all.cpp:924-958: a in {1, 2}, b = 1
+        return rs.randint(1, 3, n).astype(dt), np.ones(n, dt)
+    if kind == "uniform_counts":  # no planted structure
+        return rs.randint(1, 1000, n).astype(dt), rs.randint(1, 1000, n).astype(dt)
+    raise ValueError(kind)
+
+
+_FULL_REF_SNIPPET = r'''
+import json, sys, time
+import numpy as np
+sys.path.insert(0, %(root)r)
+from oracle import oracle_py as O
+from partitionsolvers_b200 import synth
+cfg = synth.CONFIGS["C3"]
+a, b = cfg["gen"](np.float32)
+t, score = O.time_solve("ref", a, b, cfg["T"], cfg["dist"], cfg["risk_part"], dtype=np.float32)
+print(json.dumps({"seconds": t, "score": score}))
+'''
+
+
+def cpu_reference_full_size(limit_s=330.0):
+    """SAME CONFIGURATION leg: the unmodified reference DPSolver<float> at n = 100000, T = 16 (its three (n+1)^2 float
+    tables need 120 GB; the f64 tables, 240 GB, do not fit this pool's 196 GB boxes).  Runs in a child process with a hard
+    time limit; skipped with a stated reason where memory or the predicted time does not allow it."""
+    from oracle import oracle_py as O
+    cfg = synth.CONFIGS["C3"]
+    n = cfg["n"]
+    need = 3.0 * (n + 1) ** 2 * 4
+    if os.environ.get("PS_BENCH_SKIP_FULL_REF"):
+        return {"ran": False, "why": "PS_BENCH_SKIP_FULL_REF set"}
+    if not O.have("ref"):
+        return {"ran": False, "why": "oracle/_ref/libps_ref.so absent (the reference was not compiled into this tree)"}
+    try:
+        import psutil
+        avail = float(psutil.virtual_memory().available)
+    except Exception:
+        avail = 0.0
+    if avail < 1.12 * need:
+        return {"ran": False, "why": f"needs {need / 1e9:.0f} GB of tables, {avail / 1e9:.0f} GB of host memory available"}
+    n_cal = 6000
+    a, b = cfg["gen"](np.float32, n_cal)
+    t_cal, _ = O.time_solve("ref", a, b, cfg["T"], cfg["dist"], cfg["risk_part"], dtype=np.float32)
+    predicted = t_cal * (n / n_cal) ** 2
+    if predicted > 0.9 * limit_s:
+        return {"ran": False, "why": f"predicted {predicted:.0f} s from n={n_cal} ({t_cal:.2f} s) exceeds the {limit_s:.0f} s limit"}
+    try:
+        out = subprocess.run([sys.executable, "-c", _FULL_REF_SNIPPET % {"root": ROOT}], capture_output=True, text=True,
+                             timeout=limit_s)
+        rec = json.loads(out.stdout.strip().splitlines()[-1])
+    except subprocess.TimeoutExpired:
+        return {"ran": False, "why": f"did not finish within {limit_s:.0f} s (predicted {predicted:.0f} s)"}
+    except Exception as e:
+        return {"ran": False, "why": f"child failed: {e}"}
+    return {"ran": True, "seconds": rec["seconds"], "score": rec["score"], "predicted_s": predicted,
+            "value": synth.nominal_cells(n, cfg["T"]) / rec["seconds"], "n": n, "T": cfg["T"], "dtype": "f32",
+            "table_bytes": need}
 
 
 def cpu_threads_used(kind):
@@ -148,15 +213,25 @@ def reference_arm(args):
     cfg = synth.CONFIGS["C3"]
     budget = 150.0
     per_step = max(1.0, min(8.0, budget / max(1, args.steps + args.warmup)))
-    which, kind, n_s = cpu_reference_sample(dtype, per_step)
+    # --gpus N: the GPU arm solves N instances at once (one per GPU, weak scaling), so this arm solves N instances at once
+    # on the box's host cores (N processes, each the reference's own <= 9 threads) -- the same job on the same box
+    inst = max(1, args.gpus)
+    which, kind, n_s = cpu_reference_sample(dtype, per_step, instances=inst)
+
+    def one_step():
+        if inst == 1:
+            return run_cpu_solver(which, dtype, n_s)[0]
+        import multiprocessing as mp
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(inst) as pool:
+            pool.starmap(run_cpu_solver, [(which, dtype, n_s)] * inst)
+        return time.perf_counter() - t0
+
     for _ in range(args.warmup):
-        run_cpu_solver(which, dtype, n_s)
-    times = []
-    for _ in range(args.steps):
-        t, _ = run_cpu_solver(which, dtype, n_s)
-        times.append(t)
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
     ms = 1e3 * float(np.mean(times))
-    value = synth.nominal_cells(n_s, cfg["T"]) / (ms * 1e-3)
+    value = inst * synth.nominal_cells(n_s, cfg["T"]) / (ms * 1e-3)
     sample = (f"{'unmodified reference DPSolver' if kind == 'reference' else 'oracle port'}"
               f"<{'double' if dtype == np.float64 else 'float'}> constructor at n={n_s}, T={cfg['T']} "
               f"(same generator as the headline workload; n=100000 needs {3 * 1e10 * np.dtype(dtype).itemsize / 1e9:.0f} GB of tables)")
@@ -164,9 +239,12 @@ def reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "C3 sample: Poisson multiple clustering, T=16", "n": n_s, "T": cfg["T"],
-                       "host_cores": os.cpu_count()},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads_used(kind), "kind": kind,
-                             "sample": sample},
+                       "host_cores": os.cpu_count(), "concurrent_instances": inst,
+                       "same_config_as_gpu_arm": False,
+                       "why_not": "the reference needs 3 (n+1)^2 tables: 240 GB (f64) / 120 GB (f32) at n=100000; one f32 solve at "
+                                  "full size is timed by the GPU arm's cpu_baseline leg where the box has the memory"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(os.cpu_count() or 1, inst * cpu_threads_used(kind)),
+                             "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -317,7 +395,7 @@ def main():
                "actual_cells_per_s": world * synth.actual_cells(n, T) / (ms * 1e-3),
                "level_ms_sum": float(np.sum(lev_ms)), "level_cells_sum": float(np.sum(lev_cells)),
                "level_launches": len(lev_ms), "stage_ms": stage, "screen_used": int(screened),
-               "exact_cells": float(exact_cells),
+               "exact_cells": float(exact_cells), "fallback_level": int(tm["screen_fallback_level"]),
                "bounds": bounds_d.cpu().numpy().tolist()}
         # fraction of (i,k) cells past the A = B frontier (only those evaluate division + log in the mult-clust
         # scores, exactly like the reference's ternary): Monte-Carlo estimate on the sorted inputs
@@ -375,19 +453,30 @@ def main():
     except Exception:
         prof = {}
 
+    try:
+        level_instr = json.load(open(os.path.join(ROOT, "profiles", "level_instr_r2.json")))
+    except Exception:
+        level_instr = {}
+
     def roofline_of(res, dtype_name):
-        """Roofline object of the level kernel a run used (the dominant kernel: > 90 % of a step).
-        achieved = ALGORITHMIC flops of the level launches / their CUDA-event time.  The algorithmic count charges
-        every (i,k) cell: 10 flops for a Poisson mult-clust cell with A > B, 5 for a cell with A <= B whose score is
-        0 by definition (score_impl.hpp:385-388) -- SURVEY.md 8d."""
+        """Roofline object(s) of the level kernels a run used (> 90 % of a step).
+
+        Exhaustive kernel (every cell evaluated with the reference's arithmetic): the classical one -- achieved =
+        ALGORITHMIC flops of the level launches / their CUDA-event time against the measured non-fused add/mul rate of the
+        data type (parity forbids FMA contraction of the score).  The count charges every (i,k) cell: 10 flops for a Poisson
+        mult-clust cell with A > B, 5 for a cell with A <= B whose score is 0 by definition (score_impl.hpp:385-388).
+
+        Screened path (exact branch-and-bound): the same algorithmic count divided by its time EXCEEDS the pipe peak --
+        it evaluates ~1 % of the cells and dismisses the rest in ranges, so that ratio measures pruning, not the kernel.
+        What is reported as `frac` for it is instruction-issue utilisation (executed warp instructions of the four level
+        launches, counted per level by ncu on this very workload: profiles/level_instr_r2.json) with the algorithmic ratio
+        kept beside it under `algorithmic` and labelled for what it is."""
         screened = bool(res["screen_used"])
         p_gt = res["frac_cells_A_gt_B"] if (not rp and dist_id != 2) else 1.0
         flops_cell = 5.0 + (flops_full - 5.0) * p_gt
         lev_s = res["level_ms_sum"] * 1e-3
         achieved = res["level_cells_sum"] * flops_cell / lev_s / 1e12
-        # exhaustive kernel: arithmetic in the data type; screened kernel: float bounds for all cells, data type only
-        # for the ~1 % of cells that survive
-        pipe64 = (dtype_name == "f64") and not screened
+        pipe64 = (dtype_name == "f64")
         if peaks:
             peak = (peaks["dadd_ops"] if pipe64 else peaks["fadd_ops"]) / 1e12
             peak_src = ("measured by tools/peaks.cu on this device: non-fused FP add/mul issue rate "
@@ -395,49 +484,64 @@ def main():
         else:
             peak = (148 * 64 if pipe64 else 148 * 128) * 1.965e9 / 1e12
             peak_src = "fallback: lanes x 1.965 GHz (ps_peaks binary missing)"
-        kname = "level_tile_screen_kernel" if screened else "level_tile_kernel"
-        pk = prof.get(("screen_" if screened else "") + dtype_name, {})
+        pk = prof.get(("live_" if screened else "") + dtype_name, {})
         launches = max(1, res["level_launches"])
         avg_launch_ms = res["level_ms_sum"] / launches
         alg_bytes_per_launch = ALG_HBM_BYTES_PER_ROW(8 if dtype_name == "f64" else 4) * n
         mufu_peak = peaks["mufu_lg2_ops"] if peaks else 148 * 16 * 1.965e9
-        r = {"kernel": kname, "bound": "fp64_pipe" if pipe64 else "fp32_issue",
-             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-             "traffic": pk.get("dram_bytes_per_launch"),
-             "alg_flops_per_cell": flops_cell, "alg_flops_per_evaluated_cell": flops_full,
-             "frac_cells_A_gt_B": p_gt, "cells_per_launch_avg": res["level_cells_sum"] / launches,
-             "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
+        pipes = {k: pk.get("metrics", {}).get(k, {}).get("value") for k in (
+            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active")}
+        classical = {"kernel": "level_tile_kernel (exhaustive)", "bound": "fp64_pipe" if pipe64 else "fp32_issue",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": pk.get("dram_bytes_per_launch"),
+                     "alg_flops_per_cell": flops_cell, "alg_flops_per_evaluated_cell": flops_full,
+                     "frac_cells_A_gt_B": p_gt, "cells_per_launch_avg": res["level_cells_sum"] / launches,
+                     "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
+                     "share_of_step": res["level_ms_sum"] / (res["steps"] * res["ms_per_step"]),
+                     "ncu_pipe_pct": pipes,
+                     "hbm": {"alg_bytes_per_launch": alg_bytes_per_launch,
+                             "achieved_gbs": alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                             "note": "not HBM-bound: algorithmic traffic is (4w+4)n bytes per level"}}
+        if not screened:
+            classical["sfu"] = {"ops_per_cell": 1,
+                                "what": "one MUFU reciprocal per evaluated cell (division seed); log is table-driven, no MUFU",
+                                "achieved_tops": res["level_cells_sum"] / lev_s / 1e12, "peak_tops": mufu_peak / 1e12,
+                                "frac": (res["level_cells_sum"] / lev_s) / mufu_peak}
+            return classical
+        r = {"kernel": "level_live_screen_kernel (+ screen_lb / screen_select / screen_fold of the same level)",
+             "bound": "issue", "unit": "T warp-instructions/s",
+             "cells_per_launch_avg": res["level_cells_sum"] / launches, "avg_launch_ms": avg_launch_ms,
              "share_of_step": res["level_ms_sum"] / (res["steps"] * res["ms_per_step"]),
-             "hbm": {"alg_bytes_per_launch": alg_bytes_per_launch,
-                     "achieved_gbs": alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                     "note": "not HBM-bound: algorithmic traffic is (4w+4)n bytes per level"}}
-        if screened and pk.get("warp_instructions_per_cell"):
-            # The screened kernel dismisses most cells in groups, so the algorithmic flop count says little about it (it
-            # exceeds the FP32 peak).  What bounds it is instruction ISSUE: one warp instruction per SM sub-partition and
-            # cycle.  achieved = executed warp instructions per cell (ncu, profiles/level_kernel_summary.json) x cells of
-            # the timed launches / 32 / their CUDA-event time; peak = 148 SMs x 4 sub-partitions x SM clock.
-            ipc = pk["warp_instructions_per_cell"]
-            issue_peak = 148 * 4 * 1.965e9 / 1e12
-            issue_ach = ipc * res["level_cells_sum"] / 32.0 / lev_s / 1e12
-            r["algorithmic_flops"] = {"achieved": r["achieved"], "peak": r["peak"], "unit": "TFLOP/s",
-                                      "frac": r["frac"], "peak_source": r["peak_source"]}
-            r.update({"bound": "issue", "achieved": issue_ach, "peak": issue_peak, "unit": "T warp-instructions/s",
-                      "frac": issue_ach / issue_peak,
-                      "peak_source": "148 SMs x 4 sub-partitions x 1.965 GHz, one warp instruction per cycle each"})
-        if screened:
-            r["screen"] = {
-                "exact_cell_fraction": res["exact_cells"] / max(1.0, res["level_cells_sum"]),
-                "executed_warp_instructions_per_cell": pk.get("warp_instructions_per_cell"),
-                "issue_slot_utilisation": pk.get("issue_active_pct"),
-                "note": "cells are bounded in float, singly or 8 / 128 at a time where the score is monotone in k; "
-                        "only cells that can still be the row maximum are evaluated with the reference's arithmetic. "
-                        "The algorithmic flop count (algorithmic_flops) still charges every cell, so its frac exceeds 1; "
-                        "the roofline reported is instruction issue"}
+             "traffic": pk.get("dram_bytes_per_launch"), "ncu_pipe_pct": pipes,
+             "hbm": classical["hbm"],
+             "algorithmic": {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                             "peak_source": peak_src,
+                             "note": "all (i,k) cells charged although ~99 % are dismissed by bounds: a measure of pruning "
+                                     "(how far beyond ANY kernel that evaluates every cell), not a pipe utilisation"}}
+        li = level_instr.get(dtype_name)
+        issue_peak = 148 * 4 * 1.965e9 / 1e12
+        if li and li.get("n") == n and li.get("T") == T:
+            instr_per_solve = float(sum(sum(v) for v in li["per_level"].values()))
+            issue_ach = instr_per_solve * res["steps"] / lev_s / 1e12
+            r.update({"achieved": issue_ach, "peak": issue_peak, "frac": issue_ach / issue_peak,
+                      "issue_utilisation": issue_ach / issue_peak,
+                      "warp_instructions_per_cell": instr_per_solve * res["steps"] / (res["level_cells_sum"] / 32.0),
+                      "warp_instructions_per_solve": instr_per_solve,
+                      "peak_source": "148 SMs x 4 sub-partitions x 1.965 GHz, one warp instruction per cycle each; executed "
+                                     "instructions per level from ncu on this workload (profiles/level_instr_r2.json), time from "
+                                     "this run's CUDA events"})
         else:
-            r["sfu"] = {"ops_per_cell": 1,
-                        "what": "one MUFU reciprocal per evaluated cell (division seed); log is table-driven, no MUFU",
-                        "achieved_tops": res["level_cells_sum"] / lev_s / 1e12, "peak_tops": mufu_peak / 1e12,
-                        "frac": (res["level_cells_sum"] / lev_s) / mufu_peak}
+            r.update({"achieved": None, "peak": issue_peak, "frac": None, "issue_utilisation": None,
+                      "peak_source": "profiles/level_instr_r2.json has no entry for this workload"})
+        r["screen"] = {"exact_cell_fraction": res["exact_cells"] / max(1.0, res["level_cells_sum"]),
+                       "fallback_level": res.get("fallback_level", 0),
+                       "note": "exact branch-and-bound: cells are bounded in float, singly or 8 / 128 / a tile at a time where "
+                               "the score is monotone in k; only cells that can still be the row maximum are evaluated with "
+                               "the reference's arithmetic (identical tables).  Data-dependent: see `pruning`"}
         return r
 
     main_res["steps"] = args.steps
@@ -455,6 +559,10 @@ def main():
         line["other_level_kernel"] = {"value": vx["value"], "ms_per_step": vx["ms_per_step"], "e2e": vx["e2e"],
                                       "same_partition": vx["bounds"] == main_res["bounds"],
                                       "roofline": roofline_of(vx, args.dtype)}
+        # the classical roofline of the path: the kernel that evaluates EVERY cell with the reference's arithmetic
+        ex_res = main_res if args.exhaustive else vx
+        line["roofline_exhaustive"] = dict(roofline_of(ex_res, args.dtype), ms_per_step=ex_res["ms_per_step"],
+                                           value=ex_res["value"])
         other = "f32" if args.dtype == "f64" else "f64"
         v = run_variant(other, max(2, args.steps // 2), 3, with_e2e=True)
         line["variants"] = {other: {"value": v["value"], "ms_per_step": v["ms_per_step"], "e2e": v["e2e"],
@@ -549,6 +657,56 @@ def main():
                                       "level_kernel": {0: "exhaustive", 1: "screened, exact sums",
                                                        2: "screened, running sums"}[ctx.timings()["screen_used"]]}
             line["c3_all_scores"] = per_score
+        # ---- exact branch-and-bound is data dependent: the inputs on which it cannot prune, at the headline size, on both
+        # level kernels (same tables).  constant a/b: every cell of a row ties; a in {1,2}, b = 1 (gtest_all.cpp:924-958);
+        # uniform counts: no planted structure.  The engine hands the levels to the exhaustive kernel once a screened level
+        # evaluates > 30 % of its cells exactly (ps_timings.screen_fallback_level)
+        if rank == 0:
+            npdt_a = np.float64 if args.dtype == "f64" else np.float32
+            adv = {}
+            for kind in ("constant_ratio", "one_two", "uniform_counts"):
+                a_h, b_h = hostile_inputs(kind, n, npdt_a)
+                rec = {}
+                for label, scr in (("screened_default", 0), ("exhaustive", 1)):
+                    best = 1e30
+                    for _ in range(2):
+                        ctx.solve_raw(a_h, b_h, T, dist_id, rp, dtype=npdt_a, want_perm=False, screen=scr)
+                        tmh = ctx.timings()
+                        best = min(best, tmh["total_ms"])
+                    rec[label + "_ms"] = best
+                    if scr == 0:
+                        cells_h = float(sum(tmh["level_cells"][:-1]))
+                        rec["screen_used"] = int(tmh["screen_used"])
+                        rec["exact_cell_fraction"] = tmh["screen_exact_cells"] / max(1.0, cells_h)
+                        rec["fallback_level"] = int(tmh["screen_fallback_level"])
+                rec["default_over_exhaustive"] = rec["screened_default_ms"] / rec["exhaustive_ms"]
+                adv[kind] = rec
+            line["adversarial"] = {"n": n, "T": T, "dtype": args.dtype, "score": "Poisson multiple clustering", "cases": adv,
+                                   "worst_default_over_exhaustive": max(v["default_over_exhaustive"] for v in adv.values())}
+            ex_ms = line["other_level_kernel"]["ms_per_step"] if not args.exhaustive else main_res["ms_per_step"]
+            sc_ms = main_res["ms_per_step"] if not args.exhaustive else line["other_level_kernel"]["ms_per_step"]
+            # typical case: null-model replicas (flat objectives): screened vs exhaustive on 256 replicas of configs[3]
+            a_t, b_t = synth.poisson_null(c4["n"], seed=synth.SEED + 4, dtype=np.float32, replicas=256)
+            typ = {}
+            for label, scr in (("screened", 0), ("exhaustive", 1)):
+                best = 1e30
+                for _ in range(2):
+                    ctx.solve_raw(a_t, b_t, c4["T"], c4["dist"], c4["risk_part"], dtype=np.float32, want_perm=False, screen=scr)
+                    tmt = ctx.timings()
+                    best = min(best, tmt["total_ms"])
+                typ[label + "_ms"] = best
+                if scr == 0:
+                    typ["exact_cell_fraction"] = tmt["screen_exact_cells"] / max(1.0, float(sum(tmt["level_cells"][:-1])))
+            line["pruning"] = {
+                "what": "the default level kernels are an EXACT branch-and-bound (identical maxScore_/nextStart_ tables); their "
+                        "speed over the exhaustive kernel depends on how pronounced the row maxima are",
+                "best_case": {"workload": "C3 planted 16-level counts (the headline)", "screened_ms": sc_ms,
+                              "exhaustive_ms": ex_ms, "speedup": ex_ms / sc_ms,
+                              "exact_cell_fraction": line["roofline"].get("screen", {}).get("exact_cell_fraction")},
+                "typical_case": dict(typ, workload="256 null-model replicas (configs[3]: n=5000, T=8, f32), flat objectives",
+                                     speedup=typ["exhaustive_ms"] / typ["screened_ms"]),
+                "worst_case": {"workload": "adversarial inputs at the headline size (see `adversarial`)",
+                               "default_over_exhaustive": line["adversarial"]["worst_default_over_exhaustive"]}}
         if world > 1:
             # ---- one large instance, rows of every level sharded block-cyclically over the ranks with an NCCL
             # all-gather of the level vector per level (BASELINE configs[4] shape at a size that runs in seconds)
@@ -575,13 +733,38 @@ def main():
                     np.array_equal(one["bounds"].ravel(), sh.bounds) and np.array_equal(one["perm"], sh.perm))
         if rank == 0 and world == 1:
             dtype = np.float64 if args.dtype == "f64" else np.float32
+            # (1) SAME CONFIGURATION where the box allows it: the unmodified reference DPSolver<float> at n = 100000, T = 16
+            full = cpu_reference_full_size()
+            line["cpu_reference_full_size"] = full
+            # (2) bounded sample in the headline precision (the f64 tables, 240 GB, never fit)
             which, kind, n_s = cpu_reference_sample(dtype, 10.0)
             t, _ = run_cpu_solver(which, dtype, n_s)
-            line["cpu_baseline"] = {
+            sample_rec = {
                 "value": synth.nominal_cells(n_s, T) / t, "unit": UNIT, "cores": cpu_threads_used(kind),
-                "kind": kind, "host_cores": os.cpu_count(),
+                "kind": kind, "host_cores": os.cpu_count(), "same_config": False,
                 "sample": f"one {'reference DPSolver' if kind == 'reference' else 'oracle port'} solve at n={n_s}, "
-                          f"T={T}, {args.dtype}, same generator ({t:.2f} s); the reference cannot allocate n=100000"}
+                          f"T={T}, {args.dtype}, same generator ({t:.2f} s); the reference cannot allocate n=100000 in f64"}
+            if full.get("ran"):
+                f32_ms = (line.get("variants", {}).get("f32", {}) or {}).get("e2e", {}).get("ms_per_step") if args.dtype == "f64" \
+                    else line["e2e"]["ms_per_step"]
+                # the reference's own objective at full size next to ours (device sort: stable order)
+                from partitionsolvers_b200 import host as H
+                a32, b32 = cfg["gen"](np.float32)
+                ours = H.DPSolver(n, T, a32, b32, dist_id, rp, dtype=np.float32, ctx=ctx)
+                ours_score = float(ours.get_optimal_score_extern())
+                line["cpu_baseline"] = {
+                    "value": full["value"], "unit": UNIT, "cores": cpu_threads_used("reference"), "kind": "reference",
+                    "host_cores": os.cpu_count(), "same_config": True, "dtype": "f32", "seconds": full["seconds"],
+                    "sample": f"the unmodified reference DPSolver<float> constructor on the headline workload itself: n={n}, "
+                              f"T={T}, Poisson multiple clustering, {full['table_bytes'] / 1e9:.0f} GB of tables, "
+                              f"{full['seconds']:.1f} s (f64 needs 240 GB and does not fit)",
+                    "gpu_same_config": {"dtype": "f32", "e2e_ms_per_step": f32_ms,
+                                        "speedup_e2e": (full["seconds"] * 1e3 / f32_ms) if f32_ms else None},
+                    "objective": {"reference": full["score"], "this_library_default_sort": ours_score,
+                                  "rel_diff": abs(ours_score - full["score"]) / max(abs(full["score"]), 1e-300)},
+                    "bounded_sample_in_headline_precision": sample_rec}
+            else:
+                line["cpu_baseline"] = dict(sample_rec, full_size_leg=full)
             try:
                 # the reference's native-threaded variant on the replica workload: independent DPSolver<float>
                 # constructions dispatched on its own ThreadPool (threadpool.hpp:105-113, the call pattern of
@@ -600,7 +783,7 @@ def main():
                 line["cpu_replicas_baseline"] = {"error": str(e)}
             try:
                 from oracle import oracle_py as O
-                n_p = 20000
+                n_p = 60000  # ~6 s on 16 cores
                 ap_, bp_ = cfg["gen"](dtype, n_p)
                 tp, _ = O.time_solve("port", ap_, bp_, T, dist_id, rp, dtype=dtype, nthreads=0)
                 line["cpu_baseline_all_cores"] = {

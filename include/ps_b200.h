@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PS_B200_ABI_VERSION 2
+#define PS_B200_ABI_VERSION 3
 
 typedef enum ps_status {
   PS_OK = 0,
@@ -118,6 +118,9 @@ typedef struct ps_timings {
   long long screen_violations;      /* audit mode only; must be 0                                              */
   long long screen_tiers[6];        /* audit mode only: tiles kept, dropped; warp-stages kept, dropped;        */
                                     /* warp-groups kept, dropped (a stage = 128 k, a group = 8 k, x 32 rows)   */
+  int screen_fallback_level;        /* 0, or the first level handed to the exhaustive kernel because a screened  */
+                                    /* level had to evaluate > 30 % of its cells exactly (inputs whose rows have */
+                                    /* no pronounced maximum, e.g. constant a/b); tables are identical either way */
 } ps_timings;
 
 int ps_abi_version(void);

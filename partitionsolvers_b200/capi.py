@@ -49,7 +49,7 @@ class PsTimings(C.Structure):
                 ("level_cells", C.c_longlong * PS_MAX_TIMED_LEVELS), ("kernel_launches", C.c_longlong),
                 ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("screen_used", C.c_int),
                 ("screen_exact_cells", C.c_longlong), ("screen_violations", C.c_longlong),
-                ("screen_tiers", C.c_longlong * 6)]
+                ("screen_tiers", C.c_longlong * 6), ("screen_fallback_level", C.c_int)]
 
 
 class PsError(RuntimeError):
@@ -161,7 +161,8 @@ class Context:
                     level_cells=[t.level_cells[i] for i in range(nl)],
                     kernel_launches=t.kernel_launches, h2d_bytes=t.h2d_bytes, d2h_bytes=t.d2h_bytes,
                     screen_used=t.screen_used, screen_exact_cells=t.screen_exact_cells,
-                    screen_violations=t.screen_violations, screen_tiers=[t.screen_tiers[i] for i in range(6)])
+                    screen_violations=t.screen_violations, screen_tiers=[t.screen_tiers[i] for i in range(6)],
+                    screen_fallback_level=t.screen_fallback_level)
 
     def solve_raw(self, a, b, T, dist, risk_part, dtype=np.float32, sum_mode=PS_SUM_RUNNING, perm=None,
                   sweep=False, levels=False, chunk_len=0, want_perm=True, no_fast=False, screen=0):

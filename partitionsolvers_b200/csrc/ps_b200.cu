@@ -49,6 +49,8 @@ struct ps_ctx {
   size_t ev_used = 0;
   long long launches = 0;
   int* pinned_flags = nullptr;  // [0] range/exactness flags, [2..5] screen counters (as 2 x u64)
+  unsigned long long* pinned_levels = nullptr;  // per level: cumulative exact-cell counter (screen give-up rule)
+  size_t pinned_levels_cap = 0;
   int last_fast = 0;
   int dbg_level = 0;  // development: record per-tile times of this level (PS_DEBUG_LEVEL)
   DevBuf dbg;
@@ -455,6 +457,7 @@ ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D*
     agg.screen_used = t.screen_used;
     agg.screen_exact_cells += t.screen_exact_cells;
     agg.screen_violations += t.screen_violations;
+    agg.screen_fallback_level = std::max(agg.screen_fallback_level, t.screen_fallback_level);
     for (int q = 0; q < 6; ++q) agg.screen_tiers[q] += t.screen_tiers[q];
   }
   cudaStreamSynchronize(ctx->copy_stream);
@@ -759,7 +762,42 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   D* d_lb = (D*)ctx->lb.p;
   unsigned long long* d_cnt = (unsigned long long*)ctx->scr_counters.p;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lev_ev;
+  // Exact branch-and-bound has a worst case: on inputs whose rows have no pronounced maximum (constant a/b: every cell of a
+  // row ties) the bounds dismiss nothing and a screened level costs more than an exhaustive one.  The count of cells evaluated
+  // with the reference's arithmetic is read back per level (a few bytes, no stall: the host runs two levels ahead of the
+  // device, except for one wait after the first screened level); once a level evaluates more than SCREEN_GIVE_UP of its
+  // cells exactly, the remaining levels run the exhaustive kernel on the same (prefix) records -- same tables either way.
+  constexpr double SCREEN_GIVE_UP = 0.30;
+  bool gave_up = false;
+  std::vector<cudaEvent_t> cnt_ev(Tc + 1, nullptr);
+  unsigned long long* cnt_pin = nullptr;
+  if (screen && p.screen == 0) {
+    if ((size_t)(Tc + 2) > ctx->pinned_levels_cap) {
+      if (ctx->pinned_levels) cudaFreeHost(ctx->pinned_levels);
+      ctx->pinned_levels = nullptr;
+      ctx->pinned_levels_cap = 0;
+      PS_CUDA(ctx, cudaMallocHost((void**)&ctx->pinned_levels, (size_t)(Tc + 2 + 64) * sizeof(unsigned long long)));
+      ctx->pinned_levels_cap = (size_t)Tc + 2 + 64;
+    }
+    cnt_pin = ctx->pinned_levels;
+    cnt_pin[1] = 0;
+  }
+  auto exact_share = [&](int lev) {  // share of level lev's cells evaluated exactly (its counter copy has completed)
+    const unsigned long long d = cnt_pin[lev] - cnt_pin[lev - 1];
+    return 32.0 * (double)d / (double)(level_cells(n, lev, Tc) * R);
+  };
   for (int j = 2; j <= Tc; ++j) {
+    if (cnt_pin && !gave_up && j < Tc) {
+      const int look = (j == 3) ? 2 : j - 2;  // one blocking look at level 2, then two levels behind the launches
+      if (look >= 2 && cnt_ev[look]) {
+        PS_CUDA(ctx, cudaEventSynchronize(cnt_ev[look]));
+        if (exact_share(look) > SCREEN_GIVE_UP) {
+          gave_up = true;
+          ctx->tm.screen_fallback_level = j;
+        }
+      }
+    }
+    const bool screened_level = screen && !gave_up;
     ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, tile_rows);
     const ps::Rec4<D>* rin = recs[(j - 1) & 1];
     ps::Rec4<D>* rout = recs[j & 1];
@@ -774,7 +812,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       g.sa_nch = sa_nch;
       fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
     } else {
-      if (!screen && (long long)g.ntiles * R >= 2048) {
+      if (!screened_level && (long long)g.ntiles * R >= 2048) {
         // tile -> (row block, chunk) table (one per geometry, shared by the instances of a batch), rebuilt only when the
         // geometry changes (kmax shrinks by one per level)
         if (ctx->map_key[0] != g.NCH || ctx->map_key[1] != g.G || ctx->map_key[2] != g.NRB ||
@@ -812,7 +850,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
                                                    cdiv(n, BR));
           ctx->launches++;
         }
-      } else if (screen) {
+      } else if (screened_level) {
         // row lower bounds from a few exactly evaluated cells; range tiers for every tile -> compacted list of live tiles;
         // persistent CTAs work the list off and fold finished row blocks (no combine launch)
         fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, (float*)ctx->scr_bmax.p,
@@ -844,6 +882,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
               g, (const int*)ctx->rb_slots.p, (const int*)ctx->rb_cnt.p, cdiv(n, BR), d_pv, d_pa, lo);
         ctx->launches += 3;
         fused_fold = true;
+        if (cnt_pin) {  // cumulative count of exactly evaluated warp-cells after this level -> pinned host slot
+          PS_CUDA(ctx, cudaMemcpyAsync(&cnt_pin[j], d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+          PS_TRY(mark(ctx, &cnt_ev[j]));
+        }
       } else {
         fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
       }
@@ -1322,6 +1364,7 @@ void ps_destroy(ps_ctx* ctx) {
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
+  if (ctx->pinned_levels) cudaFreeHost(ctx->pinned_levels);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;

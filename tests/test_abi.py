@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, missing
     assert sorted(capi.ABI_SYMBOLS) == declared
-    assert lib.ps_abi_version() == 2
+    assert lib.ps_abi_version() == 3
 
 
 def test_header_is_plain_c_and_struct_mirrors_match(tmp_path):
