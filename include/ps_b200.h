@@ -37,7 +37,8 @@ typedef enum ps_status {
   PS_ERR_CUDA = 3,        /* a CUDA runtime call failed; ps_last_error(ctx) has the text              */
   PS_ERR_NOMEM = 4,       /* device or host allocation failed                                         */
   PS_ERR_NODEVICE = 5,    /* no CUDA device / driver: there is deliberately no CPU path               */
-  PS_ERR_UNSUPPORTED = 6
+  PS_ERR_UNSUPPORTED = 6,
+  PS_ERR_COMM = 7         /* NCCL missing or an NCCL call failed; ps_last_error(ctx) has the text              */
 } ps_status;
 
 /* objective_fn of the reference (score.hpp:20-22) */
@@ -118,6 +119,7 @@ typedef struct ps_timings {
   long long screen_violations;      /* audit mode only; must be 0                                              */
   long long screen_tiers[6];        /* audit mode only: tiles kept, dropped; warp-stages kept, dropped;        */
                                     /* warp-groups kept, dropped (a stage = 128 k, a group = 8 k, x 32 rows)   */
+  long long comm_bytes;             /* row-sharded solves: bytes this rank received through ncclAllGather          */
   int screen_fallback_level;        /* 0, or the first level handed to the exhaustive kernel because a screened  */
                                     /* level had to evaluate > 30 % of its cells exactly (inputs whose rows have */
                                     /* no pronounced maximum, e.g. constant a/b); tables are identical either way */
@@ -169,7 +171,35 @@ ps_status ps_selftest_mufu(ps_ctx* ctx, double out[2]);
 ps_status ps_eval_log_f64(ps_ctx* ctx, long long n, const double* x, double* y_general, double* y_fast);
 ps_status ps_eval_log_f32(ps_ctx* ctx, long long n, const float* x, float* y_general, float* y_fast);
 
-/* ---- row-sharded single instance: building blocks driven by a multi-process host ----
+/* ---- row-sharded single instance inside the library -----------------------------------------------------
+ * One very large instance (BASELINE configs[4]: n = 1e6, T = 32) solved by `world` GPUs, one host process OR thread per
+ * GPU, each with its own ps_ctx.  The reference has no counterpart (its solver is one process; the nearest thing is the pool
+ * dispatch of independent solves, python_dpsolver.cpp:263-316).  Rank r owns the 128-row blocks rb with rb % world == r
+ * (equal rows and equal cells of the triangle per rank); per level each rank computes its rows and the library issues ONE
+ * ncclAllGather of the packed {maxScore_, nextStart_} chunk on the context's stream, then scatters it to row order -- no
+ * host synchronisation between levels.  Sort, scan, level T (row 0) and the backtrace are replicated, so EVERY rank
+ * returns the full result (same bytes as ps_solve_* on one GPU; checked by tests/test_gpu_shard.py).  NCCL is bound at run
+ * time (dlopen: the copy already in the process, $PS_NCCL_LIB, the system's libnccl.so.2) and only by these calls.
+ *   rank 0:     ps_comm_unique_id(id)            -> send the PS_COMM_ID_BYTES to every rank by any means (MPI, a socket,
+ *                                                   torch.distributed, a shared variable between threads)
+ *   every rank: ps_comm_create(ctx, id, rank, world, &comm)         (collective: ncclCommInitRank)
+ *               ps_solve_sharded_f64(ctx, comm, &p, a, b, &r)        (collective; p.batch must be 1; same a, b on every rank)
+ *               ps_comm_destroy(comm)                                                                                    */
+#define PS_COMM_ID_BYTES 128
+typedef struct ps_comm ps_comm;
+ps_status ps_comm_unique_id(void* id_out /* PS_COMM_ID_BYTES */);
+ps_status ps_comm_create(ps_ctx* ctx, const void* id_bytes, int rank, int world, ps_comm** out);
+void ps_comm_destroy(ps_comm* comm);
+int ps_comm_rank(const ps_comm* comm);
+int ps_comm_world(const ps_comm* comm);
+int ps_nccl_version(void); /* 0 if NCCL could not be loaded */
+ps_status ps_solve_sharded_f32(ps_ctx* ctx, ps_comm* comm, const ps_problem* p, const float* a, const float* b,
+                               ps_result* r);
+ps_status ps_solve_sharded_f64(ps_ctx* ctx, ps_comm* comm, const ps_problem* p, const double* a, const double* b,
+                               ps_result* r);
+
+/* ---- row-sharded single instance: the same thing as building blocks driven by a multi-process host (kept for hosts that
+ * bring their own collective; partitionsolvers_b200/multigpu.ShardedSolver, tests/test_dist_gloo.py) ----
  * Rank `rank` of `world` owns row blocks rb with rb % world == rank.  The caller (one process per GPU)
  * holds the level vector, calls ps_shard_level_* for its rows, and exchanges the level vector with an
  * all-gather of its own (torch.distributed / NCCL).  All pointers are DEVICE pointers.            */

@@ -50,7 +50,7 @@ def build_cuda(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(INCLUDE, "ps_b200.h")]
     if force or _newer(target, srcs):
         cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-I", INCLUDE, "-o", target, os.path.join(CSRC, "ps_b200.cu")]
+            "-I", INCLUDE, "-o", target, os.path.join(CSRC, "ps_b200.cu"), "-ldl"]
         subprocess.run(cmd, check=True)
     return target
 

@@ -27,7 +27,10 @@ ABI_SYMBOLS = [
     "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",
     "ps_shard_destroy", "ps_selftest_math", "ps_eval_log_f64", "ps_eval_log_f32",
     "ps_ltss_f32", "ps_selftest_mufu", "ps_shard_screened", "ps_shard_subset_scores",
+    "ps_comm_unique_id", "ps_comm_create", "ps_comm_destroy", "ps_comm_rank", "ps_comm_world", "ps_nccl_version",
+    "ps_solve_sharded_f32", "ps_solve_sharded_f64",
 ]
+PS_COMM_ID_BYTES = 128
 
 
 class PsProblem(C.Structure):
@@ -49,7 +52,7 @@ class PsTimings(C.Structure):
                 ("level_cells", C.c_longlong * PS_MAX_TIMED_LEVELS), ("kernel_launches", C.c_longlong),
                 ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("screen_used", C.c_int),
                 ("screen_exact_cells", C.c_longlong), ("screen_violations", C.c_longlong),
-                ("screen_tiers", C.c_longlong * 6), ("screen_fallback_level", C.c_int)]
+                ("screen_tiers", C.c_longlong * 6), ("comm_bytes", C.c_longlong), ("screen_fallback_level", C.c_int)]
 
 
 class PsError(RuntimeError):
@@ -107,6 +110,13 @@ def load():
         for nm in ("ps_eval_log_f64", "ps_eval_log_f32"):
             getattr(L, nm).argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ps_selftest_mufu.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.ps_comm_unique_id.argtypes = [C.c_void_p]
+        L.ps_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.ps_comm_destroy.argtypes = [C.c_void_p]
+        L.ps_comm_destroy.restype = None
+        for nm in ("ps_solve_sharded_f32", "ps_solve_sharded_f64"):
+            getattr(L, nm).argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PsProblem), C.c_void_p, C.c_void_p,
+                                       C.POINTER(PsResult)]
         L.ps_ltss_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         _lib = L
@@ -162,7 +172,7 @@ class Context:
                     kernel_launches=t.kernel_launches, h2d_bytes=t.h2d_bytes, d2h_bytes=t.d2h_bytes,
                     screen_used=t.screen_used, screen_exact_cells=t.screen_exact_cells,
                     screen_violations=t.screen_violations, screen_tiers=[t.screen_tiers[i] for i in range(6)],
-                    screen_fallback_level=t.screen_fallback_level)
+                    screen_fallback_level=t.screen_fallback_level, comm_bytes=t.comm_bytes)
 
     def solve_raw(self, a, b, T, dist, risk_part, dtype=np.float32, sum_mode=PS_SUM_RUNNING, perm=None,
                   sweep=False, levels=False, chunk_len=0, want_perm=True, no_fast=False, screen=0):
@@ -225,6 +235,46 @@ class Context:
                      max_score=None, next_start=None)
         fn = self.lib.ps_solve_f32 if dtype == np.float32 else self.lib.ps_solve_f64
         self._check(fn(self._h, C.byref(p), C.c_void_p(d_a), C.c_void_p(d_b), C.byref(r)))
+
+    # ---- row-sharded solve of one instance across the GPUs of a communicator (include/ps_b200.h: ps_solve_sharded_*)
+    def comm_unique_id(self):
+        """Rank 0: the bytes every rank must pass to :meth:`comm_create` (send them by any means)."""
+        buf = C.create_string_buffer(PS_COMM_ID_BYTES)
+        self._check(self.lib.ps_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_create(self, id_bytes, rank, world):
+        h = C.c_void_p()
+        self._check(self.lib.ps_comm_create(self._h, C.c_char_p(id_bytes), int(rank), int(world), C.byref(h)))
+        return h
+
+    def comm_destroy(self, comm):
+        self.lib.ps_comm_destroy(comm)
+
+    def solve_sharded(self, comm, a, b, T, dist, risk_part, dtype=np.float64, sweep=False, levels=False, screen=0,
+                      sum_mode=PS_SUM_RUNNING, perm=None):
+        """Collective over the ranks of `comm`: same a, b on every rank; every rank gets the full result."""
+        a = np.ascontiguousarray(a, dtype=dtype)
+        b = np.ascontiguousarray(b, dtype=dtype)
+        n = a.shape[0]
+        Tc = min(T, n)
+        nS = Tc + 1 if sweep else 1
+        p = PsProblem(n=n, T=T, dist=dist, risk_part=int(risk_part), sum_mode=sum_mode,
+                      sort_mode=PS_SORT_GIVEN if perm is not None else PS_SORT_DEVICE, perm=None, sweep=int(sweep),
+                      batch=1, on_device=0, no_fast_math=0, chunk_len=0, screen=int(screen))
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, dtype=np.int32)
+            p.perm = perm.ctypes.data
+        out_perm = np.empty(n, np.int32)
+        bounds = np.empty((nS, Tc + 1), np.int32)
+        sscores = np.empty((nS, Tc), dtype)
+        ms = np.empty((Tc + 1, n), dtype) if levels else None
+        ns = np.empty((Tc + 1, n), np.int32) if levels else None
+        r = PsResult(perm=_vp(out_perm), bounds=_vp(bounds), subset_scores=_vp(sscores), max_score=_vp(ms),
+                     next_start=_vp(ns))
+        fn = self.lib.ps_solve_sharded_f32 if dtype == np.float32 else self.lib.ps_solve_sharded_f64
+        self._check(fn(self._h, comm, C.byref(p), _vp(a), _vp(b), C.byref(r)))
+        return dict(n=n, T=Tc, perm=out_perm, bounds=bounds, subset_scores=sscores, max_score=ms, next_start=ns)
 
     def selftest_math(self, which, samples, seed=1):
         out = C.c_longlong(-1)

@@ -516,7 +516,7 @@ __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int
                                D* __restrict__ ms_row, int* __restrict__ ns_row, long long table_stride,
                                Rec4<D>* __restrict__ rec_next, D* __restrict__ shard_chunk,
                                float* __restrict__ pm_next, const int* __restrict__ tile_stamp = nullptr,
-                               int stamp = 0, int stamp_stride = 0) {
+                               int stamp = 0, int stamp_stride = 0, int* __restrict__ shard_arg = nullptr) {
   // CW lanes share a row: lane q folds the q-th part of the row's chunks (contiguous, ascending), then the parts are merged
   // in ascending order with the same strict > -- the first maximum still wins.  A row's fold is a chain of dependent L2
   // round trips; with many chunks (large n) splitting it four ways shortens the chain and quadruples the loads in flight;
@@ -577,15 +577,17 @@ __global__ void combine_kernel(Geom g, const D* __restrict__ part_val, const int
     }
   }
   if (q != 0 || !row_ok) return;
+  int arg = -1;
   if (i < g.nrows) {
     // the split index is read once, for the winning chunk only (a partial equal to lowest() never wins: split -1)
-    const int arg = (mc >= 0) ? part_arg[(long long)mc * g.n + i] : -1;
+    arg = (mc >= 0) ? part_arg[(long long)mc * g.n + i] : -1;
     if (ms_row) ms_row[inst * table_stride + i] = mb;
     if (ns_row) ns_row[inst * table_stride + i] = arg;
     if (rec_next) rec_next[inst * g.rec_stride + i].p = mb;
     if (pm_next) pm_next[(inst * g.rec_stride + i) * 4 + 3] = screen_pm<D>(mb);  // .w of the float record
   }
   if (shard_chunk) shard_chunk[m] = (i < g.nrows) ? mb : Lim<D>::lowest();
+  if (shard_arg) shard_arg[m] = arg;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1223,6 +1225,34 @@ __global__ void shard_unpermute_kernel(int n, int world, int chunk, const D* __r
     if (pm_next) pm_next[(long long)i * 4 + 3] = screen_pm<D>(v);
     if (level_nat) level_nat[i] = v;
   }
+}
+
+// Row-sharded solves inside the library (ps_solve_sharded_*): after a level every rank all-gathers one packed chunk
+// { D value[chunk]; int split[chunk]; } (owned rows in block-cyclic order).  This kernel scatters the gathered chunks back to
+// natural row order: maxScore_[j], nextStart_[j], the p field of the next level's records and its float image pm.
+template <typename D, int BR>
+__global__ void shard_scatter_kernel(int n, int nrows, int world, int chunk, const unsigned char* __restrict__ gathered,
+                                     D* __restrict__ ms_row, int* __restrict__ ns_row, Rec4<D>* __restrict__ rec_next,
+                                     float* __restrict__ pm_next) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)world * chunk) return;
+  const int r = (int)(g / chunk);
+  const int m = (int)(g % chunk);
+  const int rb = r + world * (m / BR);
+  const int i = rb * BR + (m % BR);
+  if (i >= nrows) return;
+  const size_t stride = (size_t)chunk * (sizeof(D) + sizeof(int));
+  const D v = reinterpret_cast<const D*>(gathered + (size_t)r * stride)[m];
+  const int a = reinterpret_cast<const int*>(gathered + (size_t)r * stride + (size_t)chunk * sizeof(D))[m];
+  if (ms_row) ms_row[i] = v;
+  if (ns_row) ns_row[i] = a;
+  if (rec_next) rec_next[i].p = v;
+  if (pm_next) pm_next[(long long)i * 4 + 3] = screen_pm<D>(v);
+}
+
+__global__ void fill_int_kernel(long long count, int value, int* __restrict__ dst) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < count) dst[g] = value;
 }
 
 }  // namespace ps

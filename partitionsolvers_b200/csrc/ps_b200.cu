@@ -7,6 +7,8 @@
 //   optimize()        -> backtrace_bounds_kernel + backtrace_scores_kernel
 // Everything runs on the context's own non-blocking stream; the call blocks on that stream only.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the functions are resolved at run time (nccl_api below)
 
 #include <algorithm>
 #include <cstdio>
@@ -42,7 +44,8 @@ struct ps_ctx {
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
       bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp, fxinfo, pfx, cpA, cpB, ipos,
-      live, rb_info, live_hdr, kbest, rb_slots, rb_cnt;  // live-tile protocol of the screened levels (screen.cuh)
+      live, rb_info, live_hdr, kbest, rb_slots, rb_cnt,  // live-tile protocol
+      shard_send, shard_recv;  // row-sharded solves: packed level chunk, gathered chunks
   int stamp = 0;  // last stamp handed to a screened level (tile_stamp holds the stamp of the level that wrote a tile)
   int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
@@ -55,6 +58,26 @@ struct ps_ctx {
   int dbg_level = 0;  // development: record per-tile times of this level (PS_DEBUG_LEVEL)
   DevBuf dbg;
   int sm_count = 148;
+};
+
+// NCCL is bound at run time: a host that already carries an NCCL (PyTorch bundles its own libnccl.so.2) keeps exactly one
+// copy in the process, and a host without multi-GPU needs never loads it.  Order: the copy already loaded (RTLD_NOLOAD),
+// $PS_NCCL_LIB, the system's libnccl.so.2.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  std::string err;
+  bool ok = false;
+};
+
+struct ps_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
 };
 
 struct ps_shard {
@@ -140,6 +163,39 @@ ps_status mark(ps_ctx* ctx, cudaEvent_t* out) {
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+NcclApi& nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a;
+    const char* names[3] = {"libnccl.so.2", getenv("PS_NCCL_LIB"), "libnccl.so.2"};
+    const int flags[3] = {RTLD_NOW | RTLD_NOLOAD, RTLD_NOW, RTLD_NOW};
+    for (int q = 0; q < 3 && !a.handle; ++q)
+      if (names[q]) a.handle = dlopen(names[q], flags[q]);
+    if (!a.handle) {
+      a.err = "libnccl.so.2 not found (set PS_NCCL_LIB)";
+      return a;
+    }
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.handle, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
+    a.GetVersion = (decltype(a.GetVersion))dlsym(a.handle, "ncclGetVersion");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+    if (!a.ok) a.err = "libnccl.so.2 lacks a required symbol";
+    return a;
+  }();
+  return api;
+}
+
+#define PS_NCCL(ctx, expr)                                                                     \
+  do {                                                                                         \
+    ncclResult_t r__ = (expr);                                                                 \
+    if (r__ != ncclSuccess) {                                                                  \
+      (ctx)->err = std::string(#expr) + ": " + nccl_api().GetErrorString(r__);                 \
+      return PS_ERR_COMM;                                                                      \
+    }                                                                                          \
+  } while (0)
 
 // k-chunk length L: a multiple of the tile height Q (128, or 256 for the two-rows-per-thread kernel) giving enough
 // equal tiles to balance 148 SMs (SURVEY.md hard part 5).  Measured on C3: 1024..1280-wide chunks beat 4096 by
@@ -387,7 +443,7 @@ ps_status sort_stage(ps_ctx* ctx, const ps_problem& p, const D* d_a, const D* d_
 
 template <typename D>
 ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res,
-                     const D* staged_a = nullptr, const D* staged_b = nullptr);
+                     const D* staged_a = nullptr, const D* staged_b = nullptr, const ps_comm* comm = nullptr);
 
 // Large batches of independent instances from HOST buffers (randomization replicas): the batch is cut into parts; all
 // host -> device copies are queued on a second stream at once, and each part is solved as soon as its inputs have arrived,
@@ -470,7 +526,7 @@ ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D*
 
 template <typename D>
 ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res, const D* staged_a,
-                     const D* staged_b) {
+                     const D* staged_b, const ps_comm* comm) {
   if (!ctx) return PS_ERR_INVALID;
   ctx->err.clear();
   if (!pp || !a || !b || !res) {
@@ -499,8 +555,22 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     return PS_ERR_INVALID;
   }
   const int n = p.n, R = p.batch;
+  if (comm && (R != 1 || comm->device != ctx->device)) {
+    ctx->err = "sharded solve: one instance per call, communicator and context on the same device";
+    return PS_ERR_INVALID;
+  }
   if (!staged_a && !p.on_device && R >= 256 && (long long)R * n * sizeof(D) >= (16LL << 20))
     return solve_pipelined<D>(ctx, p, a, b, res, 4);
+  // Row sharding (one very large instance over the GPUs of `comm`): rank r owns the 128-row blocks rb with rb % world == r
+  // (equal rows AND equal cells of the triangle).  Everything up to the level records is replicated (sort, scan: O(n));
+  // a level is computed for the owned rows only, then ONE ncclAllGather on this stream moves every rank's packed
+  // {value, split} chunk to all ranks and a scatter kernel puts them back in row order -- no host synchronisation between
+  // levels.  Level T (row 0 only) and the backtrace are replicated: every rank ends with the full tables.
+  const int rb_first = comm ? comm->rank : 0, rb_step = comm ? comm->world : 1;
+  const int world = comm ? comm->world : 1;
+  const int chunk_rows = cdiv(cdiv(n, BR), world) * BR;  // owned rows, padded: the same on every rank
+  const int owned_blocks = cdiv(n, BR) > rb_first ? (cdiv(n, BR) - rb_first + rb_step - 1) / rb_step : 0;
+  const size_t chunk_bytes = (size_t)chunk_rows * (sizeof(D) + sizeof(int));
   const int Tc = std::min(p.T, n);  // DP_impl.hpp:37-38
   int running = (p.sum_mode == PS_SUM_RUNNING);  // cleared below when the screened path takes over (exact sums)
   const int rp = p.risk_part ? 1 : 0;
@@ -629,7 +699,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // ---- level 1
   // float Poisson on the fast path runs the two-rows-per-thread packed kernel (256-row tiles) once there are enough
   // rows to fill the machine with such tiles; smaller instances keep 128-row tiles (more, finer work items)
-  const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 &&
+  if (comm) screen_run = screen_run32 = 0;  // sharded: exact-sum screen or the exhaustive kernel
+  const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 && !comm &&
                       (long long)n * R >= 16384;
   int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
   // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);
@@ -682,6 +753,31 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     return PS_OK;
   };
   // checkpoints of the running sums: at the k-chunk boundaries, or (float running-sum screen) at every 128-block boundary
+  // row-sharded solves: packed send chunk {D value[chunk_rows]; int split[chunk_rows]} and the gathered [world] chunks
+  D* send_val = nullptr;
+  int* send_arg = nullptr;
+  unsigned char* recv_all = nullptr;
+  auto shard_buffers = [&]() -> ps_status {
+    if (send_val) return PS_OK;
+    PS_TRY(ensure(ctx, ctx->shard_send, chunk_bytes));
+    PS_TRY(ensure(ctx, ctx->shard_recv, chunk_bytes * (size_t)world));
+    send_val = (D*)ctx->shard_send.p;
+    send_arg = (int*)((unsigned char*)ctx->shard_send.p + (size_t)chunk_rows * sizeof(D));
+    recv_all = (unsigned char*)ctx->shard_recv.p;
+    PS_CUDA(ctx, cudaMemsetAsync(ctx->shard_send.p, 0, chunk_bytes, st));
+    return PS_OK;
+  };
+  // all-gather the level's chunks and scatter them to row order: maxScore_[lev], nextStart_[lev], next records' p / pm
+  auto exchange = [&](int lev, int nrows_lev, ps::Rec4<D>* rec_next, float* pm_next) -> ps_status {
+    NcclApi& nc = nccl_api();
+    PS_NCCL(ctx, nc.AllGather(ctx->shard_send.p, recv_all, chunk_bytes, ncclInt8, comm->comm, st));
+    ps::shard_scatter_kernel<D, BR><<<cdiv((long long)world * chunk_rows, 256), 256, 0, st>>>(
+        n, nrows_lev, world, chunk_rows, recv_all, (D*)ctx->ms.p + (long long)lev * n, (int*)ctx->ns.p + (long long)lev * n,
+        rec_next, pm_next);
+    ctx->launches++;
+    ctx->tm.comm_bytes += (long long)chunk_bytes * world;
+    return PS_OK;
+  };
   const int sa_L = screen_run32 ? ps::SCR_BLOCK : L;
   const int sa_nch = screen_run32 ? cp_rows : nch_alloc;
   if (running) {
@@ -693,9 +789,21 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       d_SA = (D*)bufA.p;
       d_SB = (D*)bufB.p;
     }
-    ps::level1_running_kernel<D, BR><<<dim3((cdiv(n, BR) + 1) / 2, R), BR, 0, st>>>(
-        n, sa_L, sa_nch, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
-        0, 1, nullptr, cdiv(n, BR));
+    if (!comm) {
+      ps::level1_running_kernel<D, BR><<<dim3((cdiv(n, BR) + 1) / 2, R), BR, 0, st>>>(
+          n, sa_L, sa_nch, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
+          0, 1, nullptr, cdiv(n, BR));
+    } else {
+      // owned rows only (the O(n^2) walk is what is worth sharding); values travel like every other level's, splits = n
+      PS_TRY(shard_buffers());
+      if (owned_blocks > 0)
+        ps::level1_running_kernel<D, BR><<<dim3((owned_blocks + 1) / 2, 1), BR, 0, st>>>(
+            n, sa_L, sa_nch, rec_stride, p.dist, rp, rec0, d_SA, d_SB, (D*)nullptr, (int*)nullptr, table_stride,
+            (ps::Rec4<D>*)nullptr, rb_first, rb_step, send_val, owned_blocks);
+      ps::fill_int_kernel<<<cdiv(chunk_rows, 256), 256, 0, st>>>(chunk_rows, n, send_arg);
+      ctx->launches++;
+      PS_TRY(exchange(1, n, rec1, nullptr));
+    }
     if constexpr (sizeof(D) == 4) {
       if (screen_run32) {
         PS_TRY(ensure(ctx, ctx->ipos, (size_t)R * sizeof(int)));
@@ -744,6 +852,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
 
   // ---- levels 2..Tc  (DP_impl.hpp:101-118)
   ctx->last_fast = fast;
+  if (comm) ctx->map_key[0] = -1;  // the tile map depends on the ownership pattern
   auto fn = LevelLaunch<D>::pick(p.dist, rp, running, fast);
   // float Poisson on the fast path: two rows per thread, packed f32x2 pipeline, 256-row tiles
   int tile_rows = BR;
@@ -798,7 +907,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       }
     }
     const bool screened_level = screen && !gave_up;
-    ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, tile_rows);
+    ps::Geom g = make_geom(n, j, Tc, L, nch_alloc, rb_first, rb_step, tile_rows);
     const ps::Rec4<D>* rin = recs[(j - 1) & 1];
     ps::Rec4<D>* rout = recs[j & 1];
     const bool timed = (j - 2) < PS_MAX_TIMED_LEVELS;
@@ -858,10 +967,11 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         ps::LiveHdr* hdr = (ps::LiveHdr*)ctx->live_hdr.p + j;
         const long long live_cap = (long long)R * nch_alloc * nsub * cdiv(n, BR);
         g.nsub = nsub;
-        fn_sel<<<dim3(g.NRB, R), 128 * sel_tpr, (size_t)g.NCH * (4 * sizeof(D) + 12 + nsub), st>>>(
-            g, rin, d_lb, (const float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2, (const int*)ctx->scalar.p,
-            (int4*)ctx->live.p, live_cap, (unsigned int*)ctx->rb_info.p, cdiv(n, BR), hdr, d_cnt,
-            (const int*)ctx->kbest.p, (int*)ctx->rb_slots.p, (int*)ctx->rb_cnt.p);
+        if (g.NRB > 0)
+          fn_sel<<<dim3(g.NRB, R), 128 * sel_tpr, (size_t)g.NCH * (4 * sizeof(D) + 12 + nsub), st>>>(
+              g, rin, d_lb, (const float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2, (const int*)ctx->scalar.p,
+              (int4*)ctx->live.p, live_cap, (unsigned int*)ctx->rb_info.p, cdiv(n, BR), hdr, d_cnt,
+              (const int*)ctx->kbest.p, (int*)ctx->rb_slots.p, (int*)ctx->rb_cnt.p);
         ps::LevelOut<D> lo;
         lo.ms_row = d_ms + (long long)j * n;
         lo.ns_row = d_ns + (long long)j * n;
@@ -869,38 +979,61 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         lo.rec_next = rout;
         lo.pm_next = (sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr;
         lo.shard_chunk = nullptr;
+        lo.shard_arg = nullptr;
+        if (comm) {  // owned rows go to the send chunk; the scatter after the all-gather writes the tables and records
+          PS_TRY(shard_buffers());
+          lo.ms_row = nullptr;
+          lo.ns_row = nullptr;
+          lo.rec_next = nullptr;
+          lo.pm_next = nullptr;
+          lo.shard_chunk = send_val;
+          lo.shard_arg = send_arg;
+        }
         // persistent CTAs, 8 per SM (64 registers): they pull tiles until the list is empty
         const int grid_live = (int)std::min<long long>((long long)g.ntiles * R * nsub, (long long)ctx->sm_count * 8);
-        fn_scr<<<grid_live, BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt, (const int*)ctx->scalar.p,
-                                         (const int4*)ctx->live.p, live_cap, hdr,
-                                         (ctx->dbg_level == j) ? (unsigned long long*)ctx->dbg.p : nullptr);
-        if (g.NCH >= 32)  // four lanes per row once a row has enough chunks to fold
-          ps::screen_fold_kernel<D, BR, 4><<<dim3(g.NRB, R), BR * 4, 0, st>>>(
-              g, (const int*)ctx->rb_slots.p, (const int*)ctx->rb_cnt.p, cdiv(n, BR), d_pv, d_pa, lo);
-        else
-          ps::screen_fold_kernel<D, BR, 1><<<dim3(g.NRB, R), BR, 0, st>>>(
-              g, (const int*)ctx->rb_slots.p, (const int*)ctx->rb_cnt.p, cdiv(n, BR), d_pv, d_pa, lo);
+        if (grid_live > 0)
+          fn_scr<<<grid_live, BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt, (const int*)ctx->scalar.p,
+                                           (const int4*)ctx->live.p, live_cap, hdr,
+                                           (ctx->dbg_level == j) ? (unsigned long long*)ctx->dbg.p : nullptr);
+        if (g.NRB > 0) {
+          if (g.NCH >= 32)  // four lanes per row once a row has enough chunks to fold
+            ps::screen_fold_kernel<D, BR, 4><<<dim3(g.NRB, R), BR * 4, 0, st>>>(
+                g, (const int*)ctx->rb_slots.p, (const int*)ctx->rb_cnt.p, cdiv(n, BR), d_pv, d_pa, lo);
+          else
+            ps::screen_fold_kernel<D, BR, 1><<<dim3(g.NRB, R), BR, 0, st>>>(
+                g, (const int*)ctx->rb_slots.p, (const int*)ctx->rb_cnt.p, cdiv(n, BR), d_pv, d_pa, lo);
+        }
         ctx->launches += 3;
         fused_fold = true;
         if (cnt_pin) {  // cumulative count of exactly evaluated warp-cells after this level -> pinned host slot
           PS_CUDA(ctx, cudaMemcpyAsync(&cnt_pin[j], d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
           PS_TRY(mark(ctx, &cnt_ev[j]));
         }
-      } else {
+      } else if (g.ntiles > 0) {
         fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
       }
     }
-    if (timed) PS_TRY(mark(ctx, &e1));
-    if (!fused_fold) {
+    const bool sharded_level = comm && j < Tc;  // level T (row 0 only) is computed by every rank
+    if (!fused_fold && g.NRB > 0) {
       const bool wide_combine = g.NCH >= 32;  // four lanes per row once a row has enough chunks to fold
       auto fn_combine = wide_combine ? ps::combine_kernel<D, BR, 4> : ps::combine_kernel<D, BR, 1>;
-      fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
-          g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr,
-          ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr,
-          ((screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp,
-          cdiv(n, BR));
+      float* pm_out = ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr;
+      if (sharded_level) {
+        PS_TRY(shard_buffers());
+        fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
+            g, d_pv, d_pa, (D*)nullptr, (int*)nullptr, table_stride, (ps::Rec4<D>*)nullptr, send_val, (float*)nullptr,
+            (const int*)nullptr, 0, 0, send_arg);
+      } else {
+        fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
+            g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr, pm_out,
+            ((screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp,
+            cdiv(n, BR), (int*)nullptr);
+      }
       ctx->launches++;
     }
+    if (sharded_level)
+      PS_TRY(exchange(j, g.nrows, rout, ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr));
+    if (timed) PS_TRY(mark(ctx, &e1));
     ctx->launches++;
     if (timed) {
       lev_ev.push_back({e0, e1});
@@ -919,8 +1052,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   ps::backtrace_bounds_kernel<<<cdiv((long long)R * nS, 128), 128, 0, st>>>(R, n, Tc, p.sweep ? 1 : 0, d_ns,
                                                                            d_bounds);
   ps::backtrace_scores_kernel<D><<<cdiv((long long)R * nS * Tc, 128), 128, 0, st>>>(
-      R, n, Tc, p.sweep ? 1 : 0, p.dist, rp, running, d_bounds, d_as, d_bs, rec0, rec_stride, d_SA, d_SB, sa_L,
-      sa_nch, d_scores);
+      R, n, Tc, p.sweep ? 1 : 0, p.dist, rp, running, d_bounds, d_as, d_bs, rec0, rec_stride,
+      comm ? (const D*)nullptr : d_SA, comm ? (const D*)nullptr : d_SB,  // sharded: checkpoints exist for owned rows only
+      sa_L, sa_nch, d_scores);
+  if (comm) ctx->map_key[0] = -1;
   ctx->launches += 2;
   PS_CUDA(ctx, cudaGetLastError());
   PS_TRY(mark(ctx, &e_bt));
@@ -1314,6 +1449,7 @@ const char* ps_status_string(ps_status s) {
     case PS_ERR_NOMEM: return "out of memory";
     case PS_ERR_NODEVICE: return "no CUDA device (this library has no CPU path)";
     case PS_ERR_UNSUPPORTED: return "unsupported";
+    case PS_ERR_COMM: return "NCCL error";
   }
   return "unknown";
 }
@@ -1359,7 +1495,8 @@ void ps_destroy(ps_ctx* ctx) {
                     &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->sort_hist,
                     &ctx->scalar, &ctx->recf,    &ctx->lb,       &ctx->scr_stats, &ctx->scr_counters, &ctx->tile_map,
                     &ctx->scr_bmax, &ctx->tile_stamp, &ctx->fxinfo, &ctx->pfx, &ctx->cpA, &ctx->cpB, &ctx->ipos,
-                    &ctx->live, &ctx->rb_info, &ctx->live_hdr, &ctx->kbest, &ctx->rb_slots, &ctx->rb_cnt};
+                    &ctx->live, &ctx->rb_info, &ctx->live_hdr, &ctx->kbest, &ctx->rb_slots, &ctx->rb_cnt,
+                    &ctx->shard_send, &ctx->shard_recv};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -1379,6 +1516,72 @@ ps_status ps_solve_f32(ps_ctx* ctx, const ps_problem* p, const float* a, const f
 }
 ps_status ps_solve_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, ps_result* r) {
   return solve_impl<double>(ctx, p, a, b, r);
+}
+
+// ---- multi-GPU: the library drives NCCL itself, on the context's stream
+ps_status ps_comm_unique_id(void* id_out) {
+  if (!id_out) return PS_ERR_INVALID;
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) return PS_ERR_COMM;
+  ncclUniqueId id;
+  if (nc.GetUniqueId(&id) != ncclSuccess) return PS_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == PS_COMM_ID_BYTES, "ps_b200.h: PS_COMM_ID_BYTES");
+  memcpy(id_out, &id, sizeof(id));
+  return PS_OK;
+}
+
+ps_status ps_comm_create(ps_ctx* ctx, const void* id_bytes, int rank, int world, ps_comm** out) {
+  if (!ctx || !id_bytes || !out || world < 1 || rank < 0 || rank >= world) return PS_ERR_INVALID;
+  *out = nullptr;
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) {
+    ctx->err = nc.err;
+    return PS_ERR_COMM;
+  }
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  ps_comm* c = new (std::nothrow) ps_comm();
+  if (!c) return PS_ERR_NOMEM;
+  c->rank = rank;
+  c->world = world;
+  c->device = ctx->device;
+  ncclResult_t r = nc.CommInitRank(&c->comm, world, id, rank);
+  if (r != ncclSuccess) {
+    ctx->err = std::string("ncclCommInitRank: ") + nc.GetErrorString(r);
+    delete c;
+    return PS_ERR_COMM;
+  }
+  *out = c;
+  return PS_OK;
+}
+
+void ps_comm_destroy(ps_comm* c) {
+  if (!c) return;
+  if (c->comm && nccl_api().ok) {
+    cudaSetDevice(c->device);
+    nccl_api().CommDestroy(c->comm);
+  }
+  delete c;
+}
+int ps_comm_rank(const ps_comm* c) { return c ? c->rank : -1; }
+int ps_comm_world(const ps_comm* c) { return c ? c->world : 0; }
+int ps_nccl_version(void) {
+  int v = 0;
+  NcclApi& nc = nccl_api();
+  if (nc.ok && nc.GetVersion) nc.GetVersion(&v);
+  return v;
+}
+
+ps_status ps_solve_sharded_f32(ps_ctx* ctx, ps_comm* comm, const ps_problem* p, const float* a, const float* b,
+                               ps_result* r) {
+  if (!comm) return PS_ERR_INVALID;
+  return solve_impl<float>(ctx, p, a, b, r, nullptr, nullptr, comm);
+}
+ps_status ps_solve_sharded_f64(ps_ctx* ctx, ps_comm* comm, const ps_problem* p, const double* a, const double* b,
+                               ps_result* r) {
+  if (!comm) return PS_ERR_INVALID;
+  return solve_impl<double>(ctx, p, a, b, r, nullptr, nullptr, comm);
 }
 
 ps_status ps_get_timings(const ps_ctx* ctx, ps_timings* out) {

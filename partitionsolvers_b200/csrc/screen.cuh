@@ -948,6 +948,7 @@ struct LevelOut {
   Rec4<D>* rec_next;       // next level's records (p field), instance 0
   float* pm_next;          // float4 screening records of the next level viewed as floats (.w), or nullptr
   D* shard_chunk;          // row-sharded runs: owned rows in block-cyclic order, or nullptr
+  int* shard_arg;          // row-sharded runs: the split indices in the same order, or nullptr
 };
 
 // Fold the partials of every row block over its live tiles (ascending chunks = ascending k; strict > keeps the first
@@ -999,9 +1000,10 @@ screen_fold_kernel(Geom g, const int* __restrict__ rb_slots, const int* __restri
     }
   }
   if (q != 0) return;
+  int arg = -1;
   if (i < g.nrows) {
     // the split index is read once, for the winning chunk only (a partial equal to lowest() never wins: split -1)
-    const int arg = (mc >= 0) ? part_arg[(long long)mc * g.n + i] : -1;
+    arg = (mc >= 0) ? part_arg[(long long)mc * g.n + i] : -1;
     if (out.ms_row) out.ms_row[inst * out.table_stride + i] = mb;
     if (out.ns_row) out.ns_row[inst * out.table_stride + i] = arg;
     if (out.rec_next) out.rec_next[inst * g.rec_stride + i].p = mb;
@@ -1010,6 +1012,7 @@ screen_fold_kernel(Geom g, const int* __restrict__ rb_slots, const int* __restri
   if (out.shard_chunk) {
     const int m = (rb - g.rb_first) / g.rb_step;
     out.shard_chunk[(long long)m * BR + r] = (i < g.nrows) ? mb : Lim<D>::lowest();
+    if (out.shard_arg) out.shard_arg[(long long)m * BR + r] = arg;
   }
 }
 

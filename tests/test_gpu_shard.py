@@ -69,3 +69,55 @@ def test_sharded_solver_subset_scores(ctx, kind):
     assert np.array_equal(sh.bounds, full["bounds"].ravel())
     assert np.array_equal(sh.perm, full["perm"])
     assert np.array_equal(sh.subset_scores, full["subset_scores"].ravel())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ps_solve_sharded_*: the per-level loop, the NCCL all-gather and the scatter inside the library (include/ps_b200.h)
+# ------------------------------------------------------------------------------------------------------------------
+SHARD_CASES = [
+    ("counts_screened", 8192, 6, 1, False),   # exact-sum screened levels (live tiles, fold -> packed chunk)
+    ("counts_small", 1000, 5, 1, False),      # below the screening threshold: exhaustive kernel, prefix-free running sums
+    ("real_running", 3000, 5, 2, False),      # real-valued data: exhaustive kernel on RUNNING sums, sharded level-1 walk
+    ("counts_rp", 6500, 4, 1, True),          # Poisson risk-part: box tiers
+]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name,n,T,dist_id,rp", SHARD_CASES)
+def test_solve_sharded_one_rank_equals_unsharded(ctx, dt, name, n, T, dist_id, rp):
+    """A communicator of ONE rank on this device drives the complete sharded path -- owned-row kernels, ncclAllGather on the
+    engine's stream, scatter, replicated last level and backtrace -- and must return the bytes of ps_solve_*: sort index,
+    boundaries, subset scores, every maxScore_ / nextStart_ cell, with and without the sweep."""
+    if name.startswith("counts"):
+        a, b = synth.poisson_planted(n, T, seed=51, dtype=dt)
+    else:
+        a, b = synth.gaussian_mixture(n, T, seed=52, dtype=dt)
+    comm = ctx.comm_create(ctx.comm_unique_id(), 0, 1)
+    try:
+        for sweep in (False, True):
+            full = ctx.solve_raw(a, b, T, dist_id, rp, dtype=dt, levels=True, sweep=sweep)
+            used = ctx.timings()["screen_used"]
+            sh = ctx.solve_sharded(comm, a, b, T, dist_id, rp, dtype=dt, levels=True, sweep=sweep)
+            t = ctx.timings()
+            assert t["screen_used"] == used and t["comm_bytes"] > 0
+            for k in ("perm", "bounds", "subset_scores", "max_score", "next_start"):
+                assert np.array_equal(np.asarray(sh[k]).ravel(), np.asarray(full[k]).ravel()), (name, k, sweep)
+    finally:
+        ctx.comm_destroy(comm)
+
+
+def test_solve_sharded_two_processes():
+    """Two ranks, two GPUs, NCCL between them (tools/shard_check.py under torchrun): every rank's result equals the
+    single-GPU solve.  Skipped on a one-GPU box; the 8-GPU run is bench.py --gpus 8 (`sharded`)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "shard_check.py"),
+                        "--size", "20000", "--parts", "6", "--check"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SHARD_CHECK_OK" in r.stdout
