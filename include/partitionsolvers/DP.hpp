@@ -185,6 +185,11 @@ class DPSolver {
 
   // beyond the reference: what the engine measured for this construction (CUDA events)
   const ps_timings& engine_timings() const { return timings_; }
+  // beyond the reference, sweeps only: entry S = what get_optimal_score_extern() of a separate DPSolver(n, S, ...) returns
+  // (DP_impl.hpp:267-276 applied to the S-partition).  The levels of a T-solve ARE the levels of every S-solve, S <= T
+  // (gtest_all.cpp:603-662, 735-856 pin sweep[S] == solve(T = S)), so the flat API's sweep_best__DP / sweep_parallel__DP
+  // take their T results from ONE pass instead of T constructions.
+  const std::vector<DataType>& sweep_extern_scores() const { return sweep_extern_scores_; }
   const std::vector<int>& priority_sortind() const { return priority_sortind_; }
 
  private:
@@ -205,6 +210,7 @@ class DPSolver {
   bool find_optimal_t_ = false;
   all_part_scores subsets_and_scores_;
   int optimal_num_clusters_OLS_ = 0;
+  std::vector<DataType> sweep_extern_scores_;
   ps_timings timings_{};
 
   all_scores build_partition(int S, const int* bounds, const DataType* scores) {  // DP_impl.hpp:122-153
@@ -233,6 +239,15 @@ class DPSolver {
     }
     optimal -= gamma_ * std::pow(S, reg_power_);
     if (S == T_) score_by_subset_ = sc;
+    if (static_cast<size_t>(S) < sweep_extern_scores_.size()) {  // the getter of a separate S-solve, DP_impl.hpp:267-276
+      if (risk_partitioning_objective_) {
+        sweep_extern_scores_[S] = optimal;
+      } else {
+        double acc = 0.;
+        for (int q = 1; q < S; ++q) acc += sc[q];
+        sweep_extern_scores_[S] = static_cast<DataType>(acc - gamma_ * std::pow(S, reg_power_));
+      }
+    }
     return all_scores{subsets, optimal};
   }
 
@@ -256,7 +271,31 @@ class DPSolver {
     p.batch = 1;
     priority_sortind_.assign(n_, 0);
     std::vector<int> host_perm;
-    if (env_flag("PARTITIONSOLVERS_HOST_SORT")) {
+    std::vector<DataType> a_kept, b_kept;  // n < a.size(): the n lowest-priority elements, in sorted order
+    if (static_cast<size_t>(n_) < a_.size()) {
+      // The reference sorts the WHOLE vectors and keeps the first n sorted elements (DP_impl.hpp:10-27; priority_sortind_
+      // then has a.size() entries).  Rare call pattern: the order is formed on the host -- std::sort in parity mode, else the
+      // stable order the device sort produces -- and the engine is handed the kept elements already sorted.
+      std::vector<int> ind(a_.size());
+      std::iota(ind.begin(), ind.end(), 0);
+      const std::vector<DataType>&a = a_, &b = b_;
+      auto less = [&a, &b](int i, int j) { return (a[i] / b[i]) < (a[j] / b[j]); };
+      if (env_flag("PARTITIONSOLVERS_HOST_SORT"))
+        std::sort(ind.begin(), ind.end(), less);
+      else
+        std::stable_sort(ind.begin(), ind.end(), less);
+      a_kept.resize(n_);
+      b_kept.resize(n_);
+      for (int i = 0; i < n_; ++i) {
+        a_kept[i] = a_[ind[i]];
+        b_kept[i] = b_[ind[i]];
+      }
+      host_perm.resize(n_);
+      std::iota(host_perm.begin(), host_perm.end(), 0);
+      p.sort_mode = PS_SORT_GIVEN;
+      p.perm = host_perm.data();
+      priority_sortind_ = ind;
+    } else if (env_flag("PARTITIONSOLVERS_HOST_SORT")) {
       // parity mode: std::sort with the reference's comparator (DP_impl.hpp:13-16) so that tied priorities
       // land exactly where the reference leaves them
       host_perm.resize(n_);
@@ -271,11 +310,12 @@ class DPSolver {
     std::vector<DataType> sc(static_cast<size_t>(nS) * T_);
     ps_result r;
     std::memset(&r, 0, sizeof(r));
-    r.perm = priority_sortind_.data();
+    r.perm = a_kept.empty() ? priority_sortind_.data() : nullptr;  // truncated call: the sort index was formed above
     r.bounds = bounds.data();
     r.subset_scores = sc.data();
     ps_ctx* ctx = ThreadContext::get();
-    ps_status st = solve(ctx, &p, a_.data(), b_.data(), &r);
+    ps_status st = a_kept.empty() ? solve(ctx, &p, a_.data(), b_.data(), &r)
+                                  : solve(ctx, &p, a_kept.data(), b_kept.data(), &r);
     if (st == PS_ERR_DIST) throw distributionException();
     if (st != PS_OK) throw engine_error(std::string("ps_solve: ") + ps_last_error(ctx));
     ps_get_timings(ctx, &timings_);
@@ -286,6 +326,7 @@ class DPSolver {
     optimal_score_ = 0.;
     if (sweep) {  // optimize(), DP_impl.hpp:203-224
       subsets_and_scores_ = all_part_scores{static_cast<size_t>(T_ + 1)};
+      sweep_extern_scores_.assign(static_cast<size_t>(T_ + 1), DataType(0));
       for (int S = T_; S >= 1; --S)
         subsets_and_scores_[S] = build_partition(S, &bounds[static_cast<size_t>(S) * (T_ + 1)],
                                                  &sc[static_cast<size_t>(S) * T_]);

@@ -68,7 +68,9 @@ typedef struct ps_problem {
   int sweep;       /* 0: backtrace S=T only (DP_impl.hpp:226-228); 1: every S=T..1 (:203-214)         */
   int batch;       /* independent instances R>=1 (replicas); a,b are [R][n] row-major.  Host-buffer    */
                    /* batches of >= 256 instances and >= 16 MB are solved in four parts whose copies   */
-                   /* overlap the kernels of the parts before them (same outputs as one call)          */
+                   /* overlap the kernels of the parts before them (same outputs as one call; the       */
+                   /* overlap needs PINNED host buffers, pageable ones are staged synchronously).       */
+                   /* More than 65535 instances are solved in consecutive slices of that size.          */
   int on_device;   /* 1: a, b, perm AND every ps_result pointer are device pointers on ctx's device   */
   int no_fast_math;/* debug: 1 = never take the range-prechecked branch-free math path (csrc/math_fast.cuh);  */
                    /*        2 = take it, but not the packed two-rows-per-thread float kernel               */
@@ -135,6 +137,12 @@ const char* ps_last_error(const ps_ctx* ctx);
 int ps_device(const ps_ctx* ctx);
 /* cudaStream_t of the context, as an integer (for callers that order their own work after ours) */
 uintptr_t ps_stream(const ps_ctx* ctx);
+/* The engine works on its OWN non-blocking stream, which has no implicit ordering with any other stream.  Device buffers
+ * handed to the library (ps_problem.on_device = 1, ps_shard_*) must therefore be complete when the call is made -- or the
+ * caller orders them explicitly: ps_stream_wait makes everything the engine enqueues from now on wait for the work
+ * `other_stream` (a cudaStream_t as an integer; 0 = the legacy default stream) has been given so far.  Results are complete
+ * on return (every ps_solve_* blocks on the engine's stream). */
+ps_status ps_stream_wait(ps_ctx* ctx, uintptr_t other_stream);
 
 /* One call = the whole constructor of DPSolver<D>: sort_by_priority, range scores, the T-level DP
  * fill and the backtrace(s) (DP_impl.hpp:69-153,200-230).  Blocking. */

@@ -188,6 +188,25 @@ def dp_rows(a_sorted, b_sorted, prev, kmax, dist, risk_part, rows, dtype=np.floa
     return best, arg
 
 
+def ref_solve_truncated(n, a, b, T, dist, risk_part):
+    """The reference constructor with n < len(a) (f32): returns (subsets, getter score)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    Tc = min(T, n)
+    nsub, sizes, elems, sc = C.c_int(0), np.zeros(Tc, np.int32), np.zeros(n, np.int32), C.c_float(0)
+    fn = lib("ref").ref_dp_solve_trunc_f32
+    fn.restype = C.c_int
+    rc = fn(C.c_int(n), C.c_int(a.shape[0]), C.c_int(T), _ptr(a, C.c_float), _ptr(b, C.c_float), C.c_int(dist),
+            C.c_int(int(risk_part)), C.byref(nsub), _ptr(sizes, C.c_int), _ptr(elems, C.c_int), C.byref(sc))
+    if rc:
+        raise RuntimeError("ref_dp_solve_trunc_f32 failed")
+    subsets, off = [], 0
+    for s in range(nsub.value):
+        subsets.append(elems[off:off + sizes[s]].tolist())
+        off += sizes[s]
+    return subsets, np.float32(sc.value)
+
+
 def ltss(which, a, b, dist):
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)

@@ -237,4 +237,26 @@ int ref_ltss_f32(int n, const float* a, const float* b, int dist, int* perm, int
 
 int ref_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
+// The constructor called with n < a.size() (DP_impl.hpp:10-27: the sort spans the whole vectors, the first n sorted elements
+// are kept): subsets and the getter's score.
+int ref_dp_solve_trunc_f32(int n, int len, int T, const float* a, const float* b, int dist, int risk_part,
+                           int* n_subsets, int* subset_sizes, int* subset_elems, float* score) {
+  try {
+    std::vector<float> av(a, a + len), bv(b, b + len);
+    DPSolver<float> dp(n, T, av, bv, static_cast<objective_fn>(dist), risk_part != 0, true);
+    auto subsets = dp.get_optimal_subsets_extern();
+    *n_subsets = (int)subsets.size();
+    int off = 0;
+    for (size_t s = 0; s < subsets.size(); ++s) {
+      subset_sizes[s] = (int)subsets[s].size();
+      for (int v : subsets[s]) subset_elems[off++] = v;
+    }
+    *score = dp.get_optimal_score_extern();
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "ref_shim: " << e.what() << std::endl;
+    return 1;
+  }
+}
+
 }  // extern "C"

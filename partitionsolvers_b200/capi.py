@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "ps_shard_destroy", "ps_selftest_math", "ps_eval_log_f64", "ps_eval_log_f32",
     "ps_ltss_f32", "ps_selftest_mufu", "ps_shard_screened", "ps_shard_subset_scores",
     "ps_comm_unique_id", "ps_comm_create", "ps_comm_destroy", "ps_comm_rank", "ps_comm_world", "ps_nccl_version",
-    "ps_solve_sharded_f32", "ps_solve_sharded_f64",
+    "ps_solve_sharded_f32", "ps_solve_sharded_f64", "ps_stream_wait",
 ]
 PS_COMM_ID_BYTES = 128
 
@@ -110,6 +110,7 @@ def load():
         for nm in ("ps_eval_log_f64", "ps_eval_log_f32"):
             getattr(L, nm).argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ps_selftest_mufu.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.ps_stream_wait.argtypes = [C.c_void_p, C.c_size_t]
         L.ps_comm_unique_id.argtypes = [C.c_void_p]
         L.ps_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.ps_comm_destroy.argtypes = [C.c_void_p]
@@ -160,6 +161,16 @@ class Context:
     @property
     def stream(self):
         return self.lib.ps_stream(self._h)
+
+    def wait_stream(self, other_stream):
+        """Order the engine's stream after the work enqueued so far on `other_stream` (a cudaStream_t as an integer, e.g.
+        torch.cuda.current_stream().cuda_stream): device buffers produced there may then be passed to solve_device."""
+        self._check(self.lib.ps_stream_wait(self._h, int(other_stream)))
+
+    def wait_torch(self, device=None):
+        """wait_stream on torch's current stream of `device` (torch is imported only here)."""
+        import torch
+        self.wait_stream(torch.cuda.current_stream(device).cuda_stream)
 
     def timings(self):
         t = PsTimings()

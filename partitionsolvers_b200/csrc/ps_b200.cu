@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -27,6 +28,7 @@
 namespace {
 
 constexpr int BR = 128;  // rows per tile == threads per CTA == records per shared-memory stage
+constexpr int PS_MAX_BATCH_SLICE = 65535;  // instances per launch (grid.y)
 
 struct DevBuf {
   void* p = nullptr;
@@ -58,6 +60,7 @@ struct ps_ctx {
   int dbg_level = 0;  // development: record per-tile times of this level (PS_DEBUG_LEVEL)
   DevBuf dbg;
   int sm_count = 148;
+  cudaEvent_t wait_event = nullptr;  // ps_stream_wait
 };
 
 // NCCL is bound at run time: a host that already carries an NCCL (PyTorch bundles its own libnccl.so.2) keeps exactly one
@@ -210,6 +213,33 @@ int choose_chunk(int n, int batch, int user, int Q) {
   L = std::min<long long>(L, 16384);
   L = std::min<long long>(L, ((n + Q - 1) / Q) * (long long)Q);
   return (int)std::max<long long>(L, Q);
+}
+
+// The screened kernels' error budget rests on two properties of the MUFU unit (screen.cuh header: |x rcp(x) - 1| <= 4u,
+// |lg2 x - log2 x| <= 4u max(1, |log2 x|), u = 2^-24; measured 1.65u / 3.85u on B200).  They are verified on the device at
+// hand -- every float of the safe range, ~20 ms -- the first time a context on that device wants a screened level; the verdict
+// is cached per device for the life of the process.  A device that fails keeps the exhaustive kernel (same tables, slower).
+int g_mufu_state[64] = {0};  // 0 unknown, 1 claims hold, -1 claims fail
+double g_mufu_err[64][2];
+std::mutex g_mufu_mutex;
+bool mufu_claims_hold(ps_ctx* ctx) {
+  const int d = ctx->device;
+  if (d < 0 || d >= 64) return false;
+  std::lock_guard<std::mutex> lk(g_mufu_mutex);
+  if (g_mufu_state[d] == 0) {
+    double out[2] = {1e9, 1e9};
+    bool ran = ensure(ctx, ctx->scalar, 64) == PS_OK;
+    ran = ran && cudaMemsetAsync(ctx->scalar.p, 0, 2 * sizeof(double), ctx->stream) == cudaSuccess;
+    if (ran) {
+      ps::selftest_mufu_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((double*)ctx->scalar.p);
+      ran = cudaMemcpyAsync(out, ctx->scalar.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+            cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    }
+    g_mufu_err[d][0] = out[0];
+    g_mufu_err[d][1] = out[1];
+    g_mufu_state[d] = (ran && out[0] > 0.0 && out[0] <= 4.0 && out[1] > 0.0 && out[1] <= 4.0) ? 1 : -1;
+  }
+  return g_mufu_state[d] == 1;
 }
 
 template <typename D>
@@ -445,13 +475,54 @@ template <typename D>
 ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res,
                      const D* staged_a = nullptr, const D* staged_b = nullptr, const ps_comm* comm = nullptr);
 
+// timings of a call that was executed as several sub-calls
+void add_timings(ps_timings& agg, const ps_timings& t) {
+  agg.total_ms += t.total_ms;
+  agg.h2d_ms += t.h2d_ms;
+  agg.sort_scan_ms += t.sort_scan_ms;
+  agg.prepass_ms += t.prepass_ms;
+  agg.levels_ms += t.levels_ms;
+  agg.backtrace_ms += t.backtrace_ms;
+  agg.d2h_ms += t.d2h_ms;
+  agg.n_levels = t.n_levels;
+  for (int q = 0; q < t.n_levels; ++q) {
+    agg.level_ms[q] += t.level_ms[q];
+    agg.level_cells[q] += t.level_cells[q];
+  }
+  agg.kernel_launches += t.kernel_launches;
+  agg.h2d_bytes += t.h2d_bytes;
+  agg.d2h_bytes += t.d2h_bytes;
+  agg.screen_used = t.screen_used;
+  agg.screen_exact_cells += t.screen_exact_cells;
+  agg.screen_violations += t.screen_violations;
+  agg.screen_fallback_level = std::max(agg.screen_fallback_level, t.screen_fallback_level);
+  for (int q = 0; q < 6; ++q) agg.screen_tiers[q] += t.screen_tiers[q];
+}
+
+// sub-problem / sub-result of instances [r0, r0 + rk) of a batch (plain pointer arithmetic: host or device buffers alike)
+template <typename D>
+void slice_batch(const ps_problem& p, const ps_result& res, int r0, int rk, ps_problem& pk, ps_result& rk_res) {
+  const int n = p.n, Tc = std::min(p.T, n), nS = p.sweep ? Tc + 1 : 1;
+  const long long off = (long long)r0 * n;
+  pk = p;
+  pk.batch = rk;
+  if (p.perm) pk.perm = p.perm + off;
+  rk_res = res;
+  if (res.perm) rk_res.perm = res.perm + off;
+  if (res.bounds) rk_res.bounds = res.bounds + (long long)r0 * nS * (Tc + 1);
+  if (res.subset_scores) rk_res.subset_scores = (D*)res.subset_scores + (long long)r0 * nS * Tc;
+  if (res.max_score) rk_res.max_score = (D*)res.max_score + (long long)r0 * (Tc + 1) * n;
+  if (res.next_start) rk_res.next_start = res.next_start + (long long)r0 * (Tc + 1) * n;
+}
+
 // Large batches of independent instances from HOST buffers (randomization replicas): the batch is cut into parts; all
 // host -> device copies are queued on a second stream at once, and each part is solved as soon as its inputs have arrived,
-// so the copies of the later parts run under the kernels of the earlier ones.  Results are those of one call.
+// so the copies of the later parts run under the kernels of the earlier ones.  Results are those of one call.  The overlap
+// needs PINNED host buffers (cudaHostAlloc / cudaHostRegister): from pageable memory cudaMemcpyAsync stages synchronously
+// and the copies simply run first (same results, no overlap).
 template <typename D>
 ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D* b, ps_result* res, int parts) {
-  const int n = p.n, R = p.batch, Tc = std::min(p.T, n);
-  const int nS = p.sweep ? Tc + 1 : 1;
+  const int n = p.n, R = p.batch;
   PS_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->copy_stream) PS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   const long long total = (long long)R * n;
@@ -461,8 +532,21 @@ ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D*
   D* d_b = (D*)ctx->b_in.p;
   const int per = cdiv(R, parts);
   std::vector<cudaEvent_t> arrived;
+  cudaEvent_t e_c0 = nullptr, e_c1 = nullptr;  // copy-stream time of all parts -> ps_timings.h2d_ms
+  struct EventGuard {  // every exit path destroys the events created here
+    std::vector<cudaEvent_t>& v;
+    cudaEvent_t &a, &b;
+    ~EventGuard() {
+      for (cudaEvent_t e : v) cudaEventDestroy(e);
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } event_guard{arrived, e_c0, e_c1};
   // buffers of an earlier call may still be read by kernels on the compute stream
   PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PS_CUDA(ctx, cudaEventCreate(&e_c0));
+  PS_CUDA(ctx, cudaEventCreate(&e_c1));
+  PS_CUDA(ctx, cudaEventRecord(e_c0, ctx->copy_stream));
   for (int r0 = 0; r0 < R; r0 += per) {
     const long long off = (long long)r0 * n, cnt = (long long)std::min(per, R - r0) * n;
     PS_CUDA(ctx, cudaMemcpyAsync(d_a + off, a + off, cnt * sizeof(D), cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -472,6 +556,7 @@ ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D*
     PS_CUDA(ctx, cudaEventRecord(e, ctx->copy_stream));
     arrived.push_back(e);
   }
+  PS_CUDA(ctx, cudaEventRecord(e_c1, ctx->copy_stream));
   ps_timings agg;
   memset(&agg, 0, sizeof(agg));
   ps_status st = PS_OK;
@@ -479,15 +564,9 @@ ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D*
   for (int r0 = 0; r0 < R && st == PS_OK; r0 += per, ++part) {
     const int rk = std::min(per, R - r0);
     const long long off = (long long)r0 * n;
-    ps_problem pk = p;
-    pk.batch = rk;
-    if (p.perm) pk.perm = p.perm + off;
-    ps_result rk_res = *res;
-    if (res->perm) rk_res.perm = res->perm + off;
-    if (res->bounds) rk_res.bounds = res->bounds + (long long)r0 * nS * (Tc + 1);
-    if (res->subset_scores) rk_res.subset_scores = (D*)res->subset_scores + (long long)r0 * nS * Tc;
-    if (res->max_score) rk_res.max_score = (D*)res->max_score + (long long)r0 * (Tc + 1) * n;
-    if (res->next_start) rk_res.next_start = res->next_start + (long long)r0 * (Tc + 1) * n;
+    ps_problem pk;
+    ps_result rk_res;
+    slice_batch<D>(p, *res, r0, rk, pk, rk_res);
     cudaError_t ce = cudaStreamWaitEvent(ctx->stream, arrived[part], 0);
     if (ce != cudaSuccess) {
       ctx->err = std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(ce);
@@ -496,29 +575,11 @@ ps_status solve_pipelined(ps_ctx* ctx, const ps_problem& p, const D* a, const D*
     }
     st = solve_impl<D>(ctx, &pk, a + off, b + off, &rk_res, d_a + off, d_b + off);
     if (st != PS_OK) break;
-    const ps_timings& t = ctx->tm;
-    agg.total_ms += t.total_ms;
-    agg.sort_scan_ms += t.sort_scan_ms;
-    agg.prepass_ms += t.prepass_ms;
-    agg.levels_ms += t.levels_ms;
-    agg.backtrace_ms += t.backtrace_ms;
-    agg.d2h_ms += t.d2h_ms;
-    agg.n_levels = t.n_levels;
-    for (int q = 0; q < t.n_levels; ++q) {
-      agg.level_ms[q] += t.level_ms[q];
-      agg.level_cells[q] += t.level_cells[q];
-    }
-    agg.kernel_launches += t.kernel_launches;
-    agg.d2h_bytes += t.d2h_bytes;
-    agg.screen_used = t.screen_used;
-    agg.screen_exact_cells += t.screen_exact_cells;
-    agg.screen_violations += t.screen_violations;
-    agg.screen_fallback_level = std::max(agg.screen_fallback_level, t.screen_fallback_level);
-    for (int q = 0; q < 6; ++q) agg.screen_tiers[q] += t.screen_tiers[q];
+    add_timings(agg, ctx->tm);
   }
   cudaStreamSynchronize(ctx->copy_stream);
-  for (cudaEvent_t e : arrived) cudaEventDestroy(e);
   if (st != PS_OK) return st;
+  cudaEventElapsedTime(&agg.h2d_ms, e_c0, e_c1);
   agg.h2d_bytes = 2 * total * (long long)sizeof(D) + (p.perm ? total * (long long)sizeof(int) : 0);
   ctx->tm = agg;
   return PS_OK;
@@ -538,9 +599,21 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     ctx->err = "n, T and batch must be >= 1";
     return PS_ERR_INVALID;
   }
-  if (p.batch > 65535) {
-    ctx->err = "batch > 65535 instances per call: split the batch";
-    return PS_ERR_UNSUPPORTED;
+  if (p.batch > PS_MAX_BATCH_SLICE && !comm) {
+    // the instance index is a grid dimension (<= 65535): larger batches run as consecutive slices, results as one call
+    ps_timings agg;
+    memset(&agg, 0, sizeof(agg));
+    for (int r0 = 0; r0 < p.batch; r0 += PS_MAX_BATCH_SLICE) {
+      const int rk = std::min(PS_MAX_BATCH_SLICE, p.batch - r0);
+      ps_problem pk;
+      ps_result rk_res;
+      slice_batch<D>(p, *res, r0, rk, pk, rk_res);
+      const long long off = (long long)r0 * p.n;
+      PS_TRY(solve_impl<D>(ctx, &pk, a + off, b + off, &rk_res));
+      add_timings(agg, ctx->tm);
+    }
+    ctx->tm = agg;
+    return PS_OK;
   }
   if (p.dist < 0 || p.dist > 2) {
     ctx->err = "Bad distributional assignment";
@@ -612,9 +685,10 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   cudaEvent_t e_flags = nullptr;
   const bool want_fast = running && p.no_fast_math != 1;
   // screened levels (screen.cuh): worth it once a level has enough cells to amortise the extra launch
-  const bool want_screen = want_fast && p.screen != 1 && p.no_fast_math == 0 && std::min(p.T, n) >= 3 && n >= 512 &&
-                           n <= 4000000 &&            // tile geometry of the live-tile kernels (<= 32 stages, <= 1000 chunks)
-                           (long long)n * R >= 6000;  // measured crossover (tools/screen_threshold.py)
+  bool want_screen = want_fast && p.screen != 1 && p.no_fast_math == 0 && std::min(p.T, n) >= 3 && n >= 512 &&
+                     n <= 4000000 &&            // tile geometry of the live-tile kernels (<= 32 stages, <= 1000 chunks)
+                     (long long)n * R >= 6000;  // measured crossover (tools/screen_threshold.py)
+  if (want_screen && !mufu_claims_hold(ctx)) want_screen = false;  // hardware claims of the error budget, once per device
   if (want_fast) {
     PS_TRY(ensure(ctx, ctx->scalar, 64));
     PS_CUDA(ctx, cudaMemsetAsync(ctx->scalar.p, 0, 2 * sizeof(int), st));  // [0] range/exactness, [1] sortedness
@@ -1230,6 +1304,12 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   PS_CUDA(ctx, cudaSetDevice(ctx->device));
   ps_shard* s = new (std::nothrow) ps_shard();
   if (!s) return PS_ERR_NOMEM;
+  struct Guard {  // any early return below releases what has been allocated so far (cudaFree(nullptr) is a no-op)
+    ps_shard* s;
+    ~Guard() {
+      if (s) ps_shard_destroy(s);
+    }
+  } guard{s};
   s->ctx = ctx;
   s->dtype = (int)sizeof(D);
   s->p = *pp;
@@ -1253,7 +1333,8 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
     PS_CUDA(ctx, cudaMalloc((void**)&s->dflags, 2 * sizeof(int)));
     PS_CUDA(ctx, cudaMemsetAsync(s->dflags, 0, 2 * sizeof(int), st));
     ps::range_check_kernel<D><<<cdiv(n, 256), 256, 0, st>>>(n, a_s, b_s, s->dflags);
-    const bool want_screen = pp->screen != 1 && pp->screen != 2 && pp->no_fast_math == 0 && Tc >= 3 && n >= 6000 && n <= 4000000;
+    const bool want_screen = pp->screen != 1 && pp->screen != 2 && pp->no_fast_math == 0 && Tc >= 3 && n >= 6000 && n <= 4000000 &&
+                             mufu_claims_hold(ctx);
     if (want_screen) {
       PS_TRY(ensure(ctx, ctx->scr_stats, sizeof(ps::ScreenStats)));
       ps::ScreenStats* d_st = (ps::ScreenStats*)ctx->scr_stats.p;
@@ -1311,6 +1392,7 @@ ps_status shard_create_impl(ps_ctx* ctx, const ps_problem* pp, const D* a_s, con
   PS_CUDA(ctx, cudaGetLastError());
   PS_CUDA(ctx, cudaStreamSynchronize(st));
   s->cur = 0;
+  guard.s = nullptr;
   *out = s;
   return PS_OK;
 }
@@ -1501,6 +1583,7 @@ void ps_destroy(ps_ctx* ctx) {
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
+  if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
   if (ctx->pinned_levels) cudaFreeHost(ctx->pinned_levels);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1510,6 +1593,15 @@ void ps_destroy(ps_ctx* ctx) {
 const char* ps_last_error(const ps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int ps_device(const ps_ctx* ctx) { return ctx ? ctx->device : -1; }
 uintptr_t ps_stream(const ps_ctx* ctx) { return ctx ? (uintptr_t)ctx->stream : 0; }
+
+ps_status ps_stream_wait(ps_ctx* ctx, uintptr_t other_stream) {
+  if (!ctx) return PS_ERR_INVALID;
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->wait_event) PS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->wait_event, cudaEventDisableTiming));
+  PS_CUDA(ctx, cudaEventRecord(ctx->wait_event, (cudaStream_t)other_stream));
+  PS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->wait_event, 0));
+  return PS_OK;
+}
 
 ps_status ps_solve_f32(ps_ctx* ctx, const ps_problem* p, const float* a, const float* b, ps_result* r) {
   return solve_impl<float>(ctx, p, a, b, r);

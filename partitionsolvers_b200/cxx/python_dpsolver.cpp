@@ -2,10 +2,8 @@
 // thin shell around one or more DPSolver<float> constructions, which is where the GPU work happens.
 #include "python_dpsolver.hpp"
 
-#include <atomic>
+#include <algorithm>
 #include <limits>
-#include <mutex>
-#include <thread>
 
 namespace {
 
@@ -95,56 +93,39 @@ ps_scored_partition sweep_best_OLS__DP(int n, int T, std::vector<float> a, std::
   return std::make_pair(dp.get_optimal_subsets_extern(), dp.get_optimal_score_extern());
 }
 
-// python_dpsolver.cpp:230-261: T..2 separate solves, strictly better score wins
+// python_dpsolver.cpp:230-261: the reference constructs T-1 solvers (t = T..2) and keeps the strictly best score.  The
+// levels of one T-solve are the levels of every t-solve (DPSolver::sweep_extern_scores), so ONE pass serves them all.
 ps_scored_partition sweep_best__DP(int n, int T, std::vector<float> a, std::vector<float> b, int parametric_dist,
                                    bool risk_partitioning_objective, bool use_rational_optimization, float gamma,
                                    int reg_power) {
   float best = std::numeric_limits<float>::lowest();
   ps_subsets subsets;
-  for (int t = T; t > 1; --t) {
-    auto dp = make_solver(n, t, a, b, parametric_dist, risk_partitioning_objective, use_rational_optimization,
-                          gamma, reg_power);
-    const float s = dp.get_optimal_score_extern();
-    if (s > best) {
-      best = s;
-      subsets = dp.get_optimal_subsets_extern();
+  if (T < 2) return std::make_pair(subsets, best);  // the reference's loop body never runs
+  auto dp = make_solver(n, T, a, b, parametric_dist, risk_partitioning_objective, use_rational_optimization, gamma,
+                        reg_power, true);
+  const auto all = dp.get_all_subsets_and_scores_extern();
+  const auto& ext = dp.sweep_extern_scores();
+  for (int t = static_cast<int>(all.size()) - 1; t > 1; --t) {  // t > T_ (T capped at n) repeats t = T_
+    if (ext[t] > best) {
+      best = ext[t];
+      subsets = all[t].first;
     }
   }
   return std::make_pair(subsets, best);
 }
 
-// python_dpsolver.cpp:263-316: T..1 separate solves run concurrently; slot = number of subsets returned.
-// The reference dispatches them on its process-global thread pool; here a few host threads each own an
-// engine context (the GPU executes the solves back to back).
+// python_dpsolver.cpp:263-316: the reference runs T..1 separate solves on its thread pool and files each result under the
+// number of subsets it returned.  Here: one pass to level T, T backtraces (same results, see sweep_best__DP).
 std::vector<ps_scored_partition> sweep_parallel__DP(int n, int T, std::vector<float> a, std::vector<float> b,
                                                     int parametric_dist, bool risk_partitioning_objective,
                                                     bool use_rational_optimization, float gamma, int reg_power) {
   if (parametric_dist < 0 || parametric_dist > 2) throw distributionException();
-  std::vector<ps_scored_partition> results(static_cast<size_t>(T + 1));
-  std::atomic<int> next(T);
-  std::mutex mu;
-  std::exception_ptr err;
-  auto worker = [&]() {
-    for (;;) {
-      const int t = next.fetch_sub(1);
-      if (t < 1) break;
-      try {
-        auto dp = make_solver(n, t, a, b, parametric_dist, risk_partitioning_objective, use_rational_optimization,
-                              gamma, reg_power);
-        auto res = std::make_pair(dp.get_optimal_subsets_extern(), dp.get_optimal_score_extern());
-        std::lock_guard<std::mutex> lk(mu);
-        if (res.first.size() < results.size()) results[res.first.size()] = res;
-      } catch (...) {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!err) err = std::current_exception();
-      }
-    }
-  };
-  const int nthreads = std::max(1, std::min(T, 4));
-  std::vector<std::thread> th;
-  for (int q = 1; q < nthreads; ++q) th.emplace_back(worker);
-  worker();
-  for (auto& t : th) t.join();
-  if (err) std::rethrow_exception(err);
+  std::vector<ps_scored_partition> results(static_cast<size_t>(std::max(T, 0) + 1));
+  if (T < 1) return results;
+  auto dp = make_solver(n, T, a, b, parametric_dist, risk_partitioning_objective, use_rational_optimization, gamma,
+                        reg_power, true);
+  const auto all = dp.get_all_subsets_and_scores_extern();
+  const auto& ext = dp.sweep_extern_scores();
+  for (size_t t = 1; t < all.size() && t < results.size(); ++t) results[t] = std::make_pair(all[t].first, ext[t]);
   return results;
 }

@@ -94,9 +94,20 @@ class DPSolver:
         self.risk_part = bool(risk_partitioning_objective)
         self.gamma, self.reg_power = gamma, int(reg_power)
         sweep = bool(sweep_down or find_optimal_t)
+        full_index = None
+        if n < a.shape[0]:
+            # the reference sorts the WHOLE vectors and keeps the first n sorted elements (DP_impl.hpp:10-27): stable order on
+            # the host, kept elements handed to the engine already sorted
+            with np.errstate(all="ignore"):
+                key = a / b
+            full_index = np.argsort(np.where(key == 0, dtype(0), key), kind="stable").astype(np.int32)
+            a, b = a[full_index[:n]], b[full_index[:n]]
+            perm = np.arange(n, dtype=np.int32)
         raw = self.ctx.solve_raw(a[:n], b[:n], T, int(parametric_dist), self.risk_part, dtype=dtype,
                                  sum_mode=sum_mode, perm=perm, sweep=sweep, levels=levels,
                                  chunk_len=chunk_len)
+        if full_index is not None:
+            raw["perm"] = full_index
         self.raw = raw
         self.n, self.T = n, raw["T"]
         Tc = self.T

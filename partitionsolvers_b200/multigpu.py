@@ -69,6 +69,7 @@ class CudaShardEngine:
         b_d = torch.as_tensor(np.ascontiguousarray(b, dtype), device=self.device)
         n = a_d.shape[0]
         perm_d = torch.empty(n, dtype=torch.int32, device=self.device)
+        self.ctx.wait_torch(self.device)  # the engine's stream is not ordered with torch's: a_d, b_d must have arrived
         # T=1: sort + level 1 only; we only want the sort index, so level 1 takes the closed prefix form instead of
         # walking every row (O(n^2) additions in RUNNING mode: 0.2 s at n = 1e6)
         self.ctx.solve_device(a_d.data_ptr(), b_d.data_ptr(), n, 1, 2, True, dtype, d_perm_out=perm_d.data_ptr(),
@@ -80,6 +81,7 @@ class CudaShardEngine:
         p = capi.PsProblem(n=n, T=T, dist=dist_id, risk_part=int(risk_part), sum_mode=sum_mode, sort_mode=0,
                            perm=None, sweep=0, batch=1, on_device=1, no_fast_math=0, chunk_len=0, screen=0)
         fn = self.lib.ps_shard_create_f64 if dtype == np.float64 else self.lib.ps_shard_create_f32
+        self.ctx.wait_torch(self.device)  # a_s, b_s were gathered on torch's stream
         self.ctx._check(fn(self.ctx._h, C.byref(p), C.c_void_p(a_s.data_ptr()), C.c_void_p(b_s.data_ptr()), rank,
                            world, C.byref(self._h)))
         self._keep = (a_s, b_s)
@@ -99,9 +101,11 @@ class CudaShardEngine:
         return self.torch.zeros(world * self.chunk_rows, dtype=self.tdt, device=self.device)
 
     def level1(self, chunk):
+        self.ctx.wait_torch(self.device)  # the chunk's zero fill runs on torch's stream
         self.ctx._check(self.lib.ps_shard_level1(self._h, C.c_void_p(chunk.data_ptr())))
 
     def set_prev(self, gathered):
+        self.ctx.wait_torch(self.device)  # the all-gather that filled `gathered` runs on torch's stream
         self.ctx._check(self.lib.ps_shard_set_prev(self._h, C.c_void_p(gathered.data_ptr())))
 
     def level(self, j, chunk):

@@ -63,6 +63,7 @@ def solve_scores_device(ctx, a_d, b_d, cluster_list, dtype=np.float32, dist=POIS
             hi = min(R, lo + chunk)
             Rc = hi - lo
             sc_d = torch.empty((Rc, Tmax + 1, Tmax), dtype=tdt, device=a_d.device)
+            ctx.wait_torch(a_d.device)  # the engine's own stream is not ordered with torch's: the replicas must have been drawn
             ctx.solve_device(a_d[lo:hi].data_ptr(), b_d[lo:hi].data_ptr(), n, Tmax, dist, rp, dtype, R=Rc, sweep=True,
                              d_scores=sc_d.data_ptr())
             sc = sc_d.cpu().numpy()

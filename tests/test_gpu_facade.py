@@ -62,6 +62,43 @@ def test_proto_sweeps_and_ols(proto, ctx):
     assert proto.find_optimal_score__DP(n, 3, a.tolist(), b.tolist(), 2, True, False) == sw[3][1]
 
 
+def test_one_pass_sweeps_equal_separate_solves(proto):
+    """sweep_parallel__DP / sweep_best__DP take their T results from ONE pass (DPSolver::sweep_extern_scores); the reference
+    constructs a solver per T (python_dpsolver.cpp:230-316).  Both objectives, count data with tied priorities, T > n."""
+    a, b = synth.poisson_planted(1500, 5, seed=32, dtype=np.float32)
+    for dist, rp in ((1, False), (1, True), (0, False), (2, False)):
+        par = proto.sweep_parallel__DP(1500, 7, a.tolist(), b.tolist(), dist, rp, False, 0.0, 1)
+        assert len(par) == 8 and par[0] == ((), 0.0)
+        scores = []
+        for S in range(1, 8):
+            one = proto.optimize_one__DP(1500, S, a.tolist(), b.tolist(), dist, rp, False, 0.0, 1)
+            assert par[S] == one, (dist, rp, S)
+            scores.append(one[1])
+        best = proto.sweep_best__DP(1500, 7, a.tolist(), b.tolist(), dist, rp, False, 0.0, 1)
+        want = max(range(2, 8), key=lambda S: (scores[S - 1], S))  # T..2, strictly better wins: the largest S among equals
+        assert best == (par[want][0], scores[want - 1])
+    # T capped at n (DP_impl.hpp:37-38): slots above n stay empty, like the reference's results[size()] indexing
+    a5, b5 = a[:5], b[:5]
+    par = proto.sweep_parallel__DP(5, 8, a5.tolist(), b5.tolist(), 1, True, False, 0.0, 1)
+    assert len(par) == 9 and all(len(par[S][0]) == S for S in range(1, 6)) and all(par[S] == ((), 0.0) for S in range(6, 9))
+    assert proto.sweep_best__DP(5, 1, a5.tolist(), b5.tolist(), 1, True, False, 0.0, 1)[0] == ()
+
+
+def test_n_smaller_than_the_vectors_keeps_the_lowest_priorities(proto, oracle, ctx):
+    """DPSolver(n, T, a, b) with n < a.size(): the reference sorts the whole vectors and partitions the n elements of lowest
+    priority (DP_impl.hpp:10-27).  Tie-free real-valued data: subsets and score equal the reference's exactly."""
+    if not oracle.have("ref"):
+        pytest.skip("oracle/_ref not built")
+    a, b = synth.uniform_ab(500, seed=9, dtype=np.float32)
+    for dist, rp in ((2, False), (0, True), (1, True)):
+        want_subsets, want_score = oracle.ref_solve_truncated(300, a, b, 4, dist, rp)
+        subsets, score = proto.optimize_one__DP(300, 4, a.tolist(), b.tolist(), dist, rp, False, 0.0, 1)
+        assert [list(x) for x in subsets] == want_subsets
+        assert np.float32(score) == want_score
+        s = host.DPSolver(300, 4, a, b, dist, rp, dtype=np.float32, ctx=ctx)
+        assert s.get_optimal_subsets_extern() == want_subsets and s.get_optimal_score_extern() == want_score
+
+
 def test_proto_compute_score_and_errors(proto, oracle):
     a, b = synth.uniform_ab(300, seed=2, dtype=np.float32)
     got = proto.compute_score(a.tolist(), b.tolist(), 2, False, False)

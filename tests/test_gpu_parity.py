@@ -286,8 +286,10 @@ def test_batched_sweep_prefix_mode_and_limits(oracle, ctx):
                               sum_mode=capi.PS_SUM_PREFIX)
             for S in range(1, 7):
                 assert s.all[S][1] == ref["all"][S][1]
-    with pytest.raises(capi.PsError):
-        ctx.solve_raw(np.ones((65536, 4), np.float32), np.ones((65536, 4), np.float32), 2, 2, False)
+    # more than 65535 instances (the instance index is a grid dimension) run as slices: see
+    # test_batches_above_the_grid_limit_are_sliced
+    big = ctx.solve_raw(np.ones((65536, 4), np.float32), np.ones((65536, 4), np.float32), 2, 2, False)
+    assert big["bounds"].shape == (65536, 1, 3) and np.array_equal(big["bounds"][65535], big["bounds"][0])
 
 
 def test_one_million_elements_sampled_rows(oracle, ctx):
@@ -323,3 +325,17 @@ def test_large_host_batch_is_pipelined_with_identical_results(ctx):
         part = ctx.solve_raw(a[lo:hi], b[lo:hi], T, 1, False, dtype=np.float64, levels=True, sweep=True)
         for k in ("perm", "bounds", "subset_scores", "max_score", "next_start"):
             assert np.array_equal(whole[k][lo:hi], part[k]), (k, lo)
+
+
+def test_batches_above_the_grid_limit_are_sliced(ctx):
+    """ps_problem.batch > 65535 (the instance index is a grid dimension): solved as consecutive slices, same results as
+    instance-by-instance calls -- checked on the instances around the slice boundary and at both ends."""
+    R, n, T = 65535 + 70, 12, 3
+    rs = np.random.RandomState(3)
+    a = rs.uniform(0.5, 9.5, (R, n)).astype(np.float32)
+    b = rs.uniform(0.5, 9.5, (R, n)).astype(np.float32)
+    raw = ctx.solve_raw(a, b, T, 2, False, dtype=np.float32)
+    for r in (0, 1, 65533, 65534, 65535, 65536, R - 1):
+        one = ctx.solve_raw(a[r], b[r], T, 2, False, dtype=np.float32)
+        assert np.array_equal(raw["perm"][r], one["perm"]) and np.array_equal(raw["bounds"][r], one["bounds"])
+        assert np.array_equal(raw["subset_scores"][r], one["subset_scores"]), r

@@ -51,7 +51,12 @@ __global__ void __launch_bounds__(1024) bench_kernel(float* out, float seed) {
       if (KIND == K_FADD2) p[c] = __fadd2_rn(p[c], make_float2(ad, ad));
       if (KIND == K_DADD) d[c] = __dadd_rn(d[c], dad);
       if (KIND == K_DFMA) d[c] = __fma_rn(d[c], dm, dad);
-      if (KIND == K_RCP) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
+      if (KIND == K_RCP) {
+        // rcp(rcp(x)) back to back is folded away by ptxas (round 1 reported 1.6e15/s, 350x the pipe); the add between two
+        // reciprocals (FP32 pipe, 8x the MUFU rate) keeps every MUFU.RCP in the loop
+        asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
+        x[c] = __fadd_rn(x[c], ad);
+      }
       if (KIND == K_LG2) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
       if (KIND == K_F2D) {
         asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d[c]) : "f"(x[c]));
