@@ -148,3 +148,12 @@ def test_reference_programs_run_on_the_engine(prog, args):
         assert len(rows) == 401 and all(len(l.rstrip(",").split(",")) == 21 for l in rows)
         # sizes visited: n = 20, 120, 220, 320 (T + k*NStride) and T = 5, 10, 15, 20 (solver_timer.cpp:60-64)
         assert int(rows[320].rstrip(",").split(",")[20]) > 0 and int(rows[120].rstrip(",").split(",")[5]) > 0
+        # ... and the file is what the reference's plotting script consumes (src/python/plot_times.py:83-91): read_csv
+        # without a header, the trailing-delimiter column dropped, then the visited (n, T) grid selected by label
+        import io
+        import pandas as pd
+        n_, T_, NStride, TStride = 400, 20, 100, 5
+        df = pd.read_csv(io.StringIO("\n".join(rows)), sep=",", header=None, index_col=None)
+        df = df.drop(columns=[df.columns[-1]])
+        grid = df.loc[range(T_, n_ + 1, NStride), range(TStride, T_ + 1, TStride)]
+        assert grid.shape == (4, 4) and (grid.values > 0).all()
