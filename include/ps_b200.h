@@ -185,8 +185,10 @@ ps_status ps_eval_log_f32(ps_ctx* ctx, long long n, const float* x, float* y_gen
  * dispatch of independent solves, python_dpsolver.cpp:263-316).  Rank r owns the 128-row blocks rb with rb % world == r
  * (equal rows and equal cells of the triangle per rank); per level each rank computes its rows and the library issues ONE
  * ncclAllGather of the packed {maxScore_, nextStart_} chunk on the context's stream, then scatters it to row order -- no
- * host synchronisation between levels.  Sort, scan, level T (row 0) and the backtrace are replicated, so EVERY rank
- * returns the full result (same bytes as ps_solve_* on one GPU; checked by tests/test_gpu_shard.py).  NCCL is bound at run
+ * host synchronisation between levels.  Sort, scan and the backtrace are replicated (level T, row 0 only, is rank 0's and
+ * travels like the others), so EVERY rank returns the full result (same bytes as ps_solve_* on one GPU: sort index,
+ * boundaries, subset scores, and the maxScore_ / nextStart_ tables if asked for; tests/test_gpu_shard.py).  All level
+ * kernels take part: the exact-sum and running-sum screens and the exhaustive kernel.  NCCL is bound at run
  * time (dlopen: the copy already in the process, $PS_NCCL_LIB, the system's libnccl.so.2) and only by these calls.
  *   rank 0:     ps_comm_unique_id(id)            -> send the PS_COMM_ID_BYTES to every rank by any means (MPI, a socket,
  *                                                   torch.distributed, a shared variable between threads)

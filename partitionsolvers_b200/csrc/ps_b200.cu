@@ -638,7 +638,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // (equal rows AND equal cells of the triangle).  Everything up to the level records is replicated (sort, scan: O(n));
   // a level is computed for the owned rows only, then ONE ncclAllGather on this stream moves every rank's packed
   // {value, split} chunk to all ranks and a scatter kernel puts them back in row order -- no host synchronisation between
-  // levels.  Level T (row 0 only) and the backtrace are replicated: every rank ends with the full tables.
+  // levels.  The backtrace is replicated: every rank ends with the full tables.
   const int rb_first = comm ? comm->rank : 0, rb_step = comm ? comm->world : 1;
   const int world = comm ? comm->world : 1;
   const int chunk_rows = cdiv(cdiv(n, BR), world) * BR;  // owned rows, padded: the same on every rank
@@ -773,7 +773,6 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // ---- level 1
   // float Poisson on the fast path runs the two-rows-per-thread packed kernel (256-row tiles) once there are enough
   // rows to fill the machine with such tiles; smaller instances keep 128-row tiles (more, finer work items)
-  if (comm) screen_run = screen_run32 = 0;  // sharded: exact-sum screen or the exhaustive kernel
   const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 && !comm &&
                       (long long)n * R >= 16384;
   int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
@@ -990,10 +989,16 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (timed) PS_TRY(mark(ctx, &e0));
     if (j == Tc && Tc >= 2) {
       // last level: row 0 only -> k-parallel kernel, one CTA per chunk (128-row geometry)
+      // sharded: row 0 (and its running-sum checkpoints) belongs to rank 0; its value travels like every other level's
       g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, BR);
       g.sa_mul = L / sa_L;
       g.sa_nch = sa_nch;
-      fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+      if (!comm || rb_first == 0) fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+      if (comm) {
+        const int nch = g.NCH;
+        g = make_geom(n, j, Tc, L, nch_alloc, rb_first, rb_step, BR);  // owned blocks of the one-row level: {0} on rank 0
+        g.NCH = nch;
+      }
     } else {
       if (!screened_level && (long long)g.ntiles * R >= 2048) {
         // tile -> (row block, chunk) table (one per geometry, shared by the instances of a batch), rebuilt only when the
@@ -1014,7 +1019,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
           const long long cp_stride = (long long)cp_rows * n;
           fn_lb32<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, (float4*)rin, d_SA, d_SB, cp_stride, d_lb,
                                                                (float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2);
-          fn_run32<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, cp_stride, (const int*)ctx->ipos.p, d_lb, d_pv,
+          if (g.ntiles > 0) fn_run32<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, cp_stride, (const int*)ctx->ipos.p, d_lb, d_pv,
                                                      d_pa, d_cnt, (const int*)ctx->scalar.p,
                                                      (const float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2,
                                                      (int*)ctx->tile_stamp.p, ++ctx->stamp, cdiv(n, BR));
@@ -1026,7 +1031,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
           auto fn_run = ScreenRunLaunch::pick(p.dist, rp, p.screen == 2);
           fn_lbr<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_SA, d_SB, d_lb,
                                                               (float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2);
-          fn_run<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], (const longlong2*)ctx->pfx.p,
+          if (g.ntiles > 0) fn_run<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], (const longlong2*)ctx->pfx.p,
                                                    (const ps::FxInfo*)ctx->fxinfo.p, d_SA, d_SB, d_lb, d_pv, d_pa, d_cnt,
                                                    (const int*)ctx->scalar.p, (const float*)ctx->scr_bmax.p,
                                                    n / ps::SCR_BLOCK + 2, (int*)ctx->tile_stamp.p, ++ctx->stamp,
@@ -1087,7 +1092,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
       }
     }
-    const bool sharded_level = comm && j < Tc;  // level T (row 0 only) is computed by every rank
+    const bool sharded_level = comm != nullptr;
     if (!fused_fold && g.NRB > 0) {
       const bool wide_combine = g.NCH >= 32;  // four lanes per row once a row has enough chunks to fold
       auto fn_combine = wide_combine ? ps::combine_kernel<D, BR, 4> : ps::combine_kernel<D, BR, 1>;
@@ -1096,7 +1101,8 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         PS_TRY(shard_buffers());
         fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
             g, d_pv, d_pa, (D*)nullptr, (int*)nullptr, table_stride, (ps::Rec4<D>*)nullptr, send_val, (float*)nullptr,
-            (const int*)nullptr, 0, 0, send_arg);
+            ((screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp, cdiv(n, BR),
+            send_arg);
       } else {
         fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
             g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr, pm_out,

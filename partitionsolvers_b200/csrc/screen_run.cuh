@@ -179,6 +179,10 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
     for (int q = 2; q <= 8; ++q) m = fmaxf(m, recf[i + q].w);
     recf[i + 8].z = m;
   }
+  {  // row-sharded runs: the maxima above are needed for every k, lower bounds (and checkpoints) exist for owned rows only
+    const int rbi = i / SCR_BLOCK;
+    if (rbi < g.rb_first || (rbi - g.rb_first) % g.rb_step != 0) return;
+  }
   D best = Lim<D>::lowest();
   if (SA) {
     const int c0 = i / g.L + 1, c1 = min(g.kmax / g.L, g.nch_alloc - 1);
@@ -591,6 +595,10 @@ screen_lb_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, float4* __re
 #pragma unroll
     for (int q = 2; q <= 8; ++q) m = fmaxf(m, screen_pm_of<D>(recf[i + q]));
     recf[i + 8].w = m;
+  }
+  {  // row-sharded runs: lower bounds (and checkpoints) for owned rows only
+    const int rbi = i / SCR_BLOCK;
+    if (rbi < g.rb_first || (rbi - g.rb_first) % g.rb_step != 0) return;
   }
   const int m0 = i / SCR_BLOCK + 1, m1 = g.kmax / SCR_BLOCK;  // boundaries 128 m in (i, kmax]
   D best = Lim<D>::lowest();

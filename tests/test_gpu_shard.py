@@ -77,7 +77,8 @@ def test_sharded_solver_subset_scores(ctx, kind):
 SHARD_CASES = [
     ("counts_screened", 8192, 6, 1, False),   # exact-sum screened levels (live tiles, fold -> packed chunk)
     ("counts_small", 1000, 5, 1, False),      # below the screening threshold: exhaustive kernel, prefix-free running sums
-    ("real_running", 3000, 5, 2, False),      # real-valued data: exhaustive kernel on RUNNING sums, sharded level-1 walk
+    ("real_running", 6500, 5, 2, False),      # real-valued data: RUNNING sums, sharded level-1 walk; exhaustive kernel, and
+                                              # (audited, screen = 2) the running-sum screens of screen_run.cuh
     ("counts_rp", 6500, 4, 1, True),          # Poisson risk-part: box tiers
 ]
 
@@ -94,14 +95,16 @@ def test_solve_sharded_one_rank_equals_unsharded(ctx, dt, name, n, T, dist_id, r
         a, b = synth.gaussian_mixture(n, T, seed=52, dtype=dt)
     comm = ctx.comm_create(ctx.comm_unique_id(), 0, 1)
     try:
-        for sweep in (False, True):
-            full = ctx.solve_raw(a, b, T, dist_id, rp, dtype=dt, levels=True, sweep=sweep)
+        for sweep, scr in ((False, 0), (True, 0), (False, 2)):  # screen = 2: audited screens (running-sum ones at any size)
+            full = ctx.solve_raw(a, b, T, dist_id, rp, dtype=dt, levels=True, sweep=sweep, screen=scr)
             used = ctx.timings()["screen_used"]
-            sh = ctx.solve_sharded(comm, a, b, T, dist_id, rp, dtype=dt, levels=True, sweep=sweep)
+            sh = ctx.solve_sharded(comm, a, b, T, dist_id, rp, dtype=dt, levels=True, sweep=sweep, screen=scr)
             t = ctx.timings()
-            assert t["screen_used"] == used and t["comm_bytes"] > 0
+            assert t["screen_used"] == used and t["comm_bytes"] > 0 and t["screen_violations"] == 0
+            if scr == 2 and name == "real_running":
+                assert used == 2, "the running-sum screen did not run in the sharded solve"
             for k in ("perm", "bounds", "subset_scores", "max_score", "next_start"):
-                assert np.array_equal(np.asarray(sh[k]).ravel(), np.asarray(full[k]).ravel()), (name, k, sweep)
+                assert np.array_equal(np.asarray(sh[k]).ravel(), np.asarray(full[k]).ravel()), (name, k, sweep, scr)
     finally:
         ctx.comm_destroy(comm)
 
@@ -121,3 +124,11 @@ def test_solve_sharded_two_processes():
                         "--size", "20000", "--parts", "6", "--check"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARD_CHECK_OK" in r.stdout
+    # real-valued data: running sums (level-1 walk and checkpoints for owned rows only, row 0's level T on rank 0), the
+    # exhaustive kernel and -- audited -- the running-sum screen, both precisions
+    for extra in (["--data", "real", "--dtype", "f64"], ["--data", "real", "--dtype", "f32", "--screen", "2"],
+                  ["--data", "real", "--dtype", "f64", "--screen", "2"]):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29518", os.path.join(root, "tools", "shard_check.py"),
+                            "--size", "12000", "--parts", "5", "--check"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "SHARD_CHECK_OK" in r.stdout, (extra, r.stdout[-3000:] + r.stderr[-3000:])

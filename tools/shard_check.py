@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--data", default="counts", choices=["counts", "real"])
+    ap.add_argument("--screen", type=int, default=0)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -36,18 +38,23 @@ def main():
         dist.broadcast_object_list(ids, src=0)
     comm = ctx.comm_create(ids[0], rank, world)
     dt = np.float64 if args.dtype == "f64" else np.float32
-    a, b = synth.poisson_planted(args.n, args.T, seed=synth.SEED + 5, dtype=dt)
+    if args.data == "counts":
+        a, b = synth.poisson_planted(args.n, args.T, seed=synth.SEED + 5, dtype=dt)
+        dist_id = 1
+    else:  # real-valued mixture, Rational score: sums round, the levels run on the reference's running sums
+        a, b = synth.gaussian_mixture(args.n, args.T, seed=synth.SEED + 5, dtype=dt)
+        dist_id = 2
     res, secs = None, []
     for _ in range(args.reps):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        res = ctx.solve_sharded(comm, a, b, args.T, 1, False, dtype=dt)
+        res = ctx.solve_sharded(comm, a, b, args.T, dist_id, False, dtype=dt, screen=args.screen)
         secs.append(time.perf_counter() - t0)
     tm = ctx.timings()
     ok = True
     if args.check:
-        one = ctx.solve_raw(a, b, args.T, 1, False, dtype=dt)
+        one = ctx.solve_raw(a, b, args.T, dist_id, False, dtype=dt, screen=args.screen)
         ok = all(np.array_equal(np.asarray(res[k]).ravel(), np.asarray(one[k]).ravel()) for k in ("perm", "bounds", "subset_scores"))
     print(f"rank {rank}/{world}: n={args.n} T={args.T} {args.dtype} seconds {['%.4f' % s for s in secs]} device_ms {tm['total_ms']:.2f} "
           f"levels_ms {tm['levels_ms']:.2f} sort_ms {tm['sort_scan_ms']:.2f} screen {tm['screen_used']} comm_bytes {tm['comm_bytes']} "
