@@ -24,6 +24,7 @@
 #include "radix_sort.cuh"
 #include "screen.cuh"
 #include "screen_run.cuh"
+#include "screen_select.cuh"
 
 namespace {
 
@@ -45,10 +46,9 @@ struct ps_ctx {
   ps_timings tm;
   // grow-only device workspaces
   DevBuf a_in, b_in, key_in, key_out, idx_in, perm, a_s, b_s, rec, SA, SB, part_val, part_arg, ms, ns,
-      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, tile_stamp, fxinfo, pfx, cpA, cpB, ipos,
+      bounds, scores, sort_hist, scalar, recf, lb, scr_stats, scr_counters, tile_map, scr_bmax, fxinfo, pfx, cpA, cpB, ipos,
       live, rb_info, live_hdr, kbest, rb_slots, rb_cnt,  // live-tile protocol
       shard_send, shard_recv;  // row-sharded solves: packed level chunk, gathered chunks
-  int stamp = 0;  // last stamp handed to a screened level (tile_stamp holds the stamp of the level that wrote a tile)
   int map_key[4] = {-1, -1, -1, -1};  // (NCH, G, NRB, ntiles) the tile map was built for
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
@@ -289,7 +289,7 @@ struct ScreenLaunch {
   // screened level, exactly summable inputs (screen.cuh): select kernel (range tiers -> compacted list of live tiles) and
   // the persistent live-tile kernel (group / cell tiers + the fold of a finished row block)
   using SelFn = void (*)(ps::Geom, const ps::Rec4<D>*, const D*, const float*, int, const int*, int4*, long long,
-                         unsigned int*, int, ps::LiveHdr*, unsigned long long*, const int*, int*, int*);
+                         unsigned int*, int, ps::LiveHdr*, unsigned long long*, const int*, int*, int*, ps::SelSrc);
   using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const float4*, const D*, D*, int*, unsigned long long*, const int*,
                       const int4*, long long, ps::LiveHdr*, unsigned long long*);
   using LbFn = void (*)(ps::Geom, const ps::Rec4<D>*, float4*, D*, float*, int, int*);
@@ -310,10 +310,10 @@ struct ScreenLaunch {
   static SelFn pick_select(int dist, int rp, int audit, int tpr) {
     using namespace ps;
 #define PS_PICK(DI, RPV)                                                                               \
-  return audit ? (tpr == 4 ? (SelFn)screen_select_kernel<D, DI, RPV, true, 4>                          \
-                           : (SelFn)screen_select_kernel<D, DI, RPV, true, 1>)                         \
-               : (tpr == 4 ? (SelFn)screen_select_kernel<D, DI, RPV, false, 4>                         \
-                           : (SelFn)screen_select_kernel<D, DI, RPV, false, 1>);
+  return audit ? (tpr == 4 ? (SelFn)screen_select_kernel<D, DI, RPV, true, 4, SEL_PREFIX>              \
+                           : (SelFn)screen_select_kernel<D, DI, RPV, true, 1, SEL_PREFIX>)             \
+               : (tpr == 4 ? (SelFn)screen_select_kernel<D, DI, RPV, false, 4, SEL_PREFIX>             \
+                           : (SelFn)screen_select_kernel<D, DI, RPV, false, 1, SEL_PREFIX>);
     switch (dist * 2 + (rp ? 1 : 0)) {
       case 0: PS_PICK(DIST_GAUSSIAN, false)
       case 1: PS_PICK(DIST_GAUSSIAN, true)
@@ -336,15 +336,34 @@ struct ScreenLaunch {
 };
 
 struct ScreenRunLaunch {
+  // double inputs whose sums round (screen_run.cuh): live-tile protocol with the fixed-point select kernel
   using Fn = void (*)(ps::Geom, const ps::Rec4<double>*, const float4*, const longlong2*, const ps::FxInfo*,
                       const double*, const double*, const double*, double*, int*, unsigned long long*, const int*,
-                      const float*, int, int*, int, int);
-  using LbFn = void (*)(ps::Geom, const ps::Rec4<double>*, float4*, const double*, const double*, double*, float*, int);
+                      const int4*, long long, ps::LiveHdr*);
+  using LbFn = void (*)(ps::Geom, const ps::Rec4<double>*, float4*, const double*, const double*, double*, float*, int,
+                        int*);
+  using SelFn = ScreenLaunch<double>::SelFn;
+  static SelFn pick_select(int dist, int rp, int audit, int tpr) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                                                      \
+  return audit ? (tpr == 4 ? (SelFn)screen_select_kernel<double, DI, RPV, true, 4, SEL_FIXED>                 \
+                           : (SelFn)screen_select_kernel<double, DI, RPV, true, 1, SEL_FIXED>)                \
+               : (tpr == 4 ? (SelFn)screen_select_kernel<double, DI, RPV, false, 4, SEL_FIXED>                \
+                           : (SelFn)screen_select_kernel<double, DI, RPV, false, 1, SEL_FIXED>);
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: PS_PICK(DIST_GAUSSIAN, false)
+      case 1: PS_PICK(DIST_GAUSSIAN, true)
+      case 2: PS_PICK(DIST_POISSON, false)
+      case 3: PS_PICK(DIST_POISSON, true)
+      default: PS_PICK(DIST_RATIONAL, false)
+    }
+#undef PS_PICK
+  }
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
 #define PS_PICK(DI, RPV)                                                          \
-  return audit ? (Fn)level_tile_screen_run_kernel<DI, RPV, true, BR>              \
-               : (Fn)level_tile_screen_run_kernel<DI, RPV, false, BR>;
+  return audit ? (Fn)level_live_screen_run_kernel<DI, RPV, true, BR>              \
+               : (Fn)level_live_screen_run_kernel<DI, RPV, false, BR>;
     switch (dist * 2 + (rp ? 1 : 0)) {
       case 0: PS_PICK(DIST_GAUSSIAN, false)
       case 1: PS_PICK(DIST_GAUSSIAN, true)
@@ -367,21 +386,35 @@ struct ScreenRunLaunch {
 };
 
 struct ScreenRun32Launch {
+  // float inputs whose sums round (screen_run.cuh): live-tile protocol, bounds from the running-sum checkpoints
   using Fn = void (*)(ps::Geom, const ps::Rec4<float>*, const float*, const float*, long long, const int*, const float*,
-                      float*, int*, unsigned long long*, const int*, const float*, int, int*, int, int);
+                      float*, int*, unsigned long long*, const int*, const int4*, long long, ps::LiveHdr*);
   using LbFn = void (*)(ps::Geom, const ps::Rec4<float>*, float4*, const float*, const float*, long long, float*, float*,
-                        int);
+                        int, int*);
+  using SelFn = ScreenLaunch<float>::SelFn;
   static bool supported(int dist, int rp) { return dist == PS_DIST_RATIONAL || dist == PS_DIST_GAUSSIAN; }
+  static SelFn pick_select(int dist, int rp, int audit, int tpr) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                                                      \
+  return audit ? (tpr == 4 ? (SelFn)screen_select_kernel<float, DI, RPV, true, 4, SEL_RUN32>                  \
+                           : (SelFn)screen_select_kernel<float, DI, RPV, true, 1, SEL_RUN32>)                 \
+               : (tpr == 4 ? (SelFn)screen_select_kernel<float, DI, RPV, false, 4, SEL_RUN32>                 \
+                           : (SelFn)screen_select_kernel<float, DI, RPV, false, 1, SEL_RUN32>);
+    if (dist == PS_DIST_GAUSSIAN && !rp) PS_PICK(DIST_GAUSSIAN, false)
+    if (dist == PS_DIST_GAUSSIAN && rp) PS_PICK(DIST_GAUSSIAN, true)
+    PS_PICK(DIST_RATIONAL, false)
+#undef PS_PICK
+  }
   static Fn pick(int dist, int rp, int audit) {
     using namespace ps;
     if (dist == PS_DIST_GAUSSIAN && !rp)
-      return audit ? (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, false, true, BR>
-                   : (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, false, false, BR>;
+      return audit ? (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, false, true, BR>
+                   : (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, false, false, BR>;
     if (dist == PS_DIST_GAUSSIAN && rp)
-      return audit ? (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, true, true, BR>
-                   : (Fn)level_tile_screen_run32_kernel<DIST_GAUSSIAN, true, false, BR>;
-    return audit ? (Fn)level_tile_screen_run32_kernel<DIST_RATIONAL, false, true, BR>
-                 : (Fn)level_tile_screen_run32_kernel<DIST_RATIONAL, false, false, BR>;
+      return audit ? (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, true, true, BR>
+                   : (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, true, false, BR>;
+    return audit ? (Fn)level_live_screen_run32_kernel<DIST_RATIONAL, false, true, BR>
+                 : (Fn)level_live_screen_run32_kernel<DIST_RATIONAL, false, false, BR>;
   }
   static LbFn pick_lb(int dist, int rp) {
     using namespace ps;
@@ -779,14 +812,14 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);
   // at most ~200 chunks so that the per-chunk partials stay small
   if ((screen || screen_run || screen_run32) && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
-  if (screen) {
+  if (screen || screen_run || screen_run32) {
     L = std::min(L, ps::SCR_MAX_G * BR);                   // the live-stage mask of a tile is one 32-bit word
     L = std::max(L, cdiv(cdiv(n, 1000), BR) * BR);         // <= 1000 chunks: per-chunk staging of the select kernel
   }
   const int nch_alloc = std::max(1, cdiv(std::max(1, n - 1), L));
   // live-tile kernels: partial slots per k-chunk.  One big instance: the tiles around a row block's maximum are split into
   // two work items (otherwise a single tile runs for most of a level; measured: 2 beats 1 and 4 at L = 512); batches have enough tiles to level the SMs
-  int nsub = (screen && R < 64 && p.screen != 2) ? std::min(2, L / BR) : 1;
+  int nsub = ((screen || screen_run || screen_run32) && R < 64 && p.screen != 2) ? std::min(2, L / BR) : 1;
   const long long pstride = (long long)nch_alloc * nsub * n;
   PS_TRY(ensure(ctx, ctx->part_val, R * pstride * sizeof(D)));
   PS_TRY(ensure(ctx, ctx->part_arg, R * pstride * sizeof(int)));
@@ -795,19 +828,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   D* d_SA = nullptr;
   D* d_SB = nullptr;
   float4* recf[2] = {nullptr, nullptr};
-  // sortedness flag, row lower bounds, block maxima, tile stamps and counters of the screened level kernels
+  // sortedness flag, row lower bounds, block maxima, counters and live-tile lists of the screened level kernels
   auto screen_buffers = [&]() -> ps_status {
     ps::screen_sorted_kernel<D><<<dim3(cdiv(n, 256), R), 256, 0, st>>>(n, d_as, d_bs, (int*)ctx->scalar.p + 1);
     ctx->launches++;
     PS_TRY(ensure(ctx, ctx->lb, (size_t)R * n * sizeof(D)));
     PS_TRY(ensure(ctx, ctx->scr_bmax, (size_t)R * (n / ps::SCR_BLOCK + 2) * sizeof(float)));
-    const size_t need = (size_t)R * nch_alloc * cdiv(n, BR) * sizeof(int);
-    const bool fresh = need > ctx->tile_stamp.cap;
-    PS_TRY(ensure(ctx, ctx->tile_stamp, need));
-    if (fresh || ctx->stamp > 0x7ff00000) {
-      PS_CUDA(ctx, cudaMemsetAsync(ctx->tile_stamp.p, 0, ctx->tile_stamp.cap, st));
-      ctx->stamp = 0;
-    }
     PS_TRY(ensure(ctx, ctx->scr_counters, 8 * sizeof(unsigned long long)));
     PS_CUDA(ctx, cudaMemsetAsync(ctx->scr_counters.p, 0, 8 * sizeof(unsigned long long), st));
     // live-tile protocol: the compacted tile list (every tile could be live), one segment record per row block, one header
@@ -1000,7 +1026,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         g.NCH = nch;
       }
     } else {
-      if (!screened_level && (long long)g.ntiles * R >= 2048) {
+      if (!(screened_level || screen_run || screen_run32) && (long long)g.ntiles * R >= 2048) {
         // tile -> (row block, chunk) table (one per geometry, shared by the instances of a batch), rebuilt only when the
         // geometry changes (kmax shrinks by one per level)
         if (ctx->map_key[0] != g.NCH || ctx->map_key[1] != g.G || ctx->map_key[2] != g.NRB ||
@@ -1012,51 +1038,52 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         }
         g.tile_map = (const int2*)ctx->tile_map.p;
       }
-      if (screen_run32) {
-        if constexpr (sizeof(D) == 4) {
-          auto fn_lb32 = ScreenRun32Launch::pick_lb(p.dist, rp);
-          auto fn_run32 = ScreenRun32Launch::pick(p.dist, rp, p.screen == 2);
-          const long long cp_stride = (long long)cp_rows * n;
-          fn_lb32<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, (float4*)rin, d_SA, d_SB, cp_stride, d_lb,
-                                                               (float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2);
-          if (g.ntiles > 0) fn_run32<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, cp_stride, (const int*)ctx->ipos.p, d_lb, d_pv,
-                                                     d_pa, d_cnt, (const int*)ctx->scalar.p,
-                                                     (const float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2,
-                                                     (int*)ctx->tile_stamp.p, ++ctx->stamp, cdiv(n, BR));
-          ctx->launches++;
-        }
-      } else if (screen_run) {
-        if constexpr (sizeof(D) == 8) {
-          auto fn_lbr = ScreenRunLaunch::pick_lb(p.dist, rp);
-          auto fn_run = ScreenRunLaunch::pick(p.dist, rp, p.screen == 2);
-          fn_lbr<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_SA, d_SB, d_lb,
-                                                              (float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2);
-          if (g.ntiles > 0) fn_run<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, recf[(j - 1) & 1], (const longlong2*)ctx->pfx.p,
-                                                   (const ps::FxInfo*)ctx->fxinfo.p, d_SA, d_SB, d_lb, d_pv, d_pa, d_cnt,
-                                                   (const int*)ctx->scalar.p, (const float*)ctx->scr_bmax.p,
-                                                   n / ps::SCR_BLOCK + 2, (int*)ctx->tile_stamp.p, ++ctx->stamp,
-                                                   cdiv(n, BR));
-          ctx->launches++;
-        }
-      } else if (screened_level) {
-        // row lower bounds from a few exactly evaluated cells; range tiers for every tile -> compacted list of live tiles;
-        // persistent CTAs work the list off and fold finished row blocks (no combine launch)
-        fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, (float*)ctx->scr_bmax.p,
-                                                           n / ps::SCR_BLOCK + 2, (int*)ctx->kbest.p);
+      if (screen_run32 || screen_run || screened_level) {
+        // Screened level (screen.cuh, "four launches"): row lower bounds from a few exactly evaluated cells; range tiers for
+        // every tile -> compacted, cost-ordered lists of live tiles; persistent CTAs work the lists off; fold over the slots
+        // that hold a partial (no combine launch).  The three families differ in where a bound's range sums come from.
         ps::LiveHdr* hdr = (ps::LiveHdr*)ctx->live_hdr.p + j;
         const long long live_cap = (long long)R * nch_alloc * nsub * cdiv(n, BR);
+        const int nblk = n / ps::SCR_BLOCK + 2;
+        const int audit = p.screen == 2;
         g.nsub = nsub;
+        ps::SelSrc src;
+        memset(&src, 0, sizeof(src));
+        typename ScreenLaunch<D>::SelFn fn_select = fn_sel;
+        if (screen_run32) {
+          if constexpr (sizeof(D) == 4) {
+            const long long cp_stride = (long long)cp_rows * n;
+            ScreenRun32Launch::pick_lb(p.dist, rp)<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(
+                g, rin, (float4*)rin, d_SA, d_SB, cp_stride, d_lb, (float*)ctx->scr_bmax.p, nblk, (int*)ctx->kbest.p);
+            src.cpA = d_SA;
+            src.cpB = d_SB;
+            src.cp_stride = cp_stride;
+            src.ipos = (const int*)ctx->ipos.p;
+            fn_select = ScreenRun32Launch::pick_select(p.dist, rp, audit, sel_tpr);
+          }
+        } else if (screen_run) {
+          if constexpr (sizeof(D) == 8) {
+            ScreenRunLaunch::pick_lb(p.dist, rp)<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(
+                g, rin, recf[(j - 1) & 1], d_SA, d_SB, d_lb, (float*)ctx->scr_bmax.p, nblk, (int*)ctx->kbest.p);
+            src.pfx = (const longlong2*)ctx->pfx.p;
+            src.fx = (const ps::FxInfo*)ctx->fxinfo.p;
+            fn_select = ScreenRunLaunch::pick_select(p.dist, rp, audit, sel_tpr);
+          }
+        } else {
+          fn_lb<<<dim3(cdiv(g.nrows, 128), R), 128, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, (float*)ctx->scr_bmax.p, nblk,
+                                                             (int*)ctx->kbest.p);
+        }
         if (g.NRB > 0)
-          fn_sel<<<dim3(g.NRB, R), 128 * sel_tpr, (size_t)g.NCH * (4 * sizeof(D) + 12 + nsub), st>>>(
-              g, rin, d_lb, (const float*)ctx->scr_bmax.p, n / ps::SCR_BLOCK + 2, (const int*)ctx->scalar.p,
-              (int4*)ctx->live.p, live_cap, (unsigned int*)ctx->rb_info.p, cdiv(n, BR), hdr, d_cnt,
-              (const int*)ctx->kbest.p, (int*)ctx->rb_slots.p, (int*)ctx->rb_cnt.p);
+          fn_select<<<dim3(g.NRB, R), 128 * sel_tpr, (size_t)g.NCH * (4 * 8 + 12 + nsub), st>>>(
+              g, rin, d_lb, (const float*)ctx->scr_bmax.p, nblk, (const int*)ctx->scalar.p, (int4*)ctx->live.p, live_cap,
+              (unsigned int*)ctx->rb_info.p, cdiv(n, BR), hdr, d_cnt, (const int*)ctx->kbest.p, (int*)ctx->rb_slots.p,
+              (int*)ctx->rb_cnt.p, src);
         ps::LevelOut<D> lo;
         lo.ms_row = d_ms + (long long)j * n;
         lo.ns_row = d_ns + (long long)j * n;
         lo.table_stride = table_stride;
         lo.rec_next = rout;
-        lo.pm_next = (sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr;
+        lo.pm_next = ((screen || screen_run) && sizeof(D) == 8) ? (float*)recf[j & 1] : nullptr;
         lo.shard_chunk = nullptr;
         lo.shard_arg = nullptr;
         if (comm) {  // owned rows go to the send chunk; the scatter after the all-gather writes the tables and records
@@ -1068,12 +1095,25 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
           lo.shard_chunk = send_val;
           lo.shard_arg = send_arg;
         }
-        // persistent CTAs, 8 per SM (64 registers): they pull tiles until the list is empty
+        // persistent CTAs, 8 per SM (64 registers): they pull tiles until the lists are empty
         const int grid_live = (int)std::min<long long>((long long)g.ntiles * R * nsub, (long long)ctx->sm_count * 8);
-        if (grid_live > 0)
-          fn_scr<<<grid_live, BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt, (const int*)ctx->scalar.p,
-                                           (const int4*)ctx->live.p, live_cap, hdr,
-                                           (ctx->dbg_level == j) ? (unsigned long long*)ctx->dbg.p : nullptr);
+        if (grid_live > 0) {
+          if (screen_run32) {
+            if constexpr (sizeof(D) == 4)
+              ScreenRun32Launch::pick(p.dist, rp, audit)<<<grid_live, BR, 0, st>>>(
+                  g, rin, d_SA, d_SB, (long long)cp_rows * n, (const int*)ctx->ipos.p, d_lb, d_pv, d_pa, d_cnt,
+                  (const int*)ctx->scalar.p, (const int4*)ctx->live.p, live_cap, hdr);
+          } else if (screen_run) {
+            if constexpr (sizeof(D) == 8)
+              ScreenRunLaunch::pick(p.dist, rp, audit)<<<grid_live, BR, 0, st>>>(
+                  g, rin, recf[(j - 1) & 1], (const longlong2*)ctx->pfx.p, (const ps::FxInfo*)ctx->fxinfo.p, d_SA, d_SB, d_lb,
+                  d_pv, d_pa, d_cnt, (const int*)ctx->scalar.p, (const int4*)ctx->live.p, live_cap, hdr);
+          } else {
+            fn_scr<<<grid_live, BR, 0, st>>>(g, rin, recf[(j - 1) & 1], d_lb, d_pv, d_pa, d_cnt, (const int*)ctx->scalar.p,
+                                             (const int4*)ctx->live.p, live_cap, hdr,
+                                             (ctx->dbg_level == j) ? (unsigned long long*)ctx->dbg.p : nullptr);
+          }
+        }
         if (g.NRB > 0) {
           if (g.NCH >= 32)  // four lanes per row once a row has enough chunks to fold
             ps::screen_fold_kernel<D, BR, 4><<<dim3(g.NRB, R), BR * 4, 0, st>>>(
@@ -1084,7 +1124,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         }
         ctx->launches += 3;
         fused_fold = true;
-        if (cnt_pin) {  // cumulative count of exactly evaluated warp-cells after this level -> pinned host slot
+        if (cnt_pin && screened_level) {  // cumulative count of exactly evaluated warp-cells after this level -> pinned host slot
           PS_CUDA(ctx, cudaMemcpyAsync(&cnt_pin[j], d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
           PS_TRY(mark(ctx, &cnt_ev[j]));
         }
@@ -1101,13 +1141,11 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         PS_TRY(shard_buffers());
         fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
             g, d_pv, d_pa, (D*)nullptr, (int*)nullptr, table_stride, (ps::Rec4<D>*)nullptr, send_val, (float*)nullptr,
-            ((screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp, cdiv(n, BR),
-            send_arg);
+            (const int*)nullptr, 0, 0, send_arg);
       } else {
         fn_combine<<<dim3(cdiv((wide_combine ? 4LL : 1LL) * g.NRB * tile_rows, 256), R), 256, 0, st>>>(
             g, d_pv, d_pa, d_ms + (long long)j * n, d_ns + (long long)j * n, table_stride, rout, nullptr, pm_out,
-            ((screen_run || screen_run32) && j < Tc) ? (const int*)ctx->tile_stamp.p : nullptr, ctx->stamp,
-            cdiv(n, BR), (int*)nullptr);
+            (const int*)nullptr, 0, 0, (int*)nullptr);
       }
       ctx->launches++;
     }
@@ -1475,7 +1513,7 @@ ps_status shard_level_impl(ps_shard* s, int j, D* my_chunk) {
     const long long live_cap = (long long)s->nch_alloc * (s->owned_blocks + 1);
     fn_sel<<<dim3(g.NRB, 1), 128 * sel_tpr, (size_t)g.NCH * (4 * sizeof(D) + 12 + 1), st>>>(
         g, rin, (const D*)s->lb, s->bmax, n / ps::SCR_BLOCK + 2, s->dflags, s->live, live_cap, s->rb_info, cdiv(n, BR),
-        s->live_hdr + j, s->counters, s->kbest, s->rb_slots, s->rb_cnt);
+        s->live_hdr + j, s->counters, s->kbest, s->rb_slots, s->rb_cnt, ps::SelSrc{});
     ps::LevelOut<D> lo;
     lo.ms_row = nullptr;
     lo.ns_row = s->ns + (long long)j * n;
@@ -1582,7 +1620,7 @@ void ps_destroy(ps_ctx* ctx) {
                     &ctx->a_s,   &ctx->b_s,      &ctx->rec,      &ctx->SA,      &ctx->SB,     &ctx->part_val,
                     &ctx->part_arg, &ctx->ms,    &ctx->ns,       &ctx->bounds,  &ctx->scores, &ctx->sort_hist,
                     &ctx->scalar, &ctx->recf,    &ctx->lb,       &ctx->scr_stats, &ctx->scr_counters, &ctx->tile_map,
-                    &ctx->scr_bmax, &ctx->tile_stamp, &ctx->fxinfo, &ctx->pfx, &ctx->cpA, &ctx->cpB, &ctx->ipos,
+                    &ctx->scr_bmax, &ctx->fxinfo, &ctx->pfx, &ctx->cpA, &ctx->cpB, &ctx->ipos,
                     &ctx->live, &ctx->rb_info, &ctx->live_hdr, &ctx->kbest, &ctx->rb_slots, &ctx->rb_cnt,
                     &ctx->shard_send, &ctx->shard_recv};
   for (DevBuf* b : bufs)

@@ -159,7 +159,7 @@ template <int DIST, bool RP>
 __global__ void __launch_bounds__(128)
 screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __restrict__ recf,
                      const double* __restrict__ SA, const double* __restrict__ SB, double* __restrict__ LB,
-                     float* __restrict__ bmax, int nblk) {
+                     float* __restrict__ bmax, int nblk, int* __restrict__ kbest = nullptr) {
   using D = double;
   const int inst = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,9 +184,10 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
     if (rbi < g.rb_first || (rbi - g.rb_first) % g.rb_step != 0) return;
   }
   D best = Lim<D>::lowest();
+  int cb = i / g.L;  // chunk of the best sample (the row's own chunk if no boundary lies right of it): the cost hint
   if (SA) {
     const int c0 = i / g.L + 1, c1 = min(g.kmax / g.L, g.nch_alloc - 1);
-    int cb = c0;
+    cb = c0;
     auto probe = [&](const int c) {
       const D A = SA[inst * pstride + (long long)c * g.n + i];
       const D B = SB[inst * pstride + (long long)c * g.n + i];
@@ -207,316 +208,8 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
     }
   }
   LB[(long long)inst * g.n + i] = best;
+  if (kbest) kbest[(long long)inst * g.n + i] = max(1, min(cb * g.L, g.kmax));
 }
-
-// One (row block, k-chunk) tile of one level, screened, RUNNING sums.  Same tiling, tiers, partial/combine protocol and
-// counters as level_tile_screen_kernel.
-template <int DIST, bool RP, bool AUDIT, int BR>
-__global__ void __launch_bounds__(BR, 8)
-level_tile_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const float4* __restrict__ recf,
-                             const longlong2* __restrict__ pfx, const FxInfo* __restrict__ fx,
-                             const double* __restrict__ SA, const double* __restrict__ SB,
-                             const double* __restrict__ LB, double* __restrict__ part_val,
-                             int* __restrict__ part_arg, unsigned long long* __restrict__ counters,
-                             const int* __restrict__ dev_flags, const float* __restrict__ bmax, int nblk,
-                             int* __restrict__ tile_stamp, int stamp, int stamp_stride) {
-  using D = double;
-  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
-  constexpr int BK = BR;
-  constexpr int U = 8;
-  constexpr int GQ = AUDIT ? 1 : 4;  // groups whose bounds are formed together
-  constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
-  constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
-  constexpr bool BOX = !GROUPB;  // Poisson risk-part: range tiers from the box bound, no sortedness needed
-  __shared__ float4 sbuf[2][BK];
-  __shared__ float s_pmax[2][BR / 32];
-  constexpr bool kLogTab = (DIST == DIST_POISSON);
-  __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
-  if (kLogTab) {
-    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
-  }
-
-  const int inst = blockIdx.y;
-  rec += (long long)inst * g.rec_stride;
-  recf += (long long)inst * g.rec_stride;
-  pfx += (long long)inst * g.rec_stride;
-  LB += (long long)inst * g.n;
-  const long long pstride = (long long)g.nch_alloc * g.n;
-  part_val += inst * pstride;
-  part_arg += inst * pstride;
-  const FxInfo F = fx[inst];
-
-  int rb, c;
-  decode_tile(g, blockIdx.x, rb, c);
-  const int tid = threadIdx.x;
-  const int i0 = rb * BR;
-  const int i = i0 + tid;
-  const int k_lo = max(c * g.L + 1, i0 + 1);
-  const int k_hi = min((c + 1) * g.L, g.kmax);
-  const bool diag_tile = (c == rb / g.G);
-
-  const int il = min(i, g.n - 1);
-  const longlong2 Pi = pfx[il];
-  float bx = 0.f, by = 0.f;
-  D best = Lim<D>::lowest();
-  int arg = -1;
-  float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
-  unsigned int nexact = 0, nviol = 0;
-  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
-
-  // the reference's running sums of row i through cell kw (warp-uniform kw); a tile right of the diagonal starts from the
-  // checkpoint the level-1 pass left at its chunk boundary (loaded on first use)
-  D Ar = 0, Br = 0;
-  int kw = diag_tile ? i0 : c * g.L;
-  bool loaded = diag_tile;
-  auto advance_to = [&](const int k) {
-    if (!loaded) {
-      Ar = SA[inst * pstride + (long long)c * g.n + il];
-      Br = SB[inst * pstride + (long long)c * g.n + il];
-      loaded = true;
-    }
-    int q = kw + 1;
-    if (q <= i0 + BR - 1) {  // diagonal stage: row i starts at k = i + 1
-      const int qe = min(k, i0 + BR - 1);
-      for (; q <= qe; ++q) {
-        const double2 ab = *reinterpret_cast<const double2*>(&rec[q]);
-        if (q > i) {
-          Ar = add_rn<D>(Ar, ab.x);
-          Br = add_rn<D>(Br, ab.y);
-        }
-      }
-    }
-#pragma unroll 4
-    for (; q <= k; ++q) {
-      const double2 ab = *reinterpret_cast<const double2*>(&rec[q]);
-      Ar = add_rn<D>(Ar, ab.x);
-      Br = add_rn<D>(Br, ab.y);
-    }
-    kw = max(kw, k);
-  };
-  // calls are warp-uniform and ascending in k
-  auto exact_at = [&](const int k) -> D {
-    advance_to(k);
-    return add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(Ar, Br, s_log), rec[k].p);
-  };
-  auto audit_dropped = [&](const int k, const bool valid) {
-    const D v = exact_at(k);
-    if (valid && !(v < (double)thr)) ++nviol;
-  };
-  auto fsum = [&](const longlong2 P, float& A, float& B) {
-    A = __ll2float_rn(P.x - Pi.x) * F.sca;
-    B = __ll2float_rn(P.y - Pi.y) * F.scb;
-  };
-  auto cell = [&](const int k, const float4 r, const bool valid, auto from_fixed) {
-    float A, B;
-    if constexpr (decltype(from_fixed)::value) {
-      fsum(pfx[k], A, B);
-    } else {
-      A = __fadd_rn(r.x, bx);
-      B = __fadd_rn(r.y, by);
-    }
-    const float ub = ScreenUB<DIST, RP>::eval(A, B, r.w);
-    const bool pass = valid && !(ub < thr);
-    if (__any_sync(0xffffffffu, pass)) {
-      const D v = exact_at(k);
-      if (AUDIT && valid && (double)ub < v) ++nviol;
-      ++nexact;
-      if (valid && v > best) {
-        best = v;
-        arg = k;
-        thr = fmaxf(thr, screen_rd<D>(best));
-      }
-    } else if (AUDIT) {
-      audit_dropped(k, valid);
-    }
-  };
-  using T_ = std::integral_constant<bool, true>;
-  using F_ = std::integral_constant<bool, false>;
-  auto stage_max = [&](const float4 r, const int buf) {
-    float w = ((tid & 7) == 7) ? r.z : -3.402823466e+38f;
-    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 8));
-    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 16));
-    if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
-  };
-  auto finish = [&]() {
-    if (i < g.nrows) {
-      part_val[(long long)c * g.n + i] = best;
-      part_arg[(long long)c * g.n + i] = arg;
-    }
-    if (tile_stamp && tid == 0) tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + rb] = stamp;
-    if (counters) {
-      if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
-      if (AUDIT) {
-        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
-        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
-      }
-    }
-  };
-
-  if (i0 < F.ipos) {
-    // (F4) a row of this block may own non-positive range sums: no bounds, every cell with the reference's arithmetic
-    for (int k = k_lo; k <= k_hi; ++k) {
-      const D v = exact_at(k);
-      ++nexact;
-      if (k > i && v > best) {
-        best = v;
-        arg = k;
-      }
-    }
-    finish();
-    return;
-  }
-
-  if (mono) {
-    bmax += (long long)inst * nblk;
-    float tmax = -3.402823466e+38f;
-    for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
-    float At, Bt;
-    fsum(pfx[k_hi], At, Bt);
-    float Af = At, Bf = Bt;
-    const int kf = max(k_lo, i + 1);  // the row's first cell in this tile
-    if (BOX) fsum(pfx[min(kf, k_hi)], Af, Bf);
-    const bool lose = (i >= g.nrows) || (kf > k_hi) || (screen_range_ub<DIST, RP>(Af, Bf, At, Bt, tmax) < thr);
-    const bool tile_dropped = __syncthreads_and(lose);
-    if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
-    if (tile_dropped) {
-      if (AUDIT)
-        for (int k = k_lo; k <= k_hi; ++k) audit_dropped(k, k > i && i < g.nrows);
-      if (!tile_stamp && i < g.nrows) {
-        part_val[(long long)c * g.n + i] = best;
-        part_arg[(long long)c * g.n + i] = arg;
-      }
-      if (AUDIT && counters) {
-        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
-        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
-      }
-      return;
-    }
-  }
-  const int nk = k_hi - k_lo + 1;
-  const int nstages = (nk + BK - 1) / BK;
-  longlong2 onx;  // fixed-point prefix at the origin of the next stage (k = kb - 1)
-  {
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
-    sbuf[0][tid] = r;
-    stage_max(r, 0);
-    onx = pfx[k_lo - 1];
-  }
-  for (int s = 0; s < nstages; ++s) {
-    __syncthreads();
-    const int kb = k_lo + s * BK;
-    const int kn = kb + BK + tid;
-    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool has_next = (s + 1 < nstages);
-    if (has_next && kn <= k_hi) nx = recf[kn];
-    fsum(onx, bx, by);  // >= 0 on every stage right of the diagonal
-    if (has_next) onx = pfx[kb + BK - 1];
-    const int cnt = min(BK, k_hi - kb + 1);
-    const float4* __restrict__ sb = sbuf[s & 1];
-    if (kb <= i0 + BR - 1) {
-      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
-    } else if (cnt < BK) {
-      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
-    } else {
-      bool skip = false;
-      if (mono) {
-        float pmx = s_pmax[s & 1][0];
-#pragma unroll
-        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
-        const float4 re = sb[BK - 1], rf = sb[0];
-        const float ubs = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
-                                                    __fadd_rn(re.y, by), pmx);
-        skip = !__any_sync(0xffffffffu, !(ubs < thr));
-      }
-      if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
-      if (skip) {
-        if (AUDIT)
-          for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true);
-      } else {
-#pragma unroll 1
-        for (int kq = 0; kq < BK; kq += GQ * U) {
-          // group tier, GQ groups at a time (independent bound chains); audit runs keep ascending k: one group at a time
-          unsigned int keepm = (1u << GQ) - 1u;
-          if (mono) {
-            float ubg[GQ];
-#pragma unroll
-            for (int q = 0; q < GQ; ++q) {
-              const float4 re = sb[kq + q * U + U - 1], rf = sb[kq + q * U];
-              ubg[q] = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
-                                                 __fadd_rn(re.y, by), re.z);
-            }
-            keepm = 0;
-#pragma unroll
-            for (int q = 0; q < GQ; ++q)
-              if (__any_sync(0xffffffffu, !(ubg[q] < thr))) keepm |= 1u << q;
-            if (AUDIT) {  // GQ == 1
-              const bool gdrop = !(keepm & 1u);
-              if (counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
-              if (gdrop)
-                for (int u = 0; u < U; ++u) audit_dropped(kb + kq + u, true);
-            }
-            if (!keepm) continue;
-          }
-#pragma unroll 1
-          for (int q = 0; q < GQ; ++q) {
-          if (!((keepm >> q) & 1u)) continue;
-          const int kk = kq + q * U;
-          float A[U], B[U], W[U];
-          bool gt = false;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const float4 r = sb[kk + u];
-            A[u] = __fadd_rn(r.x, bx);
-            B[u] = __fadd_rn(r.y, by);
-            W[u] = r.w;
-            if (FRONTIER) gt |= A[u] > B[u];
-          }
-          bool alive = false;
-          if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) alive |= !(fmaf(B[u], SCR_TINY, W[u]) < thr);
-          } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u) alive |= !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
-          }
-          if (AUDIT) {
-#pragma unroll 1
-            for (int u = 0; u < U; ++u) cell(kb + kk + u, sb[kk + u], true, F_{});
-          } else if (__any_sync(0xffffffffu, alive)) {
-            // a survivor: walk to the group, then its U cells -- the sums are sequential (2 DADD per cell), the score
-            // evaluations that hang off them are independent chains
-            advance_to(kb + kk - 1);
-            D v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const Rec4<D> R = rec[kb + kk + u];
-              Ar = add_rn<D>(Ar, R.x);
-              Br = add_rn<D>(Br, R.y);
-              v[u] = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(Ar, Br, s_log), R.p);
-            }
-            kw = kb + kk + U - 1;
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-              if (v[u] > best) {
-                best = v[u];
-                arg = kb + kk + u;
-              }
-            thr = fmaxf(thr, screen_rd<D>(best));
-            nexact += U;
-          }
-          }
-        }
-      }
-    }
-    if (has_next) {
-      sbuf[(s + 1) & 1][tid] = nx;
-      stage_max(nx, (s + 1) & 1);
-    }
-  }
-  finish();
-}
-
 
 // =====================================================================================================================
 // FLOAT inputs whose sums round.  The reference's float running sums carry up to m u of rounding after m terms, so no
@@ -575,7 +268,7 @@ template <int DIST, bool RP>
 __global__ void __launch_bounds__(128)
 screen_lb_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, float4* __restrict__ recf,
                        const float* __restrict__ SA, const float* __restrict__ SB, long long cp_stride,
-                       float* __restrict__ LB, float* __restrict__ bmax, int nblk) {
+                       float* __restrict__ LB, float* __restrict__ bmax, int nblk, int* __restrict__ kbest = nullptr) {
   using D = float;
   const int inst = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -622,51 +315,360 @@ screen_lb_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, float4* __re
     }
   }
   LB[(long long)inst * g.n + i] = best;
+  if (kbest) kbest[(long long)inst * g.n + i] = max(1, min(mb * SCR_BLOCK, g.kmax));
 }
 
+// =====================================================================================================================
+// Live-tile protocol (screen.cuh, "Screened level = four launches") for the running-sum screens: the range tiers have run in
+// screen_select_kernel<.., SEL_FIXED / SEL_RUN32>; persistent CTAs pull live tiles from the cost-ordered lists and run the
+// group and cell tiers on the live stages; screen_fold_kernel folds the partial slots.
+// =====================================================================================================================
+// One live tile, double data whose sums round: bounds from the fixed-point prefix sums, survivors from the reference's running
+// sums (lazy warp-uniform walk from the chunk-boundary checkpoint SA/SB, which also passes through stages that are not live).
 template <int DIST, bool RP, bool AUDIT, int BR>
-__global__ void __launch_bounds__(BR)
-level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, const float* __restrict__ SA,
-                               const float* __restrict__ SB, long long cp_stride, const int* __restrict__ ipos,
-                               const float* __restrict__ LB, float* __restrict__ part_val, int* __restrict__ part_arg,
-                               unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
-                               const float* __restrict__ bmax, int nblk, int* __restrict__ tile_stamp, int stamp,
-                               int stamp_stride) {
-  using D = float;
-  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
-  static_assert(DIST == DIST_RATIONAL || DIST == DIST_GAUSSIAN, "A^2/B family and Gaussian mult-clust");
+__device__ __forceinline__ void screen_run_live_tile(const Geom& g, const int rb, const int slot,
+                                                     const unsigned int stage_mask, const Rec4<double>* __restrict__ rec,
+                                                     const float4* __restrict__ recf, const longlong2* __restrict__ pfx,
+                                                     const FxInfo& F, const double* __restrict__ SA,
+                                                     const double* __restrict__ SB, const double* __restrict__ LB,
+                                                     double* __restrict__ part_val, int* __restrict__ part_arg,
+                                                     unsigned long long* __restrict__ counters, const bool mono_in,
+                                                     float4 (*sbuf)[BR], float (*s_pmax)[BR / 32],
+                                                     const GlogEntry* __restrict__ s_log) {
+  using D = double;
   constexpr int BK = BR;
   constexpr int U = 8;
-  __shared__ float4 sbuf[2][BK];
-  __shared__ float s_pmax[2][BR / 32];
-
-  const int inst = blockIdx.y;
-  rec += (long long)inst * g.rec_stride;
-  LB += (long long)inst * g.n;
-  SA += inst * cp_stride;
-  SB += inst * cp_stride;
-  const long long pstride = (long long)g.nch_alloc * g.n;
-  part_val += inst * pstride;
-  part_arg += inst * pstride;
-  const float4* __restrict__ recf = reinterpret_cast<const float4*>(rec);
-
-  int rb, c;
-  decode_tile(g, blockIdx.x, rb, c);
+  constexpr int GQ = AUDIT ? 1 : 4;  // groups whose bounds are formed together (audit runs keep ascending k for the walk)
+  constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
+  constexpr bool kLogTab = (DIST == DIST_POISSON);
   const int tid = threadIdx.x;
   const int i0 = rb * BR;
   const int i = i0 + tid;
+  const int c = slot / g.nsub;
   const int k_lo = max(c * g.L + 1, i0 + 1);
   const int k_hi = min((c + 1) * g.L, g.kmax);
   const bool diag_tile = (c == rb / g.G);
   const int il = min(i, g.n - 1);
-
+  const longlong2 Pi = pfx[il];
+  float bx = 0.f, by = 0.f;
   D best = Lim<D>::lowest();
   int arg = -1;
-  float thr = LB[min(il, max(g.nrows - 1, 0))];
+  const float thr0 = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);  // the threshold the select kernel dropped with
+  float thr = thr0;
   unsigned int nexact = 0, nviol = 0;
-  const bool mono = dev_flags && (dev_flags[1] == 0);
-  // running sums through cell kb - 1 at the top of every stage
-  float2 S = make_float2(0.f, 0.f);
+  const bool forced = i0 < F.ipos;  // (F4) a row of this block may own non-positive sums: no bounds, every cell exactly
+  const bool mono = mono_in && !forced;
+
+  // the reference's running sums of row i through cell kw (warp-uniform kw); a tile right of the diagonal starts from the
+  // checkpoint the level-1 pass left at its chunk boundary (loaded on first use)
+  D Ar = 0, Br = 0;
+  int kw = diag_tile ? i0 : c * g.L;
+  bool loaded = diag_tile;
+  auto advance_to = [&](const int k) {
+    if (!loaded) {
+      Ar = SA[(long long)c * g.n + il];
+      Br = SB[(long long)c * g.n + il];
+      loaded = true;
+    }
+    int q = kw + 1;
+    if (q <= i0 + BR - 1) {  // diagonal stage: row i starts at k = i + 1
+      const int qe = min(k, i0 + BR - 1);
+      for (; q <= qe; ++q) {
+        const double2 ab = *reinterpret_cast<const double2*>(&rec[q]);
+        if (q > i) {
+          Ar = add_rn<D>(Ar, ab.x);
+          Br = add_rn<D>(Br, ab.y);
+        }
+      }
+    }
+#pragma unroll 4
+    for (; q <= k; ++q) {
+      const double2 ab = *reinterpret_cast<const double2*>(&rec[q]);
+      Ar = add_rn<D>(Ar, ab.x);
+      Br = add_rn<D>(Br, ab.y);
+    }
+    kw = max(kw, k);
+  };
+  // calls are warp-uniform and ascending in k
+  auto exact_at = [&](const int k) -> D {
+    advance_to(k);
+    return add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(Ar, Br, s_log), rec[k].p);
+  };
+  auto audit_dropped = [&](const int k, const bool valid, const float t) {
+    const D v = exact_at(k);
+    if (valid && !(v < (double)t)) ++nviol;
+  };
+  auto fsum = [&](const longlong2 P, float& A, float& B) {
+    A = __ll2float_rn(P.x - Pi.x) * F.sca;
+    B = __ll2float_rn(P.y - Pi.y) * F.scb;
+  };
+  auto cell = [&](const int k, const float4 r, const bool valid, auto from_fixed) {
+    float A, B;
+    if constexpr (decltype(from_fixed)::value) {
+      fsum(pfx[k], A, B);
+    } else {
+      A = __fadd_rn(r.x, bx);
+      B = __fadd_rn(r.y, by);
+    }
+    const float ub = ScreenUB<DIST, RP>::eval(A, B, r.w);
+    const bool pass = valid && (forced || !(ub < thr));
+    if (__any_sync(0xffffffffu, pass)) {
+      const D v = exact_at(k);
+      if (AUDIT && valid && !forced && (double)ub < v) ++nviol;
+      ++nexact;
+      if (valid && v > best) {
+        best = v;
+        arg = k;
+        thr = fmaxf(thr, screen_rd<D>(best));
+      }
+    } else if (AUDIT) {
+      audit_dropped(k, valid, thr);
+    }
+  };
+  using T_ = std::integral_constant<bool, true>;
+  using F_ = std::integral_constant<bool, false>;
+  auto stage_max = [&](const float4 r, const int buf) {
+    float w = ((tid & 7) == 7) ? r.z : -3.402823466e+38f;
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 8));
+    w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 16));
+    if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
+  };
+
+  const int nk = k_hi - k_lo + 1;
+  const int nstages = (nk + BK - 1) / BK;
+  if (AUDIT && counters && tid == 0) atomicAdd(&counters[stage_mask ? 2 : 3], 1ULL);
+  unsigned int todo = AUDIT ? (nstages >= 32 ? 0xffffffffu : ((1u << nstages) - 1u)) : stage_mask;
+  int s = todo ? (__ffs(todo) - 1) : -1;
+  longlong2 onx = make_longlong2(0, 0);  // fixed-point prefix at the origin of the staged stage (k = kb - 1)
+  if (s >= 0) {
+    const int kb = k_lo + s * BK;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kb + tid <= k_hi) r = recf[kb + tid];
+    sbuf[0][tid] = r;
+    stage_max(r, 0);
+    onx = pfx[kb - 1];
+  }
+  int buf = 0;
+  while (s >= 0) {
+    __syncthreads();
+    todo &= todo - 1u;
+    const int sn = todo ? (__ffs(todo) - 1) : -1;
+    const int kb = k_lo + s * BK;
+    float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sn >= 0 && k_lo + sn * BK + tid <= k_hi) nx = recf[k_lo + sn * BK + tid];
+    fsum(onx, bx, by);  // >= 0 on every stage right of the diagonal
+    if (sn >= 0) onx = pfx[k_lo + sn * BK - 1];
+    const int cnt = min(BK, k_hi - kb + 1);
+    const float4* __restrict__ sb = sbuf[buf];
+    const bool sel_dropped = AUDIT && !((stage_mask >> s) & 1u);
+    if (sel_dropped) {
+      if (counters && (tid & 31) == 0) atomicAdd(&counters[5], 1ULL);
+      for (int kk = 0; kk < cnt; ++kk) audit_dropped(kb + kk, (kb + kk > i) && (i < g.nrows), thr0);
+    } else if (forced) {
+      for (int kk = 0; kk < cnt; ++kk) {
+        const D v = exact_at(kb + kk);
+        ++nexact;
+        if (kb + kk > i && v > best) {
+          best = v;
+          arg = kb + kk;
+        }
+      }
+    } else if (kb <= i0 + BR - 1) {
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, T_{});
+    } else if (cnt < BK) {
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], true, F_{});
+    } else {
+      bool skip = false;
+      if (mono) {
+        float pmx = s_pmax[buf][0];
+#pragma unroll
+        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[buf][w]);
+        const float4 re = sb[BK - 1], rf = sb[0];
+        const float ubs = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                    __fadd_rn(re.y, by), pmx);
+        skip = !__any_sync(0xffffffffu, !(ubs < thr));
+      }
+      if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
+      if (skip) {
+        if (AUDIT)
+          for (int kk = 0; kk < BK; ++kk) audit_dropped(kb + kk, true, thr);
+      } else {
+#pragma unroll 1
+        for (int kq = 0; kq < BK; kq += GQ * U) {
+          unsigned int keepm = (1u << GQ) - 1u;
+          if (mono) {
+            float ubg[GQ];
+#pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+              const float4 re = sb[kq + q * U + U - 1], rf = sb[kq + q * U];
+              ubg[q] = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
+                                                 __fadd_rn(re.y, by), re.z);
+            }
+            keepm = 0;
+#pragma unroll
+            for (int q = 0; q < GQ; ++q)
+              if (__any_sync(0xffffffffu, !(ubg[q] < thr))) keepm |= 1u << q;
+            if (AUDIT) {  // GQ == 1
+              const bool gdrop = !(keepm & 1u);
+              if (counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
+              if (gdrop)
+                for (int u = 0; u < U; ++u) audit_dropped(kb + kq + u, true, thr);
+            }
+            if (!keepm) continue;
+          }
+#pragma unroll 1
+          for (int q = 0; q < GQ; ++q) {
+            if (!((keepm >> q) & 1u)) continue;
+            const int kk = kq + q * U;
+            float A[U], B[U], W[U];
+            bool gt = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const float4 r = sb[kk + u];
+              A[u] = __fadd_rn(r.x, bx);
+              B[u] = __fadd_rn(r.y, by);
+              W[u] = r.w;
+              if (FRONTIER) gt |= A[u] > B[u];
+            }
+            bool alive = false;
+            if (FRONTIER && !__any_sync(0xffffffffu, gt)) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) alive |= !(fmaf(B[u], SCR_TINY, W[u]) < thr);
+            } else {
+#pragma unroll
+              for (int u = 0; u < U; ++u) alive |= !(ScreenUB<DIST, RP>::eval(A[u], B[u], W[u]) < thr);
+            }
+            if (AUDIT) {
+#pragma unroll 1
+              for (int u = 0; u < U; ++u) cell(kb + kk + u, sb[kk + u], true, F_{});
+            } else if (__any_sync(0xffffffffu, alive)) {
+              // a survivor: walk to the group, then its U cells -- the sums are sequential (2 DADD per cell), the score
+              // evaluations that hang off them are independent chains
+              advance_to(kb + kk - 1);
+              D v[U];
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const Rec4<D> R = rec[kb + kk + u];
+                Ar = add_rn<D>(Ar, R.x);
+                Br = add_rn<D>(Br, R.y);
+                v[u] = add_rn<D>(screen_exact_score<D, DIST, RP, kLogTab>(Ar, Br, s_log), R.p);
+              }
+              kw = kb + kk + U - 1;
+#pragma unroll
+              for (int u = 0; u < U; ++u)
+                if (v[u] > best) {
+                  best = v[u];
+                  arg = kb + kk + u;
+                }
+              thr = fmaxf(thr, screen_rd<D>(best));
+              nexact += U;
+            }
+          }
+        }
+      }
+    }
+    if (sn >= 0) {
+      sbuf[buf ^ 1][tid] = nx;
+      stage_max(nx, buf ^ 1);
+    }
+    buf ^= 1;
+    s = sn;
+  }
+  if (i < g.nrows) {
+    part_val[(long long)slot * g.n + i] = best;
+    part_arg[(long long)slot * g.n + i] = arg;
+  }
+  if (counters) {
+    if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
+    if (AUDIT) {
+      for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+      if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+    }
+  }
+}
+
+template <int DIST, bool RP, bool AUDIT, int BR>
+__global__ void __launch_bounds__(BR, 8)
+level_live_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const float4* __restrict__ recf,
+                             const longlong2* __restrict__ pfx, const FxInfo* __restrict__ fx,
+                             const double* __restrict__ SA, const double* __restrict__ SB,
+                             const double* __restrict__ LB, double* __restrict__ part_val, int* __restrict__ part_arg,
+                             unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
+                             const int4* __restrict__ live, long long live_cap, LiveHdr* __restrict__ hdr) {
+  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
+  constexpr bool FRONTIER = !RP && DIST != DIST_RATIONAL;
+  constexpr bool GROUPB = !(DIST == DIST_POISSON && RP);
+  constexpr bool BOX = !GROUPB;
+  __shared__ float4 sbuf[2][BR];
+  __shared__ float s_pmax[2][BR / 32];
+  constexpr bool kLogTab = (DIST == DIST_POISSON);
+  __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
+  __shared__ int s_next;
+  if (kLogTab) {
+    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
+  }
+  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
+  const long long pstride = (long long)g.nch_alloc * g.nsub * g.n;  // partial slots
+  const long long sstride = (long long)g.nch_alloc * g.n;           // SA / SB checkpoints
+  const int tid = threadIdx.x;
+  int cum[SCR_CLASSES];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int q = 0; q < SCR_CLASSES; ++q) {
+      acc += hdr->nlive[q];
+      cum[q] = acc;
+    }
+  }
+  const int nlive = cum[SCR_CLASSES - 1];
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_next = atomicAdd(&hdr->cursor, 1);
+    __syncthreads();
+    const int t = s_next;
+    if (t >= nlive) break;
+    int cls = 0;
+#pragma unroll
+    for (int q = 0; q < SCR_CLASSES - 1; ++q) cls += (t >= cum[q]) ? 1 : 0;
+    const int4 e = live[(long long)cls * live_cap + (t - (cls ? cum[cls - 1] : 0))];
+    const int inst = e.x;
+    const FxInfo F = fx[inst];
+    screen_run_live_tile<DIST, RP, AUDIT, BR>(g, e.y, e.z, (unsigned int)e.w, rec + (long long)inst * g.rec_stride,
+                                              recf + (long long)inst * g.rec_stride, pfx + (long long)inst * g.rec_stride,
+                                              F, SA + inst * sstride, SB + inst * sstride, LB + (long long)inst * g.n,
+                                              part_val + inst * pstride, part_arg + inst * pstride, counters, mono, sbuf,
+                                              s_pmax, s_log);
+  }
+}
+
+// One live tile, float data whose sums round: every sum a bound is formed from IS a reference running sum.  A live stage
+// starts from the row's checkpoint at its first boundary (the level-1 pass left one at every 128-block boundary), so the
+// stages of a tile are independent of each other -- stages that are not live are never touched.
+template <int DIST, bool RP, bool AUDIT, int BR>
+__device__ __forceinline__ void screen_run32_live_tile(const Geom& g, const int rb, const int slot,
+                                                       const unsigned int stage_mask, const Rec4<float>* __restrict__ rec,
+                                                       const float* __restrict__ SA, const float* __restrict__ SB,
+                                                       const bool forced, const float* __restrict__ LB,
+                                                       float* __restrict__ part_val, int* __restrict__ part_arg,
+                                                       unsigned long long* __restrict__ counters, const bool mono,
+                                                       float4 (*sbuf)[BR], float (*s_pmax)[BR / 32]) {
+  using D = float;
+  constexpr int BK = BR;
+  constexpr int U = 8;
+  const float4* __restrict__ recf = reinterpret_cast<const float4*>(rec);
+  const int tid = threadIdx.x;
+  const int i0 = rb * BR;
+  const int i = i0 + tid;
+  const int c = slot / g.nsub;
+  const int k_lo = max(c * g.L + 1, i0 + 1);
+  const int k_hi = min((c + 1) * g.L, g.kmax);
+  const int il = min(i, g.n - 1);
+  D best = Lim<D>::lowest();
+  int arg = -1;
+  const float thr0 = LB[min(il, max(g.nrows - 1, 0))];
+  float thr = thr0;
+  unsigned int nexact = 0, nviol = 0;
+  float2 S = make_float2(0.f, 0.f);  // running sums through cell kb - 1 at the top of a stage
   auto checkpoint = [&](const int kbnd) -> float2 {  // kbnd: multiple of 128, > i for every row of the block
     const long long o = (long long)(kbnd / SCR_BLOCK) * g.n + il;
     return make_float2(SA[o], SB[o]);
@@ -676,7 +678,7 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
     return add_rn<D>(screen_exact_score<D, DIST, RP, false>(S.x, S.y, nullptr), r.z);
   };
   // one cell on its own (diagonal, ragged, forced and audit paths): walk, bound, vote, evaluate
-  auto cell = [&](const int k, const float4 r, const bool valid, const bool forced) {
+  auto cell = [&](const int k, const float4 r, const bool valid) {
     if (valid) step(r);
     const float ub = ScreenUB<DIST, RP>::eval(S.x, S.y, screen_pm_of<D>(r));
     const bool pass = valid && (forced || !(ub < thr));
@@ -693,82 +695,57 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
       if (!(exact_here(r) < thr)) ++nviol;
     }
   };
-  // audit of a dropped k-range [ka, kb]: walk it and check every cell against the threshold it was dropped with
-  auto audit_range = [&](const int ka, const int kb) {
-    for (int k = ka; k <= kb; ++k) {
-      const float4 r = recf[k];
-      if (k > i) {
-        step(r);
-        if (i < g.nrows && !(exact_here(r) < thr)) ++nviol;
-      }
-    }
-  };
   auto stage_max = [&](const float4 r, const int buf) {
     float w = ((tid & 7) == 7) ? r.w : -3.402823466e+38f;
     w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 8));
     w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, 16));
     if ((tid & 31) == 31) s_pmax[buf][tid >> 5] = w;
   };
-  auto flush_counters = [&]() {
-    if (counters) {
-      if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
-      if (AUDIT) {
-        for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
-        if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
-      }
-    }
-  };
-  if (!diag_tile) S = checkpoint(c * g.L);
 
-  const bool forced = (i0 < ipos[inst]);
-  if (!forced && mono && (k_hi % SCR_BLOCK) == 0 && k_hi >= i0 + BR) {
-    // tile tier: the row's sums at the tile's last cell are a checkpoint
-    bmax += (long long)inst * nblk;
-    float tmax = -3.402823466e+38f;
-    for (int b = (k_lo - 1) / SCR_BLOCK; b <= (k_hi - 1) / SCR_BLOCK; ++b) tmax = fmaxf(tmax, bmax[b]);
-    const float2 E = checkpoint(k_hi);
-    const bool lose = (i >= g.nrows) ||
-                      (run32_range_ub<DIST, RP>(E.x, E.y, tmax, (float)(g.L + 8), (float)(k_hi - i)) < thr);
-    const bool tile_dropped = __syncthreads_and(lose);
-    if (AUDIT && counters && tid == 0) atomicAdd(&counters[tile_dropped ? 3 : 2], 1ULL);
-    if (tile_dropped) {
-      if (AUDIT) audit_range(k_lo, k_hi);
-      if (!tile_stamp && i < g.nrows) {
-        part_val[(long long)c * g.n + i] = best;
-        part_arg[(long long)c * g.n + i] = arg;
-      }
-      nexact = 0;
-      flush_counters();
-      return;
-    }
-  }
   const int nk = k_hi - k_lo + 1;
   const int nstages = (nk + BK - 1) / BK;
-  {
+  if (AUDIT && counters && tid == 0) atomicAdd(&counters[stage_mask ? 2 : 3], 1ULL);
+  unsigned int todo = AUDIT ? (nstages >= 32 ? 0xffffffffu : ((1u << nstages) - 1u)) : stage_mask;
+  int s = todo ? (__ffs(todo) - 1) : -1;
+  if (s >= 0) {
+    const int kb = k_lo + s * BK;
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k_lo + tid <= k_hi) r = recf[k_lo + tid];
+    if (kb + tid <= k_hi) r = recf[kb + tid];
     sbuf[0][tid] = r;
     stage_max(r, 0);
   }
-  for (int s = 0; s < nstages; ++s) {
+  int buf = 0;
+  while (s >= 0) {
     __syncthreads();
+    todo &= todo - 1u;
+    const int sn = todo ? (__ffs(todo) - 1) : -1;
     const int kb = k_lo + s * BK;
-    const int kn = kb + BK + tid;
     float4 nx = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool has_next = (s + 1 < nstages);
-    if (has_next && kn <= k_hi) nx = recf[kn];
+    if (sn >= 0 && k_lo + sn * BK + tid <= k_hi) nx = recf[k_lo + sn * BK + tid];
     const int cnt = min(BK, k_hi - kb + 1);
-    const float4* __restrict__ sb = sbuf[s & 1];
-    if (kb <= i0 + BR - 1 || cnt < BK || forced) {
+    const float4* __restrict__ sb = sbuf[buf];
+    const bool diag_stage = kb <= i0 + BR - 1;
+    S = diag_stage ? make_float2(0.f, 0.f) : checkpoint(kb - 1);
+    const bool sel_dropped = AUDIT && !((stage_mask >> s) & 1u);
+    if (sel_dropped) {
+      // (audit) a stage the select kernel dropped: walk it, every cell must lose against the row's initial threshold
+      if (counters && (tid & 31) == 0) atomicAdd(&counters[5], 1ULL);
+      for (int kk = 0; kk < cnt; ++kk) {
+        if (kb + kk > i) {
+          step(sb[kk]);
+          if (i < g.nrows && !(exact_here(sb[kk]) < thr0)) ++nviol;
+        }
+      }
+    } else if (diag_stage || cnt < BK || forced) {
       // diagonal stage (row i only sees k > i), ragged last stage, rows that take no bounds: cell by cell
-      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i, forced);
+      for (int kk = 0; kk < cnt; ++kk) cell(kb + kk, sb[kk], kb + kk > i);
     } else {
       const float2 E = checkpoint(kb + BK - 1);  // the row's sums at the stage's last cell
       bool skip = false;
       if (mono) {
-        float pmx = s_pmax[s & 1][0];
+        float pmx = s_pmax[buf][0];
 #pragma unroll
-        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[s & 1][w]);
+        for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[buf][w]);
         const float ubs = run32_range_ub<DIST, RP>(E.x, E.y, pmx, (float)(BK + 8), (float)(kb + BK - 1 - i));
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
@@ -780,7 +757,6 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
             if (!(exact_here(sb[kk]) < thr)) ++nviol;
           }
         }
-        S = E;
       } else {
 #pragma unroll 1
         for (int kk = 0; kk < BK; kk += U) {
@@ -840,17 +816,68 @@ level_tile_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
         }
       }
     }
-    if (has_next) {
-      sbuf[(s + 1) & 1][tid] = nx;
-      stage_max(nx, (s + 1) & 1);
+    if (sn >= 0) {
+      sbuf[buf ^ 1][tid] = nx;
+      stage_max(nx, buf ^ 1);
     }
+    buf ^= 1;
+    s = sn;
   }
   if (i < g.nrows) {
-    part_val[(long long)c * g.n + i] = best;
-    part_arg[(long long)c * g.n + i] = arg;
+    part_val[(long long)slot * g.n + i] = best;
+    part_arg[(long long)slot * g.n + i] = arg;
   }
-  if (tile_stamp && tid == 0) tile_stamp[((long long)inst * g.nch_alloc + c) * stamp_stride + rb] = stamp;
-  flush_counters();
+  if (counters) {
+    if ((tid & 31) == 0 && nexact) atomicAdd(&counters[0], (unsigned long long)nexact);
+    if (AUDIT) {
+      for (int o = 16; o > 0; o >>= 1) nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+      if ((tid & 31) == 0 && nviol) atomicAdd(&counters[1], (unsigned long long)nviol);
+    }
+  }
+}
+
+template <int DIST, bool RP, bool AUDIT, int BR>
+__global__ void __launch_bounds__(BR, 8)
+level_live_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, const float* __restrict__ SA,
+                               const float* __restrict__ SB, long long cp_stride, const int* __restrict__ ipos,
+                               const float* __restrict__ LB, float* __restrict__ part_val, int* __restrict__ part_arg,
+                               unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
+                               const int4* __restrict__ live, long long live_cap, LiveHdr* __restrict__ hdr) {
+  static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
+  static_assert(DIST == DIST_RATIONAL || DIST == DIST_GAUSSIAN, "A^2/B family and Gaussian mult-clust");
+  __shared__ float4 sbuf[2][BR];
+  __shared__ float s_pmax[2][BR / 32];
+  __shared__ int s_next;
+  const bool mono = dev_flags && (dev_flags[1] == 0);
+  const long long pstride = (long long)g.nch_alloc * g.nsub * g.n;
+  const int tid = threadIdx.x;
+  int cum[SCR_CLASSES];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int q = 0; q < SCR_CLASSES; ++q) {
+      acc += hdr->nlive[q];
+      cum[q] = acc;
+    }
+  }
+  const int nlive = cum[SCR_CLASSES - 1];
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_next = atomicAdd(&hdr->cursor, 1);
+    __syncthreads();
+    const int t = s_next;
+    if (t >= nlive) break;
+    int cls = 0;
+#pragma unroll
+    for (int q = 0; q < SCR_CLASSES - 1; ++q) cls += (t >= cum[q]) ? 1 : 0;
+    const int4 e = live[(long long)cls * live_cap + (t - (cls ? cum[cls - 1] : 0))];
+    const int inst = e.x;
+    const bool forced = (e.y * BR) < ipos[inst];
+    screen_run32_live_tile<DIST, RP, AUDIT, BR>(g, e.y, e.z, (unsigned int)e.w, rec + (long long)inst * g.rec_stride,
+                                                SA + inst * cp_stride, SB + inst * cp_stride, forced,
+                                                LB + (long long)inst * g.n, part_val + inst * pstride,
+                                                part_arg + inst * pstride, counters, mono && !forced, sbuf, s_pmax);
+  }
 }
 
 }  // namespace ps

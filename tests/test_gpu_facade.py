@@ -156,4 +156,7 @@ def test_reference_programs_run_on_the_engine(prog, args):
         df = pd.read_csv(io.StringIO("\n".join(rows)), sep=",", header=None, index_col=None)
         df = df.drop(columns=[df.columns[-1]])
         grid = df.loc[range(T_, n_ + 1, NStride), range(TStride, T_ + 1, TStride)]
-        assert grid.shape == (4, 4) and (grid.values > 0).all()
+        assert grid.shape == (4, 4)
+        for nn in grid.index:
+            for tt in grid.columns:  # the timer only runs sampleSize > numParts (solver_timer.cpp:61)
+                assert (grid.loc[nn, tt] > 0) == (nn > tt), (nn, tt)
