@@ -100,9 +100,11 @@ int ols_num_clusters(const std::vector<DataType>& scores) {
     b0 = static_cast<float>((m * sxy - sx * sy) / den);
     b1 = static_cast<float>((sy - static_cast<double>(b0) * sx) / m);
   } else {
-    const double nrm = static_cast<double>(x[0]) * x[0] + 1.0;
-    b0 = static_cast<float>(x[0] * y[0] / nrm);
-    b1 = static_cast<float>(y[0] / nrm);
+    // one sample (T = 2): the system is under-determined.  Eigen's colPivHouseholderQr pivots on the column of larger norm
+    // (log 3 > 1) and returns the basic solution (slope = y/x, intercept 0); any exact fit leaves residual 0, so the choice
+    // below is 1 whichever solution is taken (tests/test_host_logic.py pins that)
+    b0 = static_cast<float>(static_cast<double>(y[0]) / x[0]);
+    b1 = 0.f;
   }
   int best = 0;
   DataType minres = std::numeric_limits<DataType>::max();

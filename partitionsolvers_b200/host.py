@@ -44,10 +44,9 @@ def ols_num_clusters(scores, dtype):
         if den != 0:
             b0 = np.float32((m * sxy - sx * sy) / den)
             b1 = np.float32((sy - np.float64(b0) * sx) / m)
-        else:
-            nrm = xd[0] * xd[0] + 1.0
-            b0 = np.float32(xd[0] * yd[0] / nrm)
-            b1 = np.float32(yd[0] / nrm)
+        else:  # one sample (T = 2): basic solution of the under-determined system, residual 0 -> the choice is 1
+            b0 = np.float32(yd[0] / xd[0])
+            b1 = np.float32(0.0)
         best, minres = 0, np.finfo(dtype).max
         for i in range(m):
             r = np.float32(np.float32(y[i] - np.float32(b0 * x[i])) - b1)

@@ -73,3 +73,12 @@ def test_ols_degenerate_scores_default_to_one(oracle):
     for dt in (np.float32, np.float64):
         sc = np.array([0, 5, 5, 5, 5], dt)
         assert oracle.ols(sc, dtype=dt) == host.ols_num_clusters(sc, dt)
+
+
+def test_ols_single_sample_is_one(oracle):
+    """T = 2: one regression sample, an under-determined system.  Whatever solution is taken (Eigen's colPivHouseholderQr
+    returns the basic one) the only candidate index is 0, so the choice is 1 -- for the facade's restatement and the oracle's."""
+    for dt in (np.float32, np.float64):
+        for sc in ([0.0, 3.0, 5.0], [0.0, 1.0, 1.5], [0.0, 2.0, 1.0]):
+            sc = np.array(sc, dt)
+            assert host.ols_num_clusters(sc, dt) == 1 and oracle.ols(sc, dtype=dt) == 1
