@@ -218,18 +218,23 @@ def reference_arm(args):
     inst = max(1, args.gpus)
     which, kind, n_s = cpu_reference_sample(dtype, per_step, instances=inst)
 
-    def one_step():
-        if inst == 1:
-            return run_cpu_solver(which, dtype, n_s)[0]
+    pool = None
+    if inst > 1:
         import multiprocessing as mp
-        t0 = time.perf_counter()
-        with mp.get_context("fork").Pool(inst) as pool:
-            pool.starmap(run_cpu_solver, [(which, dtype, n_s)] * inst)
-        return time.perf_counter() - t0
+        pool = mp.get_context("spawn").Pool(inst)  # fresh interpreters: the reference's library is loaded per worker
 
-    for _ in range(args.warmup):
+    def one_step():
+        if pool is None:
+            return run_cpu_solver(which, dtype, n_s)[0]
+        # the N solves start together; the step lasts as long as the slowest of them
+        return max(t for t, _ in pool.starmap(run_cpu_solver, [(which, dtype, n_s)] * inst))
+
+    for _ in range(max(args.warmup, 1 if pool else 0)):
         one_step()
     times = [one_step() for _ in range(args.steps)]
+    if pool is not None:
+        pool.close()
+        pool.join()
     ms = 1e3 * float(np.mean(times))
     value = inst * synth.nominal_cells(n_s, cfg["T"]) / (ms * 1e-3)
     sample = (f"{'unmodified reference DPSolver' if kind == 'reference' else 'oracle port'}"
