@@ -392,7 +392,9 @@ struct ScreenRun32Launch {
   using LbFn = void (*)(ps::Geom, const ps::Rec4<float>*, float4*, const float*, const float*, long long, float*, float*,
                         int, int*);
   using SelFn = ScreenLaunch<float>::SelFn;
-  static bool supported(int dist, int rp) { return dist == PS_DIST_RATIONAL || dist == PS_DIST_GAUSSIAN; }
+  static bool supported(int dist, int rp) {
+    return dist == PS_DIST_RATIONAL || dist == PS_DIST_GAUSSIAN || (dist == PS_DIST_POISSON && !rp);
+  }
   static SelFn pick_select(int dist, int rp, int audit, int tpr) {
     using namespace ps;
 #define PS_PICK(DI, RPV)                                                                                      \
@@ -402,6 +404,7 @@ struct ScreenRun32Launch {
                            : (SelFn)screen_select_kernel<float, DI, RPV, false, 1, SEL_RUN32>);
     if (dist == PS_DIST_GAUSSIAN && !rp) PS_PICK(DIST_GAUSSIAN, false)
     if (dist == PS_DIST_GAUSSIAN && rp) PS_PICK(DIST_GAUSSIAN, true)
+    if (dist == PS_DIST_POISSON) PS_PICK(DIST_POISSON, false)
     PS_PICK(DIST_RATIONAL, false)
 #undef PS_PICK
   }
@@ -413,6 +416,9 @@ struct ScreenRun32Launch {
     if (dist == PS_DIST_GAUSSIAN && rp)
       return audit ? (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, true, true, BR>
                    : (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, true, false, BR>;
+    if (dist == PS_DIST_POISSON)
+      return audit ? (Fn)level_live_screen_run32_kernel<DIST_POISSON, false, true, BR>
+                   : (Fn)level_live_screen_run32_kernel<DIST_POISSON, false, false, BR>;
     return audit ? (Fn)level_live_screen_run32_kernel<DIST_RATIONAL, false, true, BR>
                  : (Fn)level_live_screen_run32_kernel<DIST_RATIONAL, false, false, BR>;
   }
@@ -420,6 +426,7 @@ struct ScreenRun32Launch {
     using namespace ps;
     if (dist == PS_DIST_GAUSSIAN && !rp) return (LbFn)screen_lb_run32_kernel<DIST_GAUSSIAN, false>;
     if (dist == PS_DIST_GAUSSIAN && rp) return (LbFn)screen_lb_run32_kernel<DIST_GAUSSIAN, true>;
+    if (dist == PS_DIST_POISSON) return (LbFn)screen_lb_run32_kernel<DIST_POISSON, false>;
     return (LbFn)screen_lb_run32_kernel<DIST_RATIONAL, false>;
   }
 };
@@ -807,6 +814,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // float Poisson on the fast path runs the two-rows-per-thread packed kernel (256-row tiles) once there are enough
   // rows to fill the machine with such tiles; smaller instances keep 128-row tiles (more, finer work items)
   const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 && !comm &&
+                      !screen_run32 &&  // the screened levels have their own 128-row geometry
                       (long long)n * R >= 16384;
   int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
   // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);

@@ -218,7 +218,7 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
 //   * the tile and stage tiers take the row's sums at the end of the tile / stage straight from the checkpoints;
 //   * a stage that survives is walked from its starting checkpoint (one packed FADD2 per cell), group by group; the group
 //     tier bounds at the group's last cell, the cell tier at every cell, survivors are evaluated on the spot.
-// Supported scores: the A^2/B family (Rational, Gaussian risk-part) and Gaussian mult-clust (run32_range_ub).  Monotonicity on the running sums themselves: adding an
+// Supported scores: the A^2/B family (Rational, Gaussian risk-part), Gaussian and Poisson mult-clust (run32_range_ub).  Monotonicity on the running sums themselves: adding an
 // element with priority r to sums (A, B), q = A/B, changes A^2/B by b (2 q r - q^2) >= 0 whenever r >= q/2; the running
 // ratio exceeds the true ratio of the range (<= r, priorities ascending) by at most a factor 1 + 2 m u < 2.  The m' additions
 // between a cell and the cell the bound is formed at round: S(k') >= S(k) (1 - 3 m' u), carried as 1 + 64u (group, m' <= 7),
@@ -246,6 +246,25 @@ __device__ __forceinline__ float run32_range_ub(float A, float B, float pm, floa
       e = fmaf(A, SCR_TINY, e);
       e = fmaf(B, slack, e);
       return fmaf(gt, SCR_REL_UP, e);
+    }
+    return fmaf(B, SCR_TINY + slack, pm);
+  } else if constexpr (DIST == DIST_POISSON && !RP) {
+    // g = A ln(A/B) + B - A for A > B, else 0: convex in (A, B) with gradient (ln q, 1 - q), so adding an element (a, b) of
+    // priority r changes it by at least b (r ln q + 1 - q), which is >= 0 whenever r >= (q - 1) / ln q (< q).  Along the exact
+    // continuation of the running sums q <= r (1 + 2 gam), gam = 1.01 len u; with q = 1 + h, q ln q / (1 + 2 gam) + 1 - q ~
+    // h^2/2 - 2 gam h, so a decrease needs h < 4.1 gam, where g <= (A - B)^2 / 2B <= 8.4 gam^2 B (the Gaussian score dominates
+    // the Poisson one): every cell of the range has g <= g(end) + 8.4 gam^2 B(end) -- the argument of the Gaussian branch above.
+    // The span roundings move (A, B) by span u relatively: |dg| <= span u (A ln q + A - B) <= 2 span u A (q - 1).  The bound at
+    // the range's last cell is the cell bound itself (screen.cuh: it already covers MUFU, its own roundings and the reference's
+    // at that cell; the reference's rounding at an earlier cell, 2u A + 6u A ln q with A, q no larger than at the end up to
+    // 2 gam, sits in the cell bound's 5u of spare margin on A).  Carried on top: 12 gam^2 B and (2 span + 16) u on A (q - 1).
+    const float gam = len * (1.01f * SCR_U);
+    const float slack = 12.0f * gam * gam;
+    if (A > B) {
+      const float h = (A - B) * rcp_approx(B);
+      float e = (A * h) * ((2.0f * span + 16.0f) * SCR_U);
+      e = fmaf(B, slack, e);
+      return ScreenUB<DIST_POISSON, false>::eval(A, B, pm) + e;
     }
     return fmaf(B, SCR_TINY + slack, pm);
   } else {
@@ -844,7 +863,8 @@ level_live_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
                                unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
                                const int4* __restrict__ live, long long live_cap, LiveHdr* __restrict__ hdr) {
   static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
-  static_assert(DIST == DIST_RATIONAL || DIST == DIST_GAUSSIAN, "A^2/B family and Gaussian mult-clust");
+  static_assert(DIST == DIST_RATIONAL || DIST == DIST_GAUSSIAN || (DIST == DIST_POISSON && !RP),
+                "A^2/B family, Gaussian and Poisson mult-clust");
   __shared__ float4 sbuf[2][BR];
   __shared__ float s_pmax[2][BR / 32];
   __shared__ int s_next;

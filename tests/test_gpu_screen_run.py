@@ -114,8 +114,9 @@ def test_conditions_of_the_fixed_point_bounds(ctx):
     scr = ctx.solve_raw(a3, b, T, 1, False, dtype=F64, levels=True)
     assert ctx.timings()["screen_used"] == 2
     _same_tables(exh, scr)
-    # float inputs: only the scores the float running-sum screen supports leave the exhaustive kernel
-    ctx.solve_raw(a.astype(np.float32), b.astype(np.float32), T, 1, False, dtype=np.float32)
+    # float inputs: only the scores the float running-sum screen supports leave the exhaustive kernel (Poisson risk-part
+    # does not: its box bound has no counterpart on rounded running sums)
+    ctx.solve_raw(a.astype(np.float32), b.astype(np.float32), T, 1, True, dtype=np.float32)
     assert ctx.timings()["screen_used"] == 0
 
 
@@ -130,13 +131,13 @@ def test_full_size_rational(ctx):
 
 # ------------------------------------------------------------------------------------------------ float inputs
 F32 = np.float32
-F32_SCORES = [(0, False), (0, True), (2, False)]  # Gaussian and Rational (screen_run.cuh, second half)
+F32_SCORES = [(0, False), (0, True), (2, False), (1, False)]  # Gaussian, Rational, Poisson mult-clust (screen_run.cuh)
 
 
 @pytest.mark.parametrize("dist,rp", F32_SCORES)
 def test_float_running_screen_equals_exhaustive_and_audit_is_clean(ctx, dist, rp):
     n, T = 20000, 6
-    for positive in (True, False):  # False: some a <= 0, the first row blocks take no bounds
+    for positive in ((True,) if dist == 1 else (True, False)):  # False: some a <= 0, the first row blocks take no bounds
         a, b = _real_valued(n, 6, synth.SEED + 70, positive=positive)
         a, b = a.astype(F32), b.astype(F32)
         exh = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, levels=True, sweep=True, screen=1)
@@ -157,6 +158,8 @@ def test_float_running_screen_matches_oracle(oracle, ctx):
     for name, (a, b) in (("tract", synth.tract_like(n, 4, seed=synth.SEED + 71, dtype=F32)),
                          ("mixture", synth.gaussian_mixture(n, 5, seed=synth.SEED + 72, dtype=F32))):
         for dist, rp in F32_SCORES:
+            if dist == 1:
+                a = np.maximum(a, F32(0.5))  # Poisson needs positive a
             ref = oracle.solve("port", a, b, T, dist, rp, dtype=F32)
             raw = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, perm=ref["perm"], levels=True, screen=2)
             t = ctx.timings()
@@ -170,6 +173,8 @@ def test_float_running_screen_unsorted_permutation_and_batch(ctx):
     a, b = synth.gaussian_mixture(n, 5, seed=synth.SEED + 73, dtype=F32)
     perm = np.random.RandomState(7).permutation(n).astype(np.int32)
     for dist, rp in F32_SCORES:
+        if dist == 1:
+            a = np.maximum(a, F32(0.5))
         exh = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, perm=perm, levels=True, screen=1)
         aud = ctx.solve_raw(a, b, T, dist, rp, dtype=F32, perm=perm, levels=True, screen=2)
         t = ctx.timings()
@@ -191,3 +196,21 @@ def test_full_size_rational_float(ctx):
     scr = ctx.solve_raw(a, b, 4, 2, False, dtype=F32, levels=True, screen=0)
     assert ctx.timings()["screen_used"] == 2
     _same_tables(exh, scr)
+
+
+def test_full_size_poisson_float_real_valued(ctx):
+    """BASELINE configuration 3 shape, Poisson multiple clustering on REAL-VALUED float data (sums round): the float
+    running-sum screen, audited at T = 3 and plain at T = 4, against the exhaustive kernel."""
+    a, b = synth.CONFIGS["C3R"]["gen"](F32)
+    a = np.abs(a) + F32(0.25)
+    exh = ctx.solve_raw(a, b, 4, 1, False, dtype=F32, levels=True, screen=1)
+    assert ctx.timings()["screen_used"] == 0
+    scr = ctx.solve_raw(a, b, 4, 1, False, dtype=F32, levels=True, screen=0)
+    assert ctx.timings()["screen_used"] == 2
+    _same_tables(exh, scr)
+    aud = ctx.solve_raw(a, b, 3, 1, False, dtype=F32, levels=True, screen=2)
+    t = ctx.timings()
+    assert t["screen_used"] == 2 and t["screen_violations"] == 0
+    # level 3 of the T = 3 solve is its last level: row 0 only
+    assert np.array_equal(aud["max_score"][:3], exh["max_score"][:3]) and aud["max_score"][3][0] == exh["max_score"][3][0]
+    assert np.array_equal(aud["next_start"][:3], exh["next_start"][:3]) and aud["next_start"][3][0] == exh["next_start"][3][0]
