@@ -661,6 +661,18 @@ def main():
                     per_score[key] = {"ms": best, "value": synth.nominal_cells(n, T) / (best * 1e-3),
                                       "level_kernel": {0: "exhaustive", 1: "screened, exact sums",
                                                        2: "screened, running sums"}[ctx.timings()["screen_used"]]}
+                # Poisson on REAL-VALUED data as well (sums round: running-sum screens; float risk-part is the one case left
+                # on the exhaustive kernel)
+                a_r = (np.abs(a_g) + 0.25).astype(dt_s)
+                for rp_s in (False, True):
+                    best = 1e30
+                    for _ in range(3):
+                        ctx.solve_raw(a_r, b_g, T, 1, rp_s, dtype=dt_s, want_perm=False)
+                        best = min(best, ctx.timings()["total_ms"])
+                    key = f"poisson_{'rp' if rp_s else 'mc'}_realvalued_{'f64' if dt_s == np.float64 else 'f32'}"
+                    per_score[key] = {"ms": best, "value": synth.nominal_cells(n, T) / (best * 1e-3),
+                                      "level_kernel": {0: "exhaustive", 1: "screened, exact sums",
+                                                       2: "screened, running sums"}[ctx.timings()["screen_used"]]}
             line["c3_all_scores"] = per_score
         # ---- exact branch-and-bound is data dependent: the inputs on which it cannot prune, at the headline size, on both
         # level kernels (same tables).  constant a/b: every cell of a row ties; a in {1,2}, b = 1 (gtest_all.cpp:924-958);
