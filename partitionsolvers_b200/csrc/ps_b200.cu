@@ -392,9 +392,7 @@ struct ScreenRun32Launch {
   using LbFn = void (*)(ps::Geom, const ps::Rec4<float>*, float4*, const float*, const float*, long long, float*, float*,
                         int, int*);
   using SelFn = ScreenLaunch<float>::SelFn;
-  static bool supported(int dist, int rp) {
-    return dist == PS_DIST_RATIONAL || dist == PS_DIST_GAUSSIAN || (dist == PS_DIST_POISSON && !rp);
-  }
+  static bool supported(int, int) { return true; }
   static SelFn pick_select(int dist, int rp, int audit, int tpr) {
     using namespace ps;
 #define PS_PICK(DI, RPV)                                                                                      \
@@ -404,7 +402,8 @@ struct ScreenRun32Launch {
                            : (SelFn)screen_select_kernel<float, DI, RPV, false, 1, SEL_RUN32>);
     if (dist == PS_DIST_GAUSSIAN && !rp) PS_PICK(DIST_GAUSSIAN, false)
     if (dist == PS_DIST_GAUSSIAN && rp) PS_PICK(DIST_GAUSSIAN, true)
-    if (dist == PS_DIST_POISSON) PS_PICK(DIST_POISSON, false)
+    if (dist == PS_DIST_POISSON && !rp) PS_PICK(DIST_POISSON, false)
+    if (dist == PS_DIST_POISSON && rp) PS_PICK(DIST_POISSON, true)
     PS_PICK(DIST_RATIONAL, false)
 #undef PS_PICK
   }
@@ -416,9 +415,12 @@ struct ScreenRun32Launch {
     if (dist == PS_DIST_GAUSSIAN && rp)
       return audit ? (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, true, true, BR>
                    : (Fn)level_live_screen_run32_kernel<DIST_GAUSSIAN, true, false, BR>;
-    if (dist == PS_DIST_POISSON)
+    if (dist == PS_DIST_POISSON && !rp)
       return audit ? (Fn)level_live_screen_run32_kernel<DIST_POISSON, false, true, BR>
                    : (Fn)level_live_screen_run32_kernel<DIST_POISSON, false, false, BR>;
+    if (dist == PS_DIST_POISSON && rp)
+      return audit ? (Fn)level_live_screen_run32_kernel<DIST_POISSON, true, true, BR>
+                   : (Fn)level_live_screen_run32_kernel<DIST_POISSON, true, false, BR>;
     return audit ? (Fn)level_live_screen_run32_kernel<DIST_RATIONAL, false, true, BR>
                  : (Fn)level_live_screen_run32_kernel<DIST_RATIONAL, false, false, BR>;
   }
@@ -426,7 +428,8 @@ struct ScreenRun32Launch {
     using namespace ps;
     if (dist == PS_DIST_GAUSSIAN && !rp) return (LbFn)screen_lb_run32_kernel<DIST_GAUSSIAN, false>;
     if (dist == PS_DIST_GAUSSIAN && rp) return (LbFn)screen_lb_run32_kernel<DIST_GAUSSIAN, true>;
-    if (dist == PS_DIST_POISSON) return (LbFn)screen_lb_run32_kernel<DIST_POISSON, false>;
+    if (dist == PS_DIST_POISSON && !rp) return (LbFn)screen_lb_run32_kernel<DIST_POISSON, false>;
+    if (dist == PS_DIST_POISSON && rp) return (LbFn)screen_lb_run32_kernel<DIST_POISSON, true>;
     return (LbFn)screen_lb_run32_kernel<DIST_RATIONAL, false>;
   }
 };

@@ -218,7 +218,7 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
 //   * the tile and stage tiers take the row's sums at the end of the tile / stage straight from the checkpoints;
 //   * a stage that survives is walked from its starting checkpoint (one packed FADD2 per cell), group by group; the group
 //     tier bounds at the group's last cell, the cell tier at every cell, survivors are evaluated on the spot.
-// Supported scores: the A^2/B family (Rational, Gaussian risk-part), Gaussian and Poisson mult-clust (run32_range_ub).  Monotonicity on the running sums themselves: adding an
+// Every score is supported (run32_range_ub).  Monotonicity on the running sums themselves, A^2/B family: adding an
 // element with priority r to sums (A, B), q = A/B, changes A^2/B by b (2 q r - q^2) >= 0 whenever r >= q/2; the running
 // ratio exceeds the true ratio of the range (<= r, priorities ascending) by at most a factor 1 + 2 m u < 2.  The m' additions
 // between a cell and the cell the bound is formed at round: S(k') >= S(k) (1 - 3 m' u), carried as 1 + 64u (group, m' <= 7),
@@ -228,9 +228,15 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
 // =====================================================================================================================
 // Bound for every cell of a k-range of row i from the row's RUNNING sums (A, B) at the range's last cell k', the largest pm
 // of the range, span = number of additions between the range's first and last cell, len = k' - i.
+// Poisson risk-partitioning is bounded on the box instead (ScreenUB<DIST_POISSON, true>::box): (Af, Bf) are the row's running
+// sums at or before the range's first cell.  Adding a >= 0 / b >= 0 to a float never lowers it (rounding is monotone), so every
+// cell of the range has A in [Af, A] and B >= Bf exactly -- no sortedness, no span term; the box bound's own margins are the
+// cell bound's.
 template <int DIST, bool RP>
-__device__ __forceinline__ float run32_range_ub(float A, float B, float pm, float span, float len) {
-  if constexpr (DIST == DIST_GAUSSIAN && !RP) {
+__device__ __forceinline__ float run32_range_ub(float Af, float Bf, float A, float B, float pm, float span, float len) {
+  if constexpr (DIST == DIST_POISSON && RP) {
+    return ScreenUB<DIST_POISSON, true>::box(Af, Bf, A, pm);
+  } else if constexpr (DIST == DIST_GAUSSIAN && !RP) {
     // g = (A - B)^2 / (2B) for A > B, else 0.  Adding an element of priority r raises g whenever r >= (q + 1) / 2.  Along the
     // exact continuation of the running sums q <= r (1 + 2 gam), gam = 1.01 len u, so a decrease needs q < 1 + 4.1 gam, where
     // g <= 8.4 gam^2 B: every cell of the range has g <= g(end) + 8.4 gam^2 B(end).  The span roundings move (A, B) by span u
@@ -765,7 +771,7 @@ __device__ __forceinline__ void screen_run32_live_tile(const Geom& g, const int 
         float pmx = s_pmax[buf][0];
 #pragma unroll
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[buf][w]);
-        const float ubs = run32_range_ub<DIST, RP>(E.x, E.y, pmx, (float)(BK + 8), (float)(kb + BK - 1 - i));
+        const float ubs = run32_range_ub<DIST, RP>(S.x, S.y, E.x, E.y, pmx, (float)(BK + 8), (float)(kb + BK - 1 - i));
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
       if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
@@ -786,7 +792,7 @@ __device__ __forceinline__ void screen_run32_live_tile(const Geom& g, const int 
             W[u] = S;
           }
           if (mono) {
-            const float ubg = run32_range_ub<DIST, RP>(W[U - 1].x, W[U - 1].y, sb[kk + U - 1].w, (float)U,
+            const float ubg = run32_range_ub<DIST, RP>(W[0].x, W[0].y, W[U - 1].x, W[U - 1].y, sb[kk + U - 1].w, (float)U,
                                                        (float)(kb + kk + U - 1 - i));
             const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
             if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
@@ -863,12 +869,11 @@ level_live_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
                                unsigned long long* __restrict__ counters, const int* __restrict__ dev_flags,
                                const int4* __restrict__ live, long long live_cap, LiveHdr* __restrict__ hdr) {
   static_assert(BR == SCR_BLOCK, "a stage is one 128-block of k");
-  static_assert(DIST == DIST_RATIONAL || DIST == DIST_GAUSSIAN || (DIST == DIST_POISSON && !RP),
-                "A^2/B family, Gaussian and Poisson mult-clust");
   __shared__ float4 sbuf[2][BR];
   __shared__ float s_pmax[2][BR / 32];
   __shared__ int s_next;
-  const bool mono = dev_flags && (dev_flags[1] == 0);
+  // the box bound (Poisson risk-part) holds in any element order; the others need the priorities ascending
+  const bool mono = (DIST == DIST_POISSON && RP) || (dev_flags && (dev_flags[1] == 0));
   const long long pstride = (long long)g.nch_alloc * g.nsub * g.n;
   const int tid = threadIdx.x;
   int cum[SCR_CLASSES];

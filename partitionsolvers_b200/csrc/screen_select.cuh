@@ -158,7 +158,7 @@ screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restric
   auto range_ub = [&](const float Af, const float Bf, const float Al, const float Bl, const float pm, const int span,
                       const int k_last) -> float {
     if constexpr (SRC == SEL_RUN32)
-      return run32_range_ub<DIST, RP>(Al, Bl, pm, (float)(span + 8), (float)(k_last - i));
+      return run32_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm, (float)(span + 8), (float)(k_last - i));
     else
       return screen_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm);
   };
@@ -181,7 +181,7 @@ screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restric
         float Ae, Be;
         fsums(ke, Ae, Be);
         float A0 = Ae, B0 = Be;
-        if (BOX) fsums(min(k0, ke), A0, B0);
+        if (BOX) fsums(SRC == SEL_RUN32 ? kb - 1 : min(k0, ke), A0, B0);  // running sums: the boundary before the stage
         lose_s = range_ub(A0, B0, Ae, Be, bmax[(kb - 1) / BR], BR, ke) < thr;
       }
       if (!lose_s) m |= 1u << s;
@@ -218,7 +218,10 @@ screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restric
           else
             fsum2(s_ex[ce], s_ey[ce], At, Bt);
           float Af = At, Bf = Bt;
-          if (BOX) fsum2(s_fx[c4], s_fy[c4], Af, Bf);
+          if constexpr (BOX && SRC == SEL_RUN32)
+            fsums(c4 * g.L, Af, Bf);  // the boundary before the first of the four tiles (c4 > c_diag: right of the block)
+          else if (BOX)
+            fsum2(s_fx[c4], s_fy[c4], Af, Bf);
           const float pm4 = fmaxf(fmaxf(s_tmax[c4], s_tmax[c4 + 1]), fmaxf(s_tmax[c4 + 2], s_tmax[ce]));
           const bool lose4 = !row_ok || (range_ub(Af, Bf, At, Bt, pm4, 4 * g.L, k_end) < thr);
           if (!__any_sync(0xffffffffu, !lose4)) continue;
@@ -232,14 +235,16 @@ screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restric
         const int k_hi = min((c + 1) * g.L, g.kmax);
         const int kf = max(k_lo, i + 1);  // the row's first cell in this tile
         lose[u] = !row_ok || (c4 + u >= g.NCH) || (kf > k_hi);
-        if (!lose[u] && bound_at(k_hi)) {
+        if (!lose[u] && bound_at(k_hi) && !(BOX && SRC == SEL_RUN32 && c == c_diag)) {
           float At, Bt;
           if constexpr (SRC == SEL_RUN32)
             fsums(k_hi, At, Bt);
           else
             fsum2(s_ex[c], s_ey[c], At, Bt);
           float Af = At, Bf = Bt;
-          if (BOX) {
+          if constexpr (BOX && SRC == SEL_RUN32) {
+            fsums(c * g.L, Af, Bf);  // c > c_diag: the tile's left boundary lies right of the whole row block
+          } else if (BOX) {
             if (c == c_diag)
               fsums(min(kf, k_hi), Af, Bf);
             else

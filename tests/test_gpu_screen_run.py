@@ -114,10 +114,12 @@ def test_conditions_of_the_fixed_point_bounds(ctx):
     scr = ctx.solve_raw(a3, b, T, 1, False, dtype=F64, levels=True)
     assert ctx.timings()["screen_used"] == 2
     _same_tables(exh, scr)
-    # float inputs: only the scores the float running-sum screen supports leave the exhaustive kernel (Poisson risk-part
-    # does not: its box bound has no counterpart on rounded running sums)
-    ctx.solve_raw(a.astype(np.float32), b.astype(np.float32), T, 1, True, dtype=np.float32)
-    assert ctx.timings()["screen_used"] == 0
+    # float inputs: Poisson risk-part is screened too (box bound on the running sums themselves) and gives the same tables
+    af, bf = a.astype(np.float32), b.astype(np.float32)
+    exh = ctx.solve_raw(af, bf, T, 1, True, dtype=np.float32, levels=True, screen=1)
+    scr = ctx.solve_raw(af, bf, T, 1, True, dtype=np.float32, levels=True)
+    assert ctx.timings()["screen_used"] == 2
+    _same_tables(exh, scr)
 
 
 def test_full_size_rational(ctx):
@@ -131,7 +133,7 @@ def test_full_size_rational(ctx):
 
 # ------------------------------------------------------------------------------------------------ float inputs
 F32 = np.float32
-F32_SCORES = [(0, False), (0, True), (2, False), (1, False)]  # Gaussian, Rational, Poisson mult-clust (screen_run.cuh)
+F32_SCORES = [(0, False), (0, True), (2, False), (1, False), (1, True)]  # every score (screen_run.cuh)
 
 
 @pytest.mark.parametrize("dist,rp", F32_SCORES)
@@ -198,17 +200,18 @@ def test_full_size_rational_float(ctx):
     _same_tables(exh, scr)
 
 
-def test_full_size_poisson_float_real_valued(ctx):
-    """BASELINE configuration 3 shape, Poisson multiple clustering on REAL-VALUED float data (sums round): the float
+@pytest.mark.parametrize("rp", [False, True])
+def test_full_size_poisson_float_real_valued(ctx, rp):
+    """BASELINE configuration 3 shape, Poisson (both objectives) on REAL-VALUED float data (sums round): the float
     running-sum screen, audited at T = 3 and plain at T = 4, against the exhaustive kernel."""
     a, b = synth.CONFIGS["C3R"]["gen"](F32)
     a = np.abs(a) + F32(0.25)
-    exh = ctx.solve_raw(a, b, 4, 1, False, dtype=F32, levels=True, screen=1)
+    exh = ctx.solve_raw(a, b, 4, 1, rp, dtype=F32, levels=True, screen=1)
     assert ctx.timings()["screen_used"] == 0
-    scr = ctx.solve_raw(a, b, 4, 1, False, dtype=F32, levels=True, screen=0)
+    scr = ctx.solve_raw(a, b, 4, 1, rp, dtype=F32, levels=True, screen=0)
     assert ctx.timings()["screen_used"] == 2
     _same_tables(exh, scr)
-    aud = ctx.solve_raw(a, b, 3, 1, False, dtype=F32, levels=True, screen=2)
+    aud = ctx.solve_raw(a, b, 3, 1, rp, dtype=F32, levels=True, screen=2)
     t = ctx.timings()
     assert t["screen_used"] == 2 and t["screen_violations"] == 0
     # level 3 of the T = 3 solve is its last level: row 0 only
