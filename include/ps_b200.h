@@ -135,6 +135,9 @@ ps_status ps_create(ps_ctx** out, int device);
 void ps_destroy(ps_ctx* ctx);
 const char* ps_last_error(const ps_ctx* ctx);
 int ps_device(const ps_ctx* ctx);
+/* CUDA devices visible to this process (0 if the runtime reports none); for callers that spread independent instances over
+ * several devices, one context and one host thread per device (include/partitionsolvers/replicas.hpp does exactly that) */
+int ps_device_count(void);
 /* cudaStream_t of the context, as an integer (for callers that order their own work after ours) */
 uintptr_t ps_stream(const ps_ctx* ctx);
 /* The engine works on its OWN non-blocking stream, which has no implicit ordering with any other stream.  Device buffers

@@ -21,7 +21,7 @@ PS_MAX_TIMED_LEVELS = 130
 
 # every symbol include/ps_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
-    "ps_abi_version", "ps_status_string", "ps_create", "ps_destroy", "ps_last_error", "ps_device",
+    "ps_abi_version", "ps_status_string", "ps_create", "ps_destroy", "ps_last_error", "ps_device", "ps_device_count",
     "ps_stream", "ps_solve_f32", "ps_solve_f64", "ps_get_timings", "ps_range_score_f32",
     "ps_range_score_f64", "ps_shard_create_f64", "ps_shard_create_f32", "ps_shard_chunk_rows",
     "ps_shard_level1", "ps_shard_set_prev", "ps_shard_level", "ps_shard_next_start", "ps_shard_owner",

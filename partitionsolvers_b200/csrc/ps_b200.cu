@@ -1647,6 +1647,14 @@ void ps_destroy(ps_ctx* ctx) {
 
 const char* ps_last_error(const ps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int ps_device(const ps_ctx* ctx) { return ctx ? ctx->device : -1; }
+int ps_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
 uintptr_t ps_stream(const ps_ctx* ctx) { return ctx ? (uintptr_t)ctx->stream : 0; }
 
 ps_status ps_stream_wait(ps_ctx* ctx, uintptr_t other_stream) {

@@ -2,6 +2,7 @@
 // against the engine-backed facade <partitionsolvers/DP.hpp>, without gtest (not installed here).
 // Each block names the reference test it follows.  Needs a GPU; run by tests/test_gpu_facade.py.
 #include <partitionsolvers/DP.hpp>
+#include <partitionsolvers/replicas.hpp>
 
 #include <cstdio>
 #include <random>
@@ -197,6 +198,36 @@ int main() {
                                                .get_optimal_score_extern(); });
     for (auto& t : th) t.join();
     for (int q = 0; q < 4; ++q) CHECK(got[q] == ref);
+  }
+
+  {  // ReplicaSolver: R instances in one call (over every visible device) == R separate DPSolver constructions.  Count
+     // data (tied priorities: both take the engine's stable order), both objectives, R not a multiple of the device count.
+    const int R = 37, n = 400, T = 5;
+    std::vector<float> a((size_t)R * n), b((size_t)R * n);
+    std::mt19937 eng(77);
+    std::poisson_distribution<int> pb(100);
+    for (size_t i = 0; i < a.size(); ++i) {
+      b[i] = (float)std::max(1, pb(eng));
+      std::poisson_distribution<int> pa((double)b[i]);
+      a[i] = (float)std::max(1, pa(eng));
+    }
+    for (int rp = 0; rp < 2; ++rp) {
+      partitionsolvers::ReplicaSolver<float> rs(R, n, T, a.data(), b.data(), objective_fn::Poisson, rp != 0);
+      CHECK(rs.replicas() == R && rs.devices_used() >= 1 && rs.devices_used() <= ps_device_count());
+      for (int r = 0; r < R; ++r) {
+        std::vector<float> ar(a.begin() + (size_t)r * n, a.begin() + (size_t)(r + 1) * n);
+        std::vector<float> br(b.begin() + (size_t)r * n, b.begin() + (size_t)(r + 1) * n);
+        DPSolver<float> one(n, T, ar, br, objective_fn::Poisson, rp != 0, true);
+        CHECK(rs.get_optimal_score_extern(r) == one.get_optimal_score_extern());
+        CHECK(rs.get_optimal_subsets_extern(r) == one.get_optimal_subsets_extern());
+        CHECK(rs.get_score_by_subset_extern(r) == one.get_score_by_subset_extern());
+      }
+      // one device asked for: same results
+      partitionsolvers::ReplicaSolver<float> r1(R, n, T, a.data(), b.data(), objective_fn::Poisson, rp != 0, 1);
+      CHECK(r1.devices_used() == 1);
+      for (int r = 0; r < R; ++r) CHECK(r1.get_optimal_score_extern(r) == rs.get_optimal_score_extern(r));
+    }
+    std::printf("ReplicaSolver: %d device(s) visible\n", ps_device_count());
   }
 
   if (g_fail) {

@@ -88,8 +88,12 @@ def test_preconditions_send_other_inputs_to_the_exhaustive_kernel(ctx):
     # float sums beyond 2^24 are not exact in float
     a, b = synth.poisson_planted(200000, 5, seed=synth.SEED + 46, dtype=np.float32)
     assert float(a.astype(np.float64).sum()) > 2 ** 24
-    ctx.solve_raw(a, b, 3, 1, False, dtype=np.float32)
+    # ... so the exact-sum screen is out; the float running-sum screen (screen_run.cuh) takes over, same tables
+    scr = ctx.solve_raw(a, b, 3, 1, False, dtype=np.float32, levels=True)
+    assert ctx.timings()["screen_used"] == 2
+    exh = ctx.solve_raw(a, b, 3, 1, False, dtype=np.float32, levels=True, screen=1)
     assert ctx.timings()["screen_used"] == 0
+    _same_tables(exh, scr)
     # ... but fine in double
     ctx.solve_raw(a.astype(np.float64), b.astype(np.float64), 3, 1, False, dtype=np.float64)
     assert ctx.timings()["screen_used"] == 1
