@@ -129,8 +129,7 @@ level_tile_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restrict__
   constexpr bool kLogTab = (sizeof(D) == 8) && (DIST == DIST_POISSON) && FAST;
   __shared__ GlogEntry s_log[kLogTab ? 128 : 1];
   if (kLogTab) {
-    static_assert(BR >= 128, "one table entry per thread");
-    if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
+    for (int t = threadIdx.x; t < 128; t += BR) s_log[t] = g_glog_tab[t];
   }
 
   const int inst = blockIdx.y;
@@ -703,6 +702,100 @@ level1_running_kernel(int n, int L, int nch_alloc, long long rec_stride, int dis
     if (rec_next) rec_next[inst * rec_stride + i].p = v;
   }
   if (shard_chunk) shard_chunk[m * BR + tid] = v;
+  }
+}
+
+// global -> shared copies that bypass the register file (cp.async, 16 bytes each)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Level 1, RUNNING sums, small instances (ps_b200.cu: SMALL_ROWS = 32-row tiles, chunk length 32): one WARP per 32 rows.  The
+// walk is one dependent add chain per row whatever the geometry; with 32-cell stages the 128-row kernel's scheme (next stage
+// fetched into registers while the current one is walked) leaves ~300 cycles of work to hide a global load, so the records
+// come through a four-deep cp.async ring instead (three stages = 96 cells ahead) and the only synchronisation is __syncwarp.
+// Checkpoints at every multiple of 32 (L = 32).  Same sums, same order: every row adds its cells left to right.
+template <typename D>
+__global__ void __launch_bounds__(32)
+level1_running_small_kernel(int n, int nch_alloc, long long rec_stride, int dist, int rp, const Rec4<D>* __restrict__ rec,
+                            D* __restrict__ SA, D* __restrict__ SB, D* __restrict__ ms1, int* __restrict__ ns1,
+                            long long table_stride, Rec4<D>* __restrict__ rec_next, int nblocks) {
+  constexpr int BK = 32, NBUF = 4;
+  __shared__ Rec4<D> sbuf[NBUF][BK];
+  const int inst = blockIdx.y;
+  rec += (long long)inst * rec_stride;
+  const long long pstride = (long long)nch_alloc * n;
+  const int tid = threadIdx.x;
+  for (int pass = 0; pass < 2; ++pass) {  // block m, then block nblocks-1-m: every warp walks the same number of cells
+    const int m = pass ? nblocks - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    if (pass && m <= (int)blockIdx.x) break;
+    __syncwarp();
+    const int i0 = m * BK;
+    const int i = i0 + tid;
+    D A = 0, B = 0;
+    if (i0 < n) {
+      const int k_lo = i0 + 1, k_hi = n;
+      const int nstages = (k_hi - k_lo + 1 + BK - 1) / BK;
+      auto issue = [&](const int s) {
+        if (s < nstages) {
+          const int k = min(k_lo + s * BK + tid, k_hi);  // cells past k_hi are never consumed
+          cp_async16(&sbuf[s % NBUF][tid], &rec[k]);
+          if (sizeof(D) == 8)
+            cp_async16(reinterpret_cast<char*>(&sbuf[s % NBUF][tid]) + 16, reinterpret_cast<const char*>(&rec[k]) + 16);
+        }
+        cp_async_commit();  // an empty group keeps the count uniform
+      };
+      for (int s = 0; s < NBUF - 1; ++s) issue(s);
+      for (int s = 0; s < nstages; ++s) {
+        issue(s + NBUF - 1);
+        cp_async_wait_group<NBUF - 1>();
+        __syncwarp();
+        const int kb = k_lo + s * BK;
+        const int cnt = min(BK, k_hi - kb + 1);
+        const Rec4<D>* __restrict__ sb = sbuf[s % NBUF];
+        if (s == 0) {
+          for (int kk = 0; kk < cnt; ++kk) {
+            if (kb + kk > i) {
+              A = add_rn<D>(A, sb[kk].x);
+              B = add_rn<D>(B, sb[kk].y);
+            }
+          }
+        } else if (cnt == BK) {
+#pragma unroll
+          for (int kk = 0; kk < BK; ++kk) {
+            A = add_rn<D>(A, sb[kk].x);
+            B = add_rn<D>(B, sb[kk].y);
+          }
+        } else {
+          for (int kk = 0; kk < cnt; ++kk) {
+            A = add_rn<D>(A, sb[kk].x);
+            B = add_rn<D>(B, sb[kk].y);
+          }
+        }
+        if (cnt == BK && i < n && SA) {  // kend = i0 + 32 (s + 1): a chunk boundary
+          const int c = (kb + BK - 1) / BK;
+          if (c < nch_alloc) {
+            SA[inst * pstride + (long long)c * n + i] = A;
+            SB[inst * pstride + (long long)c * n + i] = B;
+          }
+        }
+        __syncwarp();  // the buffer of this stage is refilled by the next iteration's issue
+      }
+      cp_async_wait_group<0>();
+    }
+    if (i < n) {
+      const D v = score_dyn<D>(dist, rp, A, B);
+      ms1[inst * table_stride + i] = v;
+      ns1[inst * table_stride + i] = n;
+      rec_next[inst * rec_stride + i].p = v;
+    }
   }
 }
 

@@ -55,6 +55,7 @@ struct ps_ctx {
   long long launches = 0;
   int* pinned_flags = nullptr;  // [0] range/exactness flags, [2..5] screen counters (as 2 x u64)
   unsigned long long* pinned_levels = nullptr;  // per level: cumulative exact-cell counter (screen give-up rule)
+  unsigned char* pinned_out = nullptr;          // staging for small results (PINNED_OUT_BYTES): see copy_out in solve_impl
   size_t pinned_levels_cap = 0;
   int last_fast = 0;
   int dbg_level = 0;  // development: record per-tile times of this level (PS_DEBUG_LEVEL)
@@ -242,6 +243,12 @@ bool mufu_claims_hold(ps_ctx* ctx) {
   return g_mufu_state[d] == 1;
 }
 
+// Small instances: with 128-row tiles a level of n = 1000 is 36 work items whose threads each walk 128 cells one after the
+// other (23 us per level, 148 SMs mostly idle).  32-row tiles of 32 cells give ~500 one-warp work items and a chain a quarter
+// as long; same kernels, same order of evaluation inside a row, same partials folded in ascending k.
+constexpr int SMALL_ROWS = 32;
+constexpr size_t PINNED_OUT_BYTES = 256 * 1024;  // results up to this size are staged through pinned memory (solve_impl)
+
 template <typename D>
 struct LevelLaunch {
   using Fn = void (*)(ps::Geom, const ps::Rec4<D>*, const D*, const D*, D*, int*);
@@ -252,6 +259,21 @@ struct LevelLaunch {
                          : (Fn)level_tile_kernel<D, DI, RPV, false, true, BR>)                        \
               : (running ? (Fn)level_tile_kernel<D, DI, RPV, true, false, BR>                         \
                          : (Fn)level_tile_kernel<D, DI, RPV, false, false, BR>);
+    switch (dist * 2 + (rp ? 1 : 0)) {
+      case 0: PS_PICK(DIST_GAUSSIAN, false)
+      case 1: PS_PICK(DIST_GAUSSIAN, true)
+      case 2: PS_PICK(DIST_POISSON, false)
+      case 3: PS_PICK(DIST_POISSON, true)
+      default: PS_PICK(DIST_RATIONAL, false)
+    }
+#undef PS_PICK
+  }
+  // small instances (SMALL_ROWS-row tiles, chunk length SMALL_ROWS; range-prechecked math only)
+  static Fn pick_small(int dist, int rp, int running) {
+    using namespace ps;
+#define PS_PICK(DI, RPV)                                                                  \
+  return running ? (Fn)level_tile_kernel<D, DI, RPV, true, true, SMALL_ROWS>              \
+                 : (Fn)level_tile_kernel<D, DI, RPV, false, true, SMALL_ROWS>;
     switch (dist * 2 + (rp ? 1 : 0)) {
       case 0: PS_PICK(DIST_GAUSSIAN, false)
       case 1: PS_PICK(DIST_GAUSSIAN, true)
@@ -474,13 +496,13 @@ ps_status sort_stage(ps_ctx* ctx, const ps_problem& p, const D* d_a, const D* d_
                                  p.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     if (!p.on_device) ctx->tm.h2d_bytes += total * sizeof(int);
   } else if (n <= ps::SORT_SMALL_MAX) {
-    // small instances: keys + all digit passes + gather fused in one kernel, one CTA per instance
+    // small instances: keys + bitonic sort of (key, index) + gather fused in one kernel, one CTA per instance
     using U = typename ps::SortKey<D>::U;
-    const size_t smem = 2 * (size_t)n * (sizeof(U) + sizeof(int));
+    const size_t smem = (size_t)ps::sort_small_pow2(n) * (sizeof(U) + sizeof(int));
     auto kfn = ps::sort_small_kernel<D>;
     if (smem > 48 * 1024)
       PS_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kfn<<<R, ps::SORT_THREADS, smem, st>>>(n, d_a, d_b, d_perm, (D*)ctx->a_s.p, (D*)ctx->b_s.p);
+    kfn<<<R, ps::SORT_SMALL_THREADS, smem, st>>>(n, d_a, d_b, d_perm, (D*)ctx->a_s.p, (D*)ctx->b_s.p);
     ctx->launches++;
     PS_CUDA(ctx, cudaGetLastError());
     return PS_OK;
@@ -819,7 +841,11 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   const bool use_x2 = (sizeof(D) == 4) && fast && running && p.dist == PS_DIST_POISSON && p.no_fast_math != 2 && !comm &&
                       !screen_run32 &&  // the screened levels have their own 128-row geometry
                       (long long)n * R >= 16384;
-  int L = choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
+  // small geometry (SMALL_ROWS above) while 128-row tiles would leave most SMs without work
+  const long long nrb128 = cdiv(n, BR);
+  const bool small = !comm && !screen && !screen_run && !screen_run32 && !use_x2 && fast && p.chunk_len <= 0 && n > SMALL_ROWS &&
+                     (long long)R * nrb128 * (nrb128 + 1) / 2 < 4LL * ctx->sm_count;
+  int L = small ? SMALL_ROWS : choose_chunk(n, R, p.chunk_len, use_x2 ? 2 * BR : BR);
   // screened levels: most tiles are dropped whole by the tile tier, so finer tiles pay (measured: 512 at n = 1e5);
   // at most ~200 chunks so that the per-chunk partials stay small
   if ((screen || screen_run || screen_run32) && p.chunk_len <= 0) L = std::min(L, std::max(512, cdiv(cdiv(n, 200), BR) * BR));
@@ -899,7 +925,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
       d_SA = (D*)bufA.p;
       d_SB = (D*)bufB.p;
     }
-    if (!comm) {
+    if (small) {
+      static_assert(SMALL_ROWS == 32, "level1_running_small_kernel: one warp per row block, chunk length 32");
+      ps::level1_running_small_kernel<D><<<dim3((cdiv(n, SMALL_ROWS) + 1) / 2, R), SMALL_ROWS, 0, st>>>(
+          n, sa_nch, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
+          cdiv(n, SMALL_ROWS));
+    } else if (!comm) {
       ps::level1_running_kernel<D, BR><<<dim3((cdiv(n, BR) + 1) / 2, R), BR, 0, st>>>(
           n, sa_L, sa_nch, rec_stride, p.dist, rp, rec0, d_SA, d_SB, d_ms + n, d_ns + n, table_stride, rec1,
           0, 1, nullptr, cdiv(n, BR));
@@ -966,6 +997,11 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   auto fn = LevelLaunch<D>::pick(p.dist, rp, running, fast);
   // float Poisson on the fast path: two rows per thread, packed f32x2 pipeline, 256-row tiles
   int tile_rows = BR;
+  int tile_threads = BR;
+  if (small) {
+    tile_rows = tile_threads = SMALL_ROWS;
+    fn = LevelLaunch<D>::pick_small(p.dist, rp, running);
+  }
   if constexpr (sizeof(D) == 4) {
     if (use_x2) {
       tile_rows = 2 * BR;
@@ -1027,7 +1063,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (j == Tc && Tc >= 2) {
       // last level: row 0 only -> k-parallel kernel, one CTA per chunk (128-row geometry)
       // sharded: row 0 (and its running-sum checkpoints) belongs to rank 0; its value travels like every other level's
-      g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, BR);
+      g = make_geom(n, j, Tc, L, nch_alloc, 0, 1, small ? SMALL_ROWS : BR);
       g.sa_mul = L / sa_L;
       g.sa_nch = sa_nch;
       if (!comm || rb_first == 0) fn_last<<<dim3(g.NCH, R), 128, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
@@ -1140,7 +1176,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
           PS_TRY(mark(ctx, &cnt_ev[j]));
         }
       } else if (g.ntiles > 0) {
-        fn<<<dim3(g.ntiles, R), BR, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
+        fn<<<dim3(g.ntiles, R), tile_threads, 0, st>>>(g, rin, d_SA, d_SB, d_pv, d_pa);
       }
     }
     const bool sharded_level = comm != nullptr;
@@ -1190,9 +1226,36 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   PS_TRY(mark(ctx, &e_bt));
 
   // ---- outputs
+  // Small results for host callers travel through one pinned staging buffer: a device-to-pageable copy blocks the host for
+  // ~12 us each (three of them were 39 of the 245 us of a C1 solve), copies into pinned memory queue behind the kernels and
+  // cost one synchronisation together; the host then moves the bytes to the caller's arrays.
+  struct Staged {
+    void* dst;
+    size_t off, bytes;
+  };
+  std::vector<Staged> staged;
+  size_t staged_bytes = 0;
+  {
+    auto want = [&](const void* dst, size_t bytes) { return dst ? ((bytes + 15) & ~(size_t)15) : 0; };
+    const size_t need = want(res->perm, total * sizeof(int)) + want(res->bounds, (size_t)R * nS * (Tc + 1) * sizeof(int)) +
+                        want(res->subset_scores, (size_t)R * nS * Tc * sizeof(D)) +
+                        want(res->max_score, R * table_stride * sizeof(D)) +
+                        want(res->next_start, R * table_stride * sizeof(int));
+    if (!p.on_device && need > 0 && need <= PINNED_OUT_BYTES) {
+      if (!ctx->pinned_out) PS_CUDA(ctx, cudaMallocHost((void**)&ctx->pinned_out, PINNED_OUT_BYTES));
+      staged.reserve(5);
+    }
+  }
+  const bool stage_out = staged.capacity() > 0;
   auto copy_out = [&](void* dst, const void* src, size_t bytes) -> ps_status {
     if (!dst) return PS_OK;
-    PS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, out_kind, st));
+    if (stage_out) {
+      PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_out + staged_bytes, src, bytes, cudaMemcpyDeviceToHost, st));
+      staged.push_back({dst, staged_bytes, bytes});
+      staged_bytes += (bytes + 15) & ~(size_t)15;
+    } else {
+      PS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, out_kind, st));
+    }
     if (!p.on_device) ctx->tm.d2h_bytes += bytes;
     return PS_OK;
   };
@@ -1205,6 +1268,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   PS_TRY(mark(ctx, &e_end));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
+  for (const Staged& sg : staged) memcpy(sg.dst, ctx->pinned_out + sg.off, sg.bytes);
   if (ctx->dbg_level && screen && ctx->dbg.p) {
     const size_t cnt = (size_t)R * nch_alloc * nsub * cdiv(n, BR) * 4;
     std::vector<unsigned long long> h(cnt);
@@ -1638,6 +1702,7 @@ void ps_destroy(ps_ctx* ctx) {
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
+  if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
   if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
   if (ctx->pinned_levels) cudaFreeHost(ctx->pinned_levels);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -400,14 +400,6 @@ struct LiveHdr {
 };
 constexpr int SCR_MAX_G = 32;  // stages per tile: the live-stage mask of a tile is one 32-bit word
 
-// global -> shared copies that bypass the register file (the exact-arithmetic records of a stage: 32 B per k for double data)
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // One live tile: group and cell tiers on the live stages, partials to part_val / part_arg.
 template <typename D, int DIST, bool RP, bool AUDIT, int BR>
 __device__ __forceinline__ void screen_live_tile(const Geom& g, const int inst, const int rb, const int slot,

@@ -19,4 +19,16 @@ $N -k regex:level_live_screen_kernel -s 21 -c 1 -o $O/live_f32_final -f $B1 --dt
 $N -k regex:level_live_screen_run_kernel -s 31 -c 1 -o $O/live_run_f64_final -f python tools/run_c3r.py time > $O/ncu_c.log 2>&1
 $N -k regex:level_live_screen_run32_kernel -s 31 -c 1 -o $O/live_run_f32_final -f python tools/run_c3r.py time f32 > $O/ncu_d.log 2>&1
 $N -k regex:level1_running_kernel -s 2 -c 1 -o $O/level1_run_f32_final -f python tools/run_c3r.py time f32 > $O/ncu_e.log 2>&1
-cat $O/c3r_f64.log $O/c3r_f32.log
+# the five reports are 24 MB each and gpurun brings back at most 64 MiB: fold them here, keep the raw pages as csv and one report
+mkdir -p $O/ncu_raw
+for k in live_f64 live_f32 live_run_f64 live_run_f32 level1_run_f32; do
+  ncu -i $O/${k}_final.ncu-rep --page raw --csv > $O/ncu_raw/${k}.csv 2>/dev/null
+done
+ncu -i $O/live_f64_final.ncu-rep --page source --csv > $O/ncu_raw/live_f64_source.csv 2>/dev/null
+cp profiles/level_kernel_summary.json $O/level_kernel_summary.before.json
+python tools/ncu_summary.py live_f64=$O/live_f64_final.ncu-rep live_f32=$O/live_f32_final.ncu-rep \
+  live_run_f64=$O/live_run_f64_final.ncu-rep live_run_f32=$O/live_run_f32_final.ncu-rep \
+  level1_run_f32=$O/level1_run_f32_final.ncu-rep:5000050000 > $O/ncu_summary.log 2>&1
+cp profiles/level_kernel_summary.json $O/level_kernel_summary.json
+rm -f $O/live_f32_final.ncu-rep $O/live_run_f64_final.ncu-rep $O/live_run_f32_final.ncu-rep $O/level1_run_f32_final.ncu-rep
+cat $O/c3r_f64.log $O/c3r_f32.log $O/ncu_summary.log
