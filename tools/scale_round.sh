@@ -12,7 +12,7 @@ $T tools/shard_check.py --size 1000000 --parts 32 --check > $O/scale_n${N}_shard
 $T tools/shard_check.py --size 1000000 --parts 32 --data real --check > $O/scale_n${N}_shard_real.log 2>&1
 LD_LIBRARY_PATH=partitionsolvers_b200/_lib:$LD_LIBRARY_PATH partitionsolvers_b200/_lib/test_facade > $O/scale_n${N}_facade.log 2>&1
 python -m pytest tests/test_gpu_shard.py -x -q > $O/scale_n${N}_shard_tests.log 2>&1
-tail -3 $O/scale_n${N}_shard_counts.log $O/scale_n${N}_shard_real.log $O/scale_n${N}_facade.log $O/scale_n${N}_shard_tests.log
+tail -n 3 $O/scale_n${N}_shard_counts.log $O/scale_n${N}_shard_real.log $O/scale_n${N}_facade.log $O/scale_n${N}_shard_tests.log
 python - <<EOF
 import json
 d = json.loads(open("$O/scale_n${N}_bench.json").read().strip().splitlines()[-1])
