@@ -149,6 +149,11 @@ ps_status ps_stream_wait(ps_ctx* ctx, uintptr_t other_stream);
 
 /* One call = the whole constructor of DPSolver<D>: sort_by_priority, range scores, the T-level DP
  * fill and the backtrace(s) (DP_impl.hpp:69-153,200-230).  Blocking. */
+/* Small solves from host buffers (n <= 4096, below the screening threshold, device sort, RUNNING sums, inputs <= 256 KB):
+ * the second solve of a shape on a context is recorded as a CUDA graph and later ones replay it -- one graph launch instead of
+ * ~45 runtime calls (n = 1000, T = 5: 0.23 -> 0.145 ms per call).  Results are identical; ps_timings of a replayed solve
+ * carries total_ms, kernel_launches and the byte counts only.  A replay whose inputs fail the safe-range / positivity
+ * precheck is redone on the general-math kernels.  PS_NO_GRAPH=1 in the environment at ps_create time switches this off. */
 ps_status ps_solve_f32(ps_ctx* ctx, const ps_problem* p, const float* a, const float* b, ps_result* r);
 ps_status ps_solve_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, ps_result* r);
 

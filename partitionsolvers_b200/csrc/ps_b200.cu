@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -37,6 +39,23 @@ struct DevBuf {
 };
 
 }  // namespace
+
+// Output of a solve staged in pinned memory: which ps_result field, where in the staging buffer, how many bytes.
+struct StagedOut {
+  int field;  // 0 perm, 1 bounds, 2 subset_scores, 3 max_score, 4 next_start
+  size_t off, bytes;
+};
+// A small solve recorded as a CUDA graph (one cudaGraphLaunch instead of ~45 runtime calls), keyed by everything that shapes
+// the sequence of launches.
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long epoch = 0;  // ps_ctx::alloc_epoch at capture time
+  std::vector<StagedOut> staged;
+  long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  int poisson = 0;  // the recorded solve assumed a > 0 as well as the safe range
+  int seen = 0;     // eager solves seen with this key (the second one is recorded)
+  int failed = 0;   // capture failed once: stay eager
+};
 
 struct ps_ctx {
   int device = 0;
@@ -62,6 +81,13 @@ struct ps_ctx {
   DevBuf dbg;
   int sm_count = 148;
   cudaEvent_t wait_event = nullptr;  // ps_stream_wait
+  // small solves replayed from CUDA graphs (solve_small_graph below)
+  unsigned long long alloc_epoch = 0;  // bumped whenever a workspace is reallocated: graphs hold the old pointers
+  bool capturing = false;              // solve_impl is being recorded into a graph: no events, no syncs, no host reads
+  std::vector<StagedOut> cap_staged;   // outputs of the recorded solve inside pinned_out
+  unsigned char* pinned_in = nullptr;  // inputs of a replayed solve (PINNED_IN_BYTES)
+  std::map<std::array<long long, 12>, GraphEntry> graphs;
+  int graphs_enabled = 1;              // PS_NO_GRAPH=1 switches the replay off
 };
 
 // NCCL is bound at run time: a host that already carries an NCCL (PyTorch bundles its own libnccl.so.2) keeps exactly one
@@ -133,6 +159,11 @@ namespace {
 
 ps_status ensure(ps_ctx* ctx, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return PS_OK;
+  if (ctx->capturing) {  // a recorded solve must find every workspace in place (the eager solve before it sized them)
+    ctx->err = "graph capture: a workspace would have to grow";
+    return PS_ERR_CUDA;
+  }
+  ctx->alloc_epoch++;
   if (b.p) {
     PS_CUDA(ctx, cudaFree(b.p));
     b.p = nullptr;
@@ -155,6 +186,10 @@ ps_status ensure(ps_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 ps_status mark(ps_ctx* ctx, cudaEvent_t* out) {
+  if (ctx->capturing) {  // timings of a replayed solve come from two events around the graph launch
+    *out = nullptr;
+    return PS_OK;
+  }
   if (ctx->ev_used == ctx->events.size()) {
     cudaEvent_t e;
     PS_CUDA(ctx, cudaEventCreate(&e));
@@ -167,6 +202,12 @@ ps_status mark(ps_ctx* ctx, cudaEvent_t* out) {
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+void scatter_staged(const ps_ctx* ctx, const std::vector<StagedOut>& staged, const ps_result* res) {
+  void* dst[5] = {res->perm, res->bounds, res->subset_scores, res->max_score, res->next_start};
+  for (const StagedOut& sg : staged)
+    if (dst[sg.field]) memcpy(dst[sg.field], ctx->pinned_out + sg.off, sg.bytes);
+}
 
 NcclApi& nccl_api() {
   static NcclApi api = [] {
@@ -791,8 +832,12 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   int fast = 0, screen = 0, screen_run = 0, screen_run32 = 0;
   const int cp_rows = n / ps::SCR_BLOCK + 1;  // float running-sum screen: one checkpoint row per 128-block boundary
   if (want_fast) {  // the precheck ran right after the inputs arrived; its flags are on the host by now
-    PS_CUDA(ctx, cudaEventSynchronize(e_flags));
-    host_flags = *ctx->pinned_flags;
+    if (ctx->capturing) {
+      host_flags = 0;  // recorded for inputs that pass the precheck; every replay verifies the flags it produced
+    } else {
+      PS_CUDA(ctx, cudaEventSynchronize(e_flags));
+      host_flags = *ctx->pinned_flags;
+    }
     fast = ((host_flags & 1) == 0) && (p.dist != PS_DIST_POISSON || (host_flags & 2) == 0);
     // screening needs positive sums for every score (relative error of the float range sums) and exact summability
     screen = want_screen && fast && (host_flags & 2) == 0 && (host_flags & 4) == 0;
@@ -1073,7 +1118,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
         g.NCH = nch;
       }
     } else {
-      if (!(screened_level || screen_run || screen_run32) && (long long)g.ntiles * R >= 2048) {
+      if (!(screened_level || screen_run || screen_run32) && (long long)g.ntiles * R >= 2048 && !ctx->capturing) {
         // tile -> (row block, chunk) table (one per geometry, shared by the instances of a batch), rebuilt only when the
         // geometry changes (kmax shrinks by one per level)
         if (ctx->map_key[0] != g.NCH || ctx->map_key[1] != g.G || ctx->map_key[2] != g.NRB ||
@@ -1229,11 +1274,7 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
   // Small results for host callers travel through one pinned staging buffer: a device-to-pageable copy blocks the host for
   // ~12 us each (three of them were 39 of the 245 us of a C1 solve), copies into pinned memory queue behind the kernels and
   // cost one synchronisation together; the host then moves the bytes to the caller's arrays.
-  struct Staged {
-    void* dst;
-    size_t off, bytes;
-  };
-  std::vector<Staged> staged;
+  std::vector<StagedOut> staged;
   size_t staged_bytes = 0;
   {
     auto want = [&](const void* dst, size_t bytes) { return dst ? ((bytes + 15) & ~(size_t)15) : 0; };
@@ -1247,11 +1288,15 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     }
   }
   const bool stage_out = staged.capacity() > 0;
-  auto copy_out = [&](void* dst, const void* src, size_t bytes) -> ps_status {
+  if (ctx->capturing && !stage_out) {
+    ctx->err = "graph capture: results do not fit the staging buffer";
+    return PS_ERR_CUDA;
+  }
+  auto copy_out = [&](int field, void* dst, const void* src, size_t bytes) -> ps_status {
     if (!dst) return PS_OK;
     if (stage_out) {
       PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_out + staged_bytes, src, bytes, cudaMemcpyDeviceToHost, st));
-      staged.push_back({dst, staged_bytes, bytes});
+      staged.push_back({field, staged_bytes, bytes});
       staged_bytes += (bytes + 15) & ~(size_t)15;
     } else {
       PS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, out_kind, st));
@@ -1259,16 +1304,21 @@ ps_status solve_impl(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, 
     if (!p.on_device) ctx->tm.d2h_bytes += bytes;
     return PS_OK;
   };
-  PS_TRY(copy_out(res->perm, ctx->perm.p, total * sizeof(int)));
-  PS_TRY(copy_out(res->bounds, d_bounds, (size_t)R * nS * (Tc + 1) * sizeof(int)));
-  PS_TRY(copy_out(res->subset_scores, d_scores, (size_t)R * nS * Tc * sizeof(D)));
-  PS_TRY(copy_out(res->max_score, d_ms, R * table_stride * sizeof(D)));
-  PS_TRY(copy_out(res->next_start, d_ns, R * table_stride * sizeof(int)));
+  PS_TRY(copy_out(0, res->perm, ctx->perm.p, total * sizeof(int)));
+  PS_TRY(copy_out(1, res->bounds, d_bounds, (size_t)R * nS * (Tc + 1) * sizeof(int)));
+  PS_TRY(copy_out(2, res->subset_scores, d_scores, (size_t)R * nS * Tc * sizeof(D)));
+  PS_TRY(copy_out(3, res->max_score, d_ms, R * table_stride * sizeof(D)));
+  PS_TRY(copy_out(4, res->next_start, d_ns, R * table_stride * sizeof(int)));
   if (screen || screen_run || screen_run32)
     PS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned_flags + 2, d_cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   PS_TRY(mark(ctx, &e_end));
+  if (ctx->capturing) {  // recorded, not run: the replay copies the results out and fills the timings
+    ctx->cap_staged = staged;
+    ctx->tm.kernel_launches = ctx->launches;
+    return PS_OK;
+  }
   PS_CUDA(ctx, cudaStreamSynchronize(st));
-  for (const Staged& sg : staged) memcpy(sg.dst, ctx->pinned_out + sg.off, sg.bytes);
+  scatter_staged(ctx, staged, res);
   if (ctx->dbg_level && screen && ctx->dbg.p) {
     const size_t cnt = (size_t)R * nch_alloc * nsub * cdiv(n, BR) * 4;
     std::vector<unsigned long long> h(cnt);
@@ -1637,6 +1687,114 @@ ps_status shard_subset_scores_impl(ps_shard* s, int count, const int* bounds, D*
 }  // namespace
 
 // =================================================================================== C ABI
+namespace {
+
+constexpr size_t PINNED_IN_BYTES = 256 * 1024;
+
+// Small solves from host buffers, replayed from a CUDA graph.  Such a solve is ~16 kernels of a few microseconds each and ~45
+// runtime calls (launches, event records, copies); the host's call rate, not the device, sets its latency.  The first solve
+// of a shape runs eagerly (it sizes the workspaces), the second is recorded by running solve_impl under stream capture
+// (no events, no synchronisation, the device flags assumed to pass), and from then on a solve is: copy a, b into pinned
+// memory, ONE cudaGraphLaunch, one synchronisation, copy the results out of pinned memory.  The only data-dependent host
+// decision of these shapes is the safe-range / positivity precheck (math_fast.cuh); the recorded graph still computes the
+// flags, and a replay whose flags would have sent the eager solve down another path is discarded and redone eagerly.
+// A graph holds workspace pointers: any reallocation (ps_ctx::alloc_epoch) retires it.
+template <typename D>
+ps_status solve_small_graph(ps_ctx* ctx, const ps_problem* pp, const D* a, const D* b, ps_result* res) {
+  if (!ctx || !pp || !a || !b || !res || !ctx->graphs_enabled) return solve_impl<D>(ctx, pp, a, b, res);
+  const ps_problem& p = *pp;
+  const long long n = p.n, R = p.batch;
+  const long long nrb128 = (n + BR - 1) / BR;
+  const size_t in_bytes = (size_t)(R * n) * sizeof(D);
+  const bool eligible = n > SMALL_ROWS && n <= ps::SORT_SMALL_MAX && R >= 1 && p.T >= 1 && !p.on_device && !p.perm &&
+                        p.sort_mode != PS_SORT_GIVEN && p.sum_mode == PS_SUM_RUNNING && p.no_fast_math == 0 &&
+                        p.chunk_len <= 0 && p.screen >= 0 && p.screen <= 2 && p.dist >= 0 && p.dist <= 2 &&
+                        !ctx->dbg_level && 2 * in_bytes <= PINNED_IN_BYTES &&
+                        R * nrb128 * (nrb128 + 1) / 2 < 4LL * ctx->sm_count &&
+                        // below the screening threshold of solve_impl (want_screen)
+                        (p.screen == 1 || std::min<long long>(p.T, n) < 3 || n < 512 || n * R < 6000);
+  if (!eligible) return solve_impl<D>(ctx, pp, a, b, res);
+  const std::array<long long, 12> key = {(long long)sizeof(D), n, p.T, p.dist, p.risk_part ? 1 : 0, p.sweep ? 1 : 0, R,
+                                         (res->perm ? 1 : 0) | (res->bounds ? 2 : 0) | (res->subset_scores ? 4 : 0) |
+                                             (res->max_score ? 8 : 0) | (res->next_start ? 16 : 0),
+                                         p.screen, 0, 0, 0};
+  if (ctx->graphs.size() >= 256 && !ctx->graphs.count(key)) {  // a caller that sweeps over many shapes: start over
+    for (auto& kv : ctx->graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ctx->graphs.clear();
+  }
+  GraphEntry& ge = ctx->graphs[key];
+  if (ge.exec && ge.epoch != ctx->alloc_epoch) {  // a workspace moved since the recording
+    cudaGraphExecDestroy(ge.exec);
+    ge.exec = nullptr;
+    ge.seen = 1;
+  }
+  if (!ge.exec) {
+    if (ge.failed || ge.seen == 0) {
+      ge.seen++;
+      return solve_impl<D>(ctx, pp, a, b, res);
+    }
+    // second solve of this shape: record it
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return solve_impl<D>(ctx, pp, a, b, res);
+    if (!ctx->pinned_in && cudaMallocHost((void**)&ctx->pinned_in, PINNED_IN_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      ge.failed = 1;
+      return solve_impl<D>(ctx, pp, a, b, res);
+    }
+    const D* pa = reinterpret_cast<const D*>(ctx->pinned_in);
+    const D* pb = reinterpret_cast<const D*>(ctx->pinned_in + in_bytes);
+    cudaGraph_t graph = nullptr;
+    ps_status st = PS_ERR_CUDA;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      ctx->capturing = true;
+      st = solve_impl<D>(ctx, pp, pa, pb, res);
+      ctx->capturing = false;
+      if (cudaStreamEndCapture(ctx->stream, &graph) != cudaSuccess) st = PS_ERR_CUDA;
+    }
+    if (st == PS_OK && graph && cudaGraphInstantiate(&ge.exec, graph, 0) != cudaSuccess) {
+      ge.exec = nullptr;
+      st = PS_ERR_CUDA;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (st != PS_OK || !ge.exec) {
+      cudaGetLastError();
+      ge.failed = 1;
+      ge.exec = nullptr;
+      return solve_impl<D>(ctx, pp, a, b, res);
+    }
+    ge.epoch = ctx->alloc_epoch;
+    ge.staged = ctx->cap_staged;
+    ge.launches = ctx->tm.kernel_launches;
+    ge.h2d_bytes = ctx->tm.h2d_bytes;
+    ge.d2h_bytes = ctx->tm.d2h_bytes;
+    ge.poisson = p.dist == PS_DIST_POISSON;
+  }
+  // replay
+  ctx->err.clear();
+  PS_CUDA(ctx, cudaSetDevice(ctx->device));
+  memcpy(ctx->pinned_in, a, in_bytes);
+  memcpy(ctx->pinned_in + in_bytes, b, in_bytes);
+  ctx->ev_used = 0;
+  cudaEvent_t e0, e1;
+  PS_TRY(mark(ctx, &e0));
+  PS_CUDA(ctx, cudaGraphLaunch(ge.exec, ctx->stream));
+  PS_TRY(mark(ctx, &e1));
+  PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int flags = *ctx->pinned_flags;
+  if ((flags & 1) || (ge.poisson && (flags & 2)))  // these inputs take the general-math kernels: solve them eagerly
+    return solve_impl<D>(ctx, pp, a, b, res);
+  scatter_staged(ctx, ge.staged, res);
+  memset(&ctx->tm, 0, sizeof(ctx->tm));
+  cudaEventElapsedTime(&ctx->tm.total_ms, e0, e1);
+  ctx->tm.kernel_launches = ge.launches;
+  ctx->tm.h2d_bytes = ge.h2d_bytes;
+  ctx->tm.d2h_bytes = ge.d2h_bytes;
+  ctx->last_fast = 1;
+  return PS_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int ps_abi_version(void) { return PS_B200_ABI_VERSION; }
@@ -1679,6 +1837,7 @@ ps_status ps_create(ps_ctx** out, int device) {
   }
   memset(&ctx->tm, 0, sizeof(ctx->tm));
   if (const char* e = getenv("PS_DEBUG_LEVEL")) ctx->dbg_level = atoi(e);
+  if (const char* e = getenv("PS_NO_GRAPH")) ctx->graphs_enabled = (atoi(e) == 0);
   {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
@@ -1689,7 +1848,10 @@ ps_status ps_create(ps_ctx** out, int device) {
 
 void ps_destroy(ps_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  if (cudaSetDevice(ctx->device) == cudaErrorCudartUnloading) {  // process exit after the runtime went away: nothing to free
+    delete ctx;
+    return;
+  }
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->a_in,  &ctx->b_in,     &ctx->key_in,   &ctx->key_out, &ctx->idx_in, &ctx->perm,
                     &ctx->a_s,   &ctx->b_s,      &ctx->rec,      &ctx->SA,      &ctx->SB,     &ctx->part_val,
@@ -1703,6 +1865,9 @@ void ps_destroy(ps_ctx* ctx) {
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
   if (ctx->pinned_out) cudaFreeHost(ctx->pinned_out);
+  if (ctx->pinned_in) cudaFreeHost(ctx->pinned_in);
+  for (auto& kv : ctx->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
   if (ctx->pinned_levels) cudaFreeHost(ctx->pinned_levels);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1732,10 +1897,10 @@ ps_status ps_stream_wait(ps_ctx* ctx, uintptr_t other_stream) {
 }
 
 ps_status ps_solve_f32(ps_ctx* ctx, const ps_problem* p, const float* a, const float* b, ps_result* r) {
-  return solve_impl<float>(ctx, p, a, b, r);
+  return solve_small_graph<float>(ctx, p, a, b, r);
 }
 ps_status ps_solve_f64(ps_ctx* ctx, const ps_problem* p, const double* a, const double* b, ps_result* r) {
-  return solve_impl<double>(ctx, p, a, b, r);
+  return solve_small_graph<double>(ctx, p, a, b, r);
 }
 
 // ---- multi-GPU: the library drives NCCL itself, on the context's stream

@@ -65,3 +65,61 @@ def test_small_batches_and_sweep(oracle, ctx):
         one = ctx.solve_raw(a[r], b[r], T, 1, True, dtype=np.float32, levels=True, sweep=True, chunk_len=128)
         for k in ("perm", "max_score", "next_start", "bounds", "subset_scores"):
             assert np.array_equal(raw[k][r], one[k]), (r, k)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_repeated_small_solves_replay_a_graph_with_the_same_results(oracle, dt):
+    """The second solve of a shape is recorded as a CUDA graph and every later one replays it (ps_b200.cu:
+    solve_small_graph): different data through the same graph must give what an eager context gives, tables included."""
+    eager = capi.Context(0)
+    g = capi.Context(0)
+    n, T = 1500, 5
+    launches = []
+    for rep in range(5):
+        for dist, rp in ((1, False), (2, False), (0, True)):
+            a, b = synth.gaussian_mixture(n, 4, seed=700 + rep, dtype=dt)
+            if dist == 1:
+                a = np.maximum(a, dt(0.5))
+            got = g.solve_raw(a, b, T, dist, rp, dtype=dt, levels=True, sweep=True)
+            launches.append(g.timings()["kernel_launches"])
+            # the eager side: a user-given chunk length is never recorded (and takes the 128-row geometry)
+            want = eager.solve_raw(a, b, T, dist, rp, dtype=dt, levels=True, sweep=True, chunk_len=128)
+            for k in ("perm", "max_score", "next_start", "bounds", "subset_scores"):
+                assert np.array_equal(got[k], want[k]), (rep, dist, k)
+            ref = oracle.solve("port", a, b, T, dist, rp, dtype=dt)
+            if np.array_equal(got["perm"], ref["perm"]):  # tied priorities: the port's order may differ from the stable one
+                assert np.array_equal(got["max_score"], ref["max_score"]), (rep, dist)
+                assert np.array_equal(got["next_start"], ref["next_start"]), (rep, dist)
+    assert min(launches) > 0
+
+
+def test_graph_replay_falls_back_when_the_precheck_fails(oracle):
+    """A recorded solve assumes the inputs pass the safe-range / positivity precheck; a replay on data that does not (a <= 0
+    under the Poisson score, a value outside the safe range) must be redone on the general-math kernels."""
+    g = capi.Context(0)
+    n, T, dt = 900, 4, np.float64
+    a, b = synth.uniform_ab(n, seed=11, dtype=dt)
+    for _ in range(3):
+        g.solve_raw(a, b, T, 2, False, dtype=dt, levels=True)  # records and replays
+    a2 = a.copy()
+    a2[10] = 1e-40  # outside the safe range of the branch-free math path
+    got = g.solve_raw(a2, b, T, 2, False, dtype=dt, levels=True)
+    ref = oracle.solve("port", a2, b, T, 2, False, dtype=dt)
+    assert np.array_equal(got["max_score"], ref["max_score"]) and np.array_equal(got["next_start"], ref["next_start"])
+    # ... and the graph is still good for the next well-behaved input
+    got = g.solve_raw(a, b, T, 2, False, dtype=dt, levels=True)
+    ref = oracle.solve("port", a, b, T, 2, False, dtype=dt)
+    assert np.array_equal(got["max_score"], ref["max_score"]) and np.array_equal(got["next_start"], ref["next_start"])
+
+
+def test_graphs_survive_workspace_growth():
+    """A larger solve in between reallocates workspaces; recorded graphs hold the old pointers and must be retired."""
+    g = capi.Context(0)
+    a, b = synth.poisson_planted(800, 4, seed=21, dtype=np.float32)
+    first = [g.solve_raw(a, b, 4, 1, True, dtype=np.float32, levels=True) for _ in range(3)]
+    A, B = synth.poisson_planted(30000, 4, seed=22, dtype=np.float32)
+    g.solve_raw(A, B, 4, 1, True, dtype=np.float32)
+    again = [g.solve_raw(a, b, 4, 1, True, dtype=np.float32, levels=True) for _ in range(3)]
+    for r in first + again:
+        for k in ("perm", "max_score", "next_start", "bounds", "subset_scores"):
+            assert np.array_equal(r[k], first[0][k]), k
