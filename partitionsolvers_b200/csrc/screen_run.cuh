@@ -357,7 +357,7 @@ __device__ __forceinline__ void screen_run_live_tile(const Geom& g, const int rb
                                                      const FxInfo& F, const double* __restrict__ SA,
                                                      const double* __restrict__ SB, const double* __restrict__ LB,
                                                      double* __restrict__ part_val, int* __restrict__ part_arg,
-                                                     unsigned long long* __restrict__ counters, const bool mono_in,
+                                                     unsigned long long* __restrict__ counters, const int mono_in,
                                                      float4 (*sbuf)[BR], float (*s_pmax)[BR / 32],
                                                      const GlogEntry* __restrict__ s_log) {
   using D = double;
@@ -382,7 +382,7 @@ __device__ __forceinline__ void screen_run_live_tile(const Geom& g, const int rb
   float thr = thr0;
   unsigned int nexact = 0, nviol = 0;
   const bool forced = i0 < F.ipos;  // (F4) a row of this block may own non-positive sums: no bounds, every cell exactly
-  const bool mono = mono_in && !forced;
+  const int mono = forced ? 0 : mono_in;  // range-tier mode (screen_range_ub)
 
   // the reference's running sums of row i through cell kw (warp-uniform kw); a tile right of the diagonal starts from the
   // checkpoint the level-1 pass left at its chunk boundary (loaded on first use)
@@ -510,7 +510,7 @@ __device__ __forceinline__ void screen_run_live_tile(const Geom& g, const int rb
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[buf][w]);
         const float4 re = sb[BK - 1], rf = sb[0];
         const float ubs = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
-                                                    __fadd_rn(re.y, by), pmx);
+                                                    __fadd_rn(re.y, by), pmx, mono);
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
       if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
@@ -527,7 +527,7 @@ __device__ __forceinline__ void screen_run_live_tile(const Geom& g, const int rb
             for (int q = 0; q < GQ; ++q) {
               const float4 re = sb[kq + q * U + U - 1], rf = sb[kq + q * U];
               ubg[q] = screen_range_ub<DIST, RP>(__fadd_rn(rf.x, bx), __fadd_rn(rf.y, by), __fadd_rn(re.x, bx),
-                                                 __fadd_rn(re.y, by), re.z);
+                                                 __fadd_rn(re.y, by), re.z, mono);
             }
             keepm = 0;
 #pragma unroll
@@ -632,7 +632,8 @@ level_live_screen_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, const
   if (kLogTab) {
     if (threadIdx.x < 128) s_log[threadIdx.x] = g_glog_tab[threadIdx.x];
   }
-  const bool mono = BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0));
+  const bool sorted = dev_flags && (dev_flags[1] == 0);
+  const int mono = BOX ? (sorted ? 2 : 1) : (((FRONTIER || GROUPB) && sorted) ? 1 : 0);  // range-tier mode (screen_range_ub)
   const long long pstride = (long long)g.nch_alloc * g.nsub * g.n;  // partial slots
   const long long sstride = (long long)g.nch_alloc * g.n;           // SA / SB checkpoints
   const int tid = threadIdx.x;

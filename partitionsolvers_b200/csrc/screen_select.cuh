@@ -120,6 +120,7 @@ screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restric
   const float* cpB = (SRC == SEL_RUN32) ? src.cpB + inst * src.cp_stride : nullptr;
   const float thr = screen_rd<D>(LB[min(il, max(g.nrows - 1, 0))]);
   const bool mono = !no_bounds && (BOX || ((FRONTIER || GROUPB) && dev_flags && (dev_flags[1] == 0)));
+  const int rmode = (BOX && dev_flags && (dev_flags[1] == 0)) ? 2 : 1;  // Poisson risk-part: hull bound on ascending priorities
   const bool row_ok = i < g.nrows;
   if (kbest) {
     // the chunk of the row's best sample; the row maximum and the cells that survive the bounds lie around it
@@ -160,7 +161,7 @@ screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restric
     if constexpr (SRC == SEL_RUN32)
       return run32_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm, (float)(span + 8), (float)(k_last - i));
     else
-      return screen_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm);
+      return screen_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm, rmode);
   };
   auto bound_at = [&](const int k_last) -> bool {  // can a bound be formed at k_last for every row of the block?
     return SRC != SEL_RUN32 || ((k_last % SCR_BLOCK) == 0 && k_last >= i0 + BR);
