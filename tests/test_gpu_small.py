@@ -123,3 +123,33 @@ def test_graphs_survive_workspace_growth():
     for r in first + again:
         for k in ("perm", "max_score", "next_start", "bounds", "subset_scores"):
             assert np.array_equal(r[k], first[0][k]), k
+
+
+def test_random_small_shapes_graph_replay_equals_eager():
+    """Randomised: 40 shapes (n, T, score, objective, precision, sweep, batch), each solved three times with fresh data on a
+    context that records / replays graphs and on one created with PS_NO_GRAPH=1 -- every output array must be identical."""
+    import os
+    os.environ["PS_NO_GRAPH"] = "1"
+    try:
+        eager = capi.Context(0)
+    finally:
+        del os.environ["PS_NO_GRAPH"]
+    g = capi.Context(0)
+    rs = np.random.RandomState(2024)
+    for case in range(40):
+        n = int(rs.choice([33, 64, 100, 257, 700, 1024, 1500, 2089, 3000, 4096]))
+        T = int(rs.randint(1, 9))
+        dist, rp = [(1, False), (1, True), (0, False), (0, True), (2, False)][rs.randint(5)]
+        dt = np.float32 if rs.rand() < 0.5 else np.float64
+        sweep = bool(rs.rand() < 0.4)
+        R = int(rs.choice([1, 1, 1, 2, 3]))
+        for rep in range(3):
+            b = rs.uniform(0.5, 50.0, (R, n)) if rs.rand() < 0.5 else rs.poisson(30, (R, n)).clip(1).astype(np.float64)
+            a = rs.uniform(0.5, 50.0, (R, n)) if dist == 1 else rs.normal(0.0, 5.0, (R, n)) + b
+            a, b = a.astype(dt), b.astype(dt)
+            if R == 1:
+                a, b = a[0], b[0]
+            x = g.solve_raw(a, b, T, dist, rp, dtype=dt, levels=True, sweep=sweep)
+            y = eager.solve_raw(a, b, T, dist, rp, dtype=dt, levels=True, sweep=sweep)
+            for k in ("perm", "max_score", "next_start", "bounds", "subset_scores"):
+                assert np.array_equal(x[k], y[k]), (case, rep, n, T, dist, rp, dt.__name__, sweep, R, k)
