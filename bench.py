@@ -614,17 +614,26 @@ def main():
                 "columns": sorted(tab.keys()), "dtype": "f32",
                 "what": "device-side replica generation + rp and mcd scores for every T (8 reference solves per replica)"}
         # ---- the reference's own small configurations (BASELINE configs[0], [1]): latency of one host-buffer call
+        # (repeated solves of a shape are replayed from a CUDA graph; a context created with PS_NO_GRAPH=1 shows the eager call)
         small = {}
+        os.environ["PS_NO_GRAPH"] = "1"
+        try:
+            from partitionsolvers_b200 import capi as _capi
+            ctx_eager = _capi.Context(local_rank)
+        finally:
+            del os.environ["PS_NO_GRAPH"]
         for nm, dt_small in (("C1", np.float32), ("C2", np.float64)):
             c = synth.CONFIGS[nm]
             a_c, b_c = c["gen"](dt_small)
-            for _ in range(3):
-                ctx.solve_raw(a_c, b_c, c["T"], c["dist"], c["risk_part"], dtype=dt_small)
-            t0 = time.perf_counter()
-            for _ in range(20):
-                ctx.solve_raw(a_c, b_c, c["T"], c["dist"], c["risk_part"], dtype=dt_small)
-            small[nm] = {"n": c["n"], "T": c["T"], "dtype": np.dtype(dt_small).name,
-                         "ms_per_call_host_buffers": 1e3 * (time.perf_counter() - t0) / 20}
+            per = {}
+            for key, cx in (("ms_per_call_host_buffers", ctx), ("ms_per_call_eager_no_graph", ctx_eager)):
+                for _ in range(3):
+                    cx.solve_raw(a_c, b_c, c["T"], c["dist"], c["risk_part"], dtype=dt_small)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    cx.solve_raw(a_c, b_c, c["T"], c["dist"], c["risk_part"], dtype=dt_small)
+                per[key] = 1e3 * (time.perf_counter() - t0) / 20
+            small[nm] = {"n": c["n"], "T": c["T"], "dtype": np.dtype(dt_small).name, **per}
         line["small_configs"] = small
         # ---- OLS partition-size sweep (BASELINE configs[3], second half): one pass to level 64 serves every S = 1..64
         # (DP_impl.hpp:200-230), then the elbow regression (find_optimal_t); planted 4-level mixture as in
