@@ -82,3 +82,37 @@ def test_ols_single_sample_is_one(oracle):
         for sc in ([0.0, 3.0, 5.0], [0.0, 1.0, 1.5], [0.0, 2.0, 1.0]):
             sc = np.array(sc, dt)
             assert host.ols_num_clusters(sc, dt) == 1 and oracle.ols(sc, dtype=dt) == 1
+
+
+def test_poisson_risk_part_score_is_quasi_convex_along_a_row():
+    """The claim behind the range tiers of Poisson risk-partitioning (csrc/screen.cuh, ScreenUB<DIST_POISSON, true>::hull):
+    with the elements in ascending priority a/b, f(k) = A ln(A/B) over the range [i, k) falls, then rises, as k grows -- so
+    any k-range is bounded by the larger of its two end cells.  Checked here in extended precision on random data of the
+    kinds the engine sees (counts, null-model counts, real-valued), for many rows."""
+    rs = np.random.RandomState(77)
+    for kind in range(3):
+        n = 3000
+        if kind == 0:
+            b = rs.poisson(100, n).clip(1).astype(np.float64)
+            a = rs.poisson(np.repeat(rs.uniform(0.2, 2.5, 10), n // 10) * b).clip(1).astype(np.float64)
+        elif kind == 1:
+            b = rs.poisson(100, n).clip(1).astype(np.float64)
+            a = rs.poisson(b).clip(1).astype(np.float64)
+        else:
+            b = rs.uniform(1e-3, 10.0, n)
+            a = rs.uniform(1e-3, 10.0, n)
+        order = np.argsort(a / b, kind="stable")
+        a, b = a[order].astype(np.longdouble), b[order].astype(np.longdouble)
+        for i in rs.randint(0, n - 2, 60):
+            A = np.cumsum(a[i:])
+            B = np.cumsum(b[i:])
+            f = A * np.log(A / B)
+            d = np.diff(f)
+            tol = 1e-12 * np.maximum(np.abs(f[1:]), np.abs(f[:-1])) + 1e-15
+            rising = np.nonzero(d > tol)[0]
+            if rising.size:  # after the first rise nothing falls any more
+                assert not np.any(d[rising[0]:] < -tol[rising[0]:]), (kind, int(i))
+            # hence every k-range is bounded by its end cells
+            for lo, hi in ((0, len(f) - 1), (len(f) // 3, 2 * len(f) // 3)):
+                if hi > lo:
+                    assert f[lo:hi + 1].max() <= max(f[lo], f[hi]) + 1e-9 * max(abs(f[lo]), abs(f[hi]), 1.0)
