@@ -228,14 +228,27 @@ screen_lb_run_kernel(Geom g, const Rec4<double>* __restrict__ rec, float4* __res
 // =====================================================================================================================
 // Bound for every cell of a k-range of row i from the row's RUNNING sums (A, B) at the range's last cell k', the largest pm
 // of the range, span = number of additions between the range's first and last cell, len = k' - i.
-// Poisson risk-partitioning is bounded on the box instead (ScreenUB<DIST_POISSON, true>::box): (Af, Bf) are the row's running
-// sums at or before the range's first cell.  Adding a >= 0 / b >= 0 to a float never lowers it (rounding is monotone), so every
-// cell of the range has A in [Af, A] and B >= Bf exactly -- no sortedness, no span term; the box bound's own margins are the
-// cell bound's.
+// Poisson risk-partitioning, (Af, Bf) = the row's running sums at or before the range's first cell:
+//   * priorities not known to ascend: the box (ScreenUB<DIST_POISSON, true>::box).  Adding a >= 0 / b >= 0 to a float never
+//     lowers it (rounding is monotone), so every cell of the range has A in [Af, A] and B >= Bf exactly -- no span term;
+//   * ascending priorities (`sorted`): the larger END cell (screen.cuh: hull).  Continue the running sums from (Af, Bf) with the
+//     elements added EXACTLY: along that path f is quasi-convex whatever the starting ratio (the persistence step of the proof
+//     only needs r' >= r and q' between q and r), so it is bounded by its two ends.  The float path strays from it by at most
+//     m u relatively after m additions, and |df| <= m u A (|1 + ln q| + 1); the same at the far end.  Carried:
+//     2 span u A (max |ln q| + 2) on top of the cell bound's margins.  At span = 8 that is 2.4e-6 A where the box is loose by
+//     A dB/B ~ 1e-4 A.
 template <int DIST, bool RP>
-__device__ __forceinline__ float run32_range_ub(float Af, float Bf, float A, float B, float pm, float span, float len) {
+__device__ __forceinline__ float run32_range_ub(float Af, float Bf, float A, float B, float pm, float span, float len,
+                                                const bool sorted = false) {
   if constexpr (DIST == DIST_POISSON && RP) {
-    return ScreenUB<DIST_POISSON, true>::box(Af, Bf, A, pm);
+    if (!sorted) return ScreenUB<DIST_POISSON, true>::box(Af, Bf, A, pm);
+    const float l1 = lg2_approx(Af * rcp_approx(Bf)), l2 = lg2_approx(A * rcp_approx(B));
+    const float t1 = Af * l1, t2 = A * l2;
+    const float e1 = fmaf(fabsf(t1), 0.693147182464599609375f * 16.0f * SCR_U, t1 * 0.693147182464599609375f);
+    const float e2 = fmaf(fabsf(t2), 0.693147182464599609375f * 16.0f * SCR_U, t2 * 0.693147182464599609375f);
+    const float lq = fmaf(fmaxf(fabsf(l1), fabsf(l2)), 0.6931472f, 2.05f);  // max |ln q| + 2, a little more
+    const float stray = (2.02f * SCR_U * span) * (A * lq);
+    return fmaxf(e1, e2) + fmaf(A, SCR_CA, pm) + stray;
   } else if constexpr (DIST == DIST_GAUSSIAN && !RP) {
     // g = (A - B)^2 / (2B) for A > B, else 0.  Adding an element of priority r raises g whenever r >= (q + 1) / 2.  Along the
     // exact continuation of the running sums q <= r (1 + 2 gam), gam = 1.01 len u, so a decrease needs q < 1 + 4.1 gam, where
@@ -676,7 +689,7 @@ __device__ __forceinline__ void screen_run32_live_tile(const Geom& g, const int 
                                                        const float* __restrict__ SA, const float* __restrict__ SB,
                                                        const bool forced, const float* __restrict__ LB,
                                                        float* __restrict__ part_val, int* __restrict__ part_arg,
-                                                       unsigned long long* __restrict__ counters, const bool mono,
+                                                       unsigned long long* __restrict__ counters, const int mono,
                                                        float4 (*sbuf)[BR], float (*s_pmax)[BR / 32]) {
   using D = float;
   constexpr int BK = BR;
@@ -772,7 +785,7 @@ __device__ __forceinline__ void screen_run32_live_tile(const Geom& g, const int 
         float pmx = s_pmax[buf][0];
 #pragma unroll
         for (int w = 1; w < BR / 32; ++w) pmx = fmaxf(pmx, s_pmax[buf][w]);
-        const float ubs = run32_range_ub<DIST, RP>(S.x, S.y, E.x, E.y, pmx, (float)(BK + 8), (float)(kb + BK - 1 - i));
+        const float ubs = run32_range_ub<DIST, RP>(S.x, S.y, E.x, E.y, pmx, (float)(BK + 8), (float)(kb + BK - 1 - i), mono == 2);
         skip = !__any_sync(0xffffffffu, !(ubs < thr));
       }
       if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[skip ? 5 : 4], 1ULL);
@@ -794,7 +807,7 @@ __device__ __forceinline__ void screen_run32_live_tile(const Geom& g, const int 
           }
           if (mono) {
             const float ubg = run32_range_ub<DIST, RP>(W[0].x, W[0].y, W[U - 1].x, W[U - 1].y, sb[kk + U - 1].w, (float)U,
-                                                       (float)(kb + kk + U - 1 - i));
+                                                       (float)(kb + kk + U - 1 - i), mono == 2);
             const bool gdrop = !__any_sync(0xffffffffu, !(ubg < thr));
             if (AUDIT && counters && (tid & 31) == 0) atomicAdd(&counters[gdrop ? 7 : 6], 1ULL);
             if (gdrop) {
@@ -873,8 +886,10 @@ level_live_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
   __shared__ float4 sbuf[2][BR];
   __shared__ float s_pmax[2][BR / 32];
   __shared__ int s_next;
-  // the box bound (Poisson risk-part) holds in any element order; the others need the priorities ascending
-  const bool mono = (DIST == DIST_POISSON && RP) || (dev_flags && (dev_flags[1] == 0));
+  // range-tier mode: 0 none, 1 on, 2 on and the priorities ascend (Poisson risk-part: end-cell bound instead of the box, which
+  // holds in any element order); the other scores need the priorities ascending
+  const bool sorted = dev_flags && (dev_flags[1] == 0);
+  const int mono = (DIST == DIST_POISSON && RP) ? (sorted ? 2 : 1) : (sorted ? 1 : 0);
   const long long pstride = (long long)g.nch_alloc * g.nsub * g.n;
   const int tid = threadIdx.x;
   int cum[SCR_CLASSES];
@@ -902,7 +917,7 @@ level_live_screen_run32_kernel(Geom g, const Rec4<float>* __restrict__ rec, cons
     screen_run32_live_tile<DIST, RP, AUDIT, BR>(g, e.y, e.z, (unsigned int)e.w, rec + (long long)inst * g.rec_stride,
                                                 SA + inst * cp_stride, SB + inst * cp_stride, forced,
                                                 LB + (long long)inst * g.n, part_val + inst * pstride,
-                                                part_arg + inst * pstride, counters, mono && !forced, sbuf, s_pmax);
+                                                part_arg + inst * pstride, counters, forced ? 0 : mono, sbuf, s_pmax);
   }
 }
 

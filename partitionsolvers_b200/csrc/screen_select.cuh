@@ -159,7 +159,7 @@ screen_select_kernel(Geom g, const Rec4<D>* __restrict__ rec, const D* __restric
   auto range_ub = [&](const float Af, const float Bf, const float Al, const float Bl, const float pm, const int span,
                       const int k_last) -> float {
     if constexpr (SRC == SEL_RUN32)
-      return run32_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm, (float)(span + 8), (float)(k_last - i));
+      return run32_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm, (float)(span + 8), (float)(k_last - i), rmode == 2);
     else
       return screen_range_ub<DIST, RP>(Af, Bf, Al, Bl, pm, rmode);
   };
